@@ -1,0 +1,542 @@
+// acn_geom.h — packed scene view + ray/shape intersection, CSG evaluation and compound traversal.
+//
+// Host+device templates on the real type R.  On the device this is the intersection stage of the
+// wavefront tracer (R = float, or double in validation mode); on the host (R = double) it serves
+// scene construction only (Monte-Carlo envelope estimation, objects.c:312-363) — never rendering.
+//
+// Node table layout (one entry per compound_s / obj_*_s, indices instead of pointers):
+//   env [n]      R4  envelope centre xyz, radius              (objects.c:35-40)
+//   link[n]      I4  kind | flags<<8, a, b, material          a,b: CSG children, or compound child range
+//   geo [5n+0]   R4  pos.xyz, tail0
+//   geo [5n+1]   R4  rax.x (row), tail1
+//   geo [5n+2]   R4  rax.y (row), tail2
+//   geo [5n+3]   R4  rax.z (row), tail3
+//   geo [5n+4]   R4  surface_roughness, -, -, -
+// A sphere test touches env+link+geo0 = 48 B (f32); a plane adds geo3.
+#pragma once
+
+#include "acn_math.h"
+
+namespace acn {
+
+template <typename R> struct alignas( sizeof( R ) * 4 ) R4 { R x, y, z, w; };
+struct alignas( 16 ) I4 { int x, y, z, w; };
+
+enum
+{
+    K_COMPOUND = 0, K_PLANE = 1, K_SPHERE = 2, K_SQUAROID = 3, K_DIST_SPHERE = 4, K_DIST_TORUS = 5,
+    K_PAIR_INSIDE = 6, K_PAIR_OUTSIDE = 7, K_NEG = 8, K_SCALE = 9
+};
+enum { F_ENV = 1, F_ROUGH = 2 };
+enum { GEO_STRIDE = 5 };
+enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
+enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
+
+template <typename R> struct SceneView
+{
+    const R4<R>* env;
+    const I4*    link;
+    const R4<R>* geo;
+    const int*   children;
+    R   eps;            // shell thickness (f3_eps, vectors.h:33)
+    int light_root;
+    int matter_root;
+    int seed_mode;
+};
+
+template <typename R> struct Ray { V3<R> p, d; };
+
+// per-ray context: key of the ray in the ray tree (index-keyed roughness seeding)
+struct HitCtx { u64 key; };
+
+// trans_data_s (compound.h:31-36); -1 = no object
+template <typename R> struct Trans { V3<R> exit_nor; int exit_obj; int enter_obj; };
+
+template <typename R> ACN_HD V3<R> xyz( const R4<R>& v ) { return v3<R>( v.x, v.y, v.z ); }
+ACN_HD int node_kind( const I4& l )  { return l.x & 0xFF; }
+ACN_HD int node_flags( const I4& l ) { return l.x >> 8; }
+
+// ---------------------------------------------------------------------------------------------
+// sphere: sphere_ray_hit / sphere_observer_side (gmath.h:64-97) with the discriminant taken from the
+// rejection vector (r^2 - |p - (p.d)d|^2), which keeps FP32 accurate when |p| >> r.
+// ---------------------------------------------------------------------------------------------
+template <typename R> ACN_HD bool envelope_hits( const R4<R>& e, const Ray<R>& ray )                  // objects.c:90-93
+{
+    V3<R> p = ray.p - xyz( e );
+    R s = dot( p, ray.d );
+    R q = sqr( p ) - e.w * e.w;
+    V3<R> l = p - ray.d * s;
+    R disc = e.w * e.w - sqr( l );
+    return disc >= R( 0 ) && ( s < R( 0 ) || q < R( 0 ) );
+}
+
+template <typename R> ACN_HD R sphere_hit( V3<R> c, R r, const Ray<R>& ray, R eps, V3<R>* nor )
+{
+    V3<R> p = ray.p - c;
+    R s = dot( p, ray.d );
+    R q = sqr( p ) - r * r;
+    V3<R> l = p - ray.d * s;
+    R disc = r * r - sqr( l );
+    if( disc < R( 0 ) ) return Num<R>::inf();
+    R offs;
+    if( s < R( 0 ) && q > R( 0 ) )      offs = -s - r_sqrt( disc ) - eps;   // entry
+    else if( s < R( 0 ) || q < R( 0 ) ) offs = -s + r_sqrt( disc ) - eps;   // exit
+    else return Num<R>::inf();
+    if( nor ) *nor = unit( madd( p, ray.d, offs ) );
+    return offs;
+}
+
+template <typename R> ACN_HD int sphere_side( V3<R> c, R r, V3<R> pos ) { return sqr( pos - c ) > r * r ? 1 : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// distance functions (distance.c:39-42,83-92)
+// ---------------------------------------------------------------------------------------------
+template <typename R> ACN_HD R dist_fn( int kind, R ex_radius, V3<R> p )
+{
+    if( kind == K_DIST_SPHERE ) return r_sqrt( sqr( p ) ) - R( 1 );
+    R f = r_sqrt( p.x * p.x + p.y * p.y );
+    R fi = f > R( 0 ) ? R( 1 ) / f : R( 1 );
+    R x = p.x * fi - p.x, y = p.y * fi - p.y;
+    return r_sqrt( x * x + y * y + p.z * p.z ) - ex_radius;
+}
+
+template <typename R> ACN_HD M3<R> node_rax( const SceneView<R>& sv, int n )
+{
+    M3<R> m;
+    m.x = xyz( sv.geo[ n * GEO_STRIDE + 1 ] );
+    m.y = xyz( sv.geo[ n * GEO_STRIDE + 2 ] );
+    m.z = xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// primitives: fp_ray_hit of plane / sphere / squaroid / distance objects
+// (gmath.h:38-45, objects.c:529-537,649-657,778-821,903-959).  No envelope test, no roughness.
+// ---------------------------------------------------------------------------------------------
+template <typename R> ACN_HD R prim_hit( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, V3<R>* nor )
+{
+    const R inf = Num<R>::inf();
+    const R eps = sv.eps;
+    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
+    const V3<R> pos = xyz( g0 );
+
+    if( kind == K_SPHERE ) return sphere_hit( pos, g0.w, ray, eps, nor );
+
+    if( kind == K_PLANE )
+    {
+        V3<R> nz = xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
+        R div = dot( nz, ray.d );
+        if( div == R( 0 ) ) return inf;
+        R offs = dot( pos - ray.p, nz ) / div;
+        if( nor ) *nor = nz;
+        return offs > R( 0 ) ? offs - eps : inf;
+    }
+
+    const M3<R> rax = node_rax( sv, n );
+
+    if( kind == K_SQUAROID )
+    {
+        const R qa = g0.w;
+        const R qb = sv.geo[ n * GEO_STRIDE + 1 ].w;
+        const R qc = sv.geo[ n * GEO_STRIDE + 2 ].w;
+        const R qr = sv.geo[ n * GEO_STRIDE + 3 ].w;
+        V3<R> p = mlv( rax, ray.p - pos );
+        V3<R> d = mlv( rax, ray.d );
+        V3<R> ad = v3<R>( qa * d.x, qb * d.y, qc * d.z );
+        R f  = dot( ad, d );
+        R fs = dot( ad, p );
+        R fq = qa * p.x * p.x + qb * p.y * p.y + qc * p.z * p.z + qr;
+        R a;
+        if( f != R( 0 ) )
+        {
+            R fi = R( 1 ) / f;
+            R s = fs * fi, q = fq * fi;
+            R r = s * s - q;
+            if( r < R( 0 ) ) return inf;
+            r = r_sqrt( r );
+            a = -s - r;
+            if( a < R( 0 ) ) a = -s + r;
+            if( a < R( 0 ) ) return inf;
+        }
+        else
+        {
+            if( fq == R( 0 ) ) return inf;
+            a = -fs / ( R( 2 ) * fq );          // sic: objects.c:802
+        }
+        if( !( a < inf ) ) return inf;
+        if( nor )
+        {
+            V3<R> x = madd( p, d, a );
+            *nor = unit( tmlv( rax, v3<R>( x.x * qa, x.y * qb, x.z * qc ) ) );
+        }
+        return a - eps;
+    }
+
+    // distance-field objects: sphere tracing in the scaled object frame
+    {
+        const R inv_scale = g0.w;
+        const R ex_radius = sv.geo[ n * GEO_STRIDE + 1 ].w;
+        const int cycles  = ( int )sv.geo[ n * GEO_STRIDE + 2 ].w;
+        const I4 lk = sv.link[ n ];
+        Ray<R> rl = ray;
+        R offs0 = R( 0 );
+        if( node_flags( lk ) & F_ENV )
+        {
+            const R4<R> e = sv.env[ n ];
+            if( sphere_side( xyz( e ), e.w, ray.p ) == 1 )
+            {
+                offs0 = sphere_hit<R>( xyz( e ), e.w, ray, eps, nullptr );
+                if( !( offs0 < inf ) ) return inf;
+                rl.p = madd( ray.p, ray.d, offs0 );
+            }
+        }
+        V3<R> lp = mlv( rax, rl.p - pos ) * inv_scale;
+        V3<R> ld = mlv( rax, rl.d );
+        R offs1 = R( 0 );
+        R dist = dist_fn( kind, ex_radius, lp );
+        if( dist > R( 0 ) )
+        {
+            for( int i = 0; i < cycles; i++ )
+            {
+                offs1 += dist + eps;
+                dist = dist_fn( kind, ex_radius, madd( lp, ld, offs1 ) );
+                if( dist < R( 0 ) || dist > Num<R>::mag() ) break;
+            }
+        }
+        else
+        {
+            for( int i = 0; i < cycles; i++ )
+            {
+                offs1 -= dist - eps;
+                dist = dist_fn( kind, ex_radius, madd( lp, ld, offs1 ) );
+                if( dist > R( 0 ) || dist < -Num<R>::mag() ) break;
+            }
+        }
+        if( r_abs( dist ) <= eps )
+        {
+            if( nor )
+            {
+                V3<R> p = madd( lp, ld, offs1 );
+                R d0 = dist_fn( kind, ex_radius, p );
+                V3<R> g;
+                g.x = ( dist_fn( kind, ex_radius, v3<R>( p.x + eps, p.y, p.z ) ) - d0 ) / eps;
+                g.y = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y + eps, p.z ) ) - d0 ) / eps;
+                g.z = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y, p.z + eps ) ) - d0 ) / eps;
+                *nor = unit( tmlv( rax, g ) );
+            }
+            return offs0 + offs1 / inv_scale - eps;
+        }
+        return inf;
+    }
+}
+
+// fp_side of the primitives (gmath.h:52-55,93-97, objects.c:823-827,961-966)
+template <typename R> ACN_HD int prim_side( const SceneView<R>& sv, int kind, int n, V3<R> x )
+{
+    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
+    const V3<R> pos = xyz( g0 );
+    if( kind == K_SPHERE ) return sphere_side( pos, g0.w, x );
+    if( kind == K_PLANE )  return dot( x - pos, xyz( sv.geo[ n * GEO_STRIDE + 3 ] ) ) > R( 0 ) ? 1 : -1;
+    const M3<R> rax = node_rax( sv, n );
+    V3<R> p = mlv( rax, x - pos );
+    if( kind == K_SQUAROID )
+    {
+        R v = g0.w * p.x * p.x + sv.geo[ n * GEO_STRIDE + 1 ].w * p.y * p.y +
+              sv.geo[ n * GEO_STRIDE + 2 ].w * p.z * p.z + sv.geo[ n * GEO_STRIDE + 3 ].w;
+        return v > R( 0 ) ? 1 : -1;
+    }
+    return dist_fn( kind, sv.geo[ n * GEO_STRIDE + 1 ].w, p * g0.w ) > R( 0 ) ? 1 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// obj_ray_hit / obj_side (objects.c:261-284,365-370) over the whole object algebra.
+// CSG nodes recurse (device stack); the recursion depth is the CSG nesting depth.
+// ---------------------------------------------------------------------------------------------
+template <typename R> ACN_HDN int obj_side( const SceneView<R>& sv, int n, V3<R> x );
+template <typename R> ACN_HDN R   obj_ray_hit( const SceneView<R>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx );
+
+// roughness perturbation of the normal (objects.c:266-282)
+template <typename R> ACN_HD void roughen( const SceneView<R>& sv, int n, const Ray<R>& ray, R a, V3<R>* nor, HitCtx ctx )
+{
+    R rough = sv.geo[ n * GEO_STRIDE + 4 ].x;
+    u64 rv = sv.seed_mode == SEED_POSITION_HASH ? random_seed( madd( ray.p, ray.d, a ), ( u64 )1246 )
+                                                : mix64( mix64( ctx.key, KEY_ROUGH ), ( u64 )n );
+    V3<R> v = *nor;
+    R f;
+    f = rnd0<R>( &rv ) * R( 0.99 ); v.x += rough * r_log( ( R( 1 ) - f ) / ( R( 1 ) + f ) );
+    f = rnd0<R>( &rv ) * R( 0.99 ); v.y += rough * r_log( ( R( 1 ) - f ) / ( R( 1 ) + f ) );
+    f = rnd0<R>( &rv ) * R( 0.99 ); v.z += rough * r_log( ( R( 1 ) - f ) / ( R( 1 ) + f ) );
+    *nor = unit( v );
+}
+
+// A&B (want = -1) and A|B (want = +1): first boundary point of either child lying on the wanted
+// side of the other; alternating march with 2*eps steps (objects.c:1052-1094,1209-1251)
+template <typename R> ACN_HDN R pair_hit( const SceneView<R>& sv, int o1, int o2, int want, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+{
+    const R inf = Num<R>::inf();
+    V3<R> n1, n2;
+    R a1 = obj_ray_hit( sv, o1, ray, nor ? &n1 : nullptr, ctx );
+    R a2 = obj_ray_hit( sv, o2, ray, nor ? &n2 : nullptr, ctx );
+    if( a1 < a2 && obj_side( sv, o2, madd( ray.p, ray.d, a1 ) ) == want )
+    {
+        if( nor ) *nor = n1;
+        return a1;
+    }
+    if( !( a2 < inf ) ) return inf;
+    if( obj_side( sv, o1, madd( ray.p, ray.d, a2 ) ) == want )
+    {
+        if( nor ) *nor = n2;
+        return a2;
+    }
+    R offs = a2;
+    int cur = o1, other = o2;
+    Ray<R> r2; r2.d = ray.d;
+    for( int it = 0; it < CSG_MAX_STEPS && offs < inf; it++ )
+    {
+        r2.p = madd( ray.p, ray.d, offs );
+        R a = obj_ray_hit( sv, cur, r2, nor ? &n1 : nullptr, ctx );
+        if( !( a < inf ) ) return inf;
+        if( obj_side( sv, other, madd( r2.p, r2.d, a ) ) == want )
+        {
+            if( nor ) *nor = n1;
+            return offs + a;
+        }
+        offs += a + R( 2 ) * sv.eps;
+        int t = cur; cur = other; other = t;
+    }
+    return inf;
+}
+
+// fp_ray_hit dispatch without the own-envelope test and without roughness
+template <typename R> ACN_HD R shape_hit( const SceneView<R>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+{
+    const int kind = node_kind( lk );
+    if( kind <= K_DIST_TORUS ) return prim_hit( sv, kind, n, ray, nor );
+    if( kind == K_PAIR_INSIDE )  return pair_hit( sv, lk.y, lk.z, -1, ray, nor, ctx );
+    if( kind == K_PAIR_OUTSIDE ) return pair_hit( sv, lk.y, lk.z, +1, ray, nor, ctx );
+    if( kind == K_NEG )                                                                  // objects.c:1329-1339
+    {
+        R a = obj_ray_hit( sv, lk.y, ray, nor, ctx );
+        if( a < Num<R>::inf() && nor ) *nor = -( *nor );
+        return a;
+    }
+    // K_SCALE (objects.c:1418-1437)
+    {
+        const V3<R> pos = xyz( sv.geo[ n * GEO_STRIDE ] );
+        const M3<R> rax = node_rax( sv, n );
+        const V3<R> inv = v3<R>( sv.geo[ n * GEO_STRIDE ].w, sv.geo[ n * GEO_STRIDE + 1 ].w, sv.geo[ n * GEO_STRIDE + 2 ].w );
+        Ray<R> rl;
+        rl.p = mul( mlv( rax, ray.p - pos ), inv );
+        rl.d = mul( mlv( rax, ray.d ), inv );
+        R len = r_sqrt( sqr( rl.d ) );
+        R fac = len > R( 0 ) ? R( 1 ) / len : R( 0 );
+        rl.d = rl.d * fac;
+        V3<R> n1;
+        R a1 = obj_ray_hit( sv, lk.y, rl, nor ? &n1 : nullptr, ctx ) + sv.eps;
+        if( a1 < Num<R>::inf() )
+        {
+            if( nor ) *nor = unit( tmlv( rax, mul( n1, inv ) ) );
+            return a1 * fac - sv.eps;
+        }
+        return Num<R>::inf();
+    }
+}
+
+// obj_ray_hit body after the envelope test: shape + roughness
+template <typename R> ACN_HD R obj_hit_noenv( const SceneView<R>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+{
+    R a = shape_hit( sv, lk, n, ray, nor, ctx );
+    if( nor && ( node_flags( lk ) & F_ROUGH ) && a < Num<R>::inf() ) roughen( sv, n, ray, a, nor, ctx );
+    return a;
+}
+
+template <typename R> ACN_HDN R obj_ray_hit( const SceneView<R>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+{
+    const I4 lk = sv.link[ n ];
+    if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ n ], ray ) ) return Num<R>::inf();
+    return obj_hit_noenv( sv, lk, n, ray, nor, ctx );
+}
+
+// obj_side (objects.c:365-370): "outside" whenever outside the own envelope — also for negations
+template <typename R> ACN_HDN int obj_side( const SceneView<R>& sv, int n, V3<R> x )
+{
+    const I4 lk = sv.link[ n ];
+    if( node_flags( lk ) & F_ENV )
+    {
+        const R4<R> e = sv.env[ n ];
+        if( sphere_side( xyz( e ), e.w, x ) == 1 ) return 1;
+    }
+    const int kind = node_kind( lk );
+    if( kind <= K_DIST_TORUS ) return prim_side( sv, kind, n, x );
+    if( kind == K_PAIR_INSIDE )  return ( obj_side( sv, lk.y, x ) + obj_side( sv, lk.z, x ) == -2 ) ? -1 : 1;   // objects.c:1096-1099
+    if( kind == K_PAIR_OUTSIDE ) return ( obj_side( sv, lk.y, x ) + obj_side( sv, lk.z, x ) ==  2 ) ? 1 : -1;   // objects.c:1253-1256
+    if( kind == K_NEG ) return -obj_side( sv, lk.y, x );                                                        // objects.c:1341-1344
+    {                                                                                                           // objects.c:1439-1443
+        const V3<R> pos = xyz( sv.geo[ n * GEO_STRIDE ] );
+        const M3<R> rax = node_rax( sv, n );
+        const V3<R> inv = v3<R>( sv.geo[ n * GEO_STRIDE ].w, sv.geo[ n * GEO_STRIDE + 1 ].w, sv.geo[ n * GEO_STRIDE + 2 ].w );
+        return obj_side( sv, lk.y, mul( mlv( rax, x - pos ), inv ) );
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compound_s_ray_hit (compound.c:215-244): closest hit over a tree of compounds.  The recursion of
+// the reference becomes an explicit stack of child ranges; a single running minimum with strict
+// '<' selects the same element as the nested minima do (first in depth-first order wins ties).
+//   t_any: a hit with a <= t_any ends the search at once — exact for the shadow test, which only
+//          consumes (min > a) (scene.c:569); pass -inf for a full closest-hit search.
+// ---------------------------------------------------------------------------------------------
+template <typename R> ACN_HD R compound_ray_hit( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, int* hit_obj, HitCtx ctx, R t_any )
+{
+    const R inf = Num<R>::inf();
+    const I4 rl = sv.link[ root ];
+    if( ( node_flags( rl ) & F_ENV ) && !envelope_hits( sv.env[ root ], ray ) ) return inf;
+    int sb[ COMPOUND_STACK ], se[ COMPOUND_STACK ];
+    int sp = 0;
+    int beg = rl.y, end = rl.y + rl.z;
+    R min_a = inf;
+    V3<R> n;
+    for( ;; )
+    {
+        while( beg < end )
+        {
+            const int c = sv.children[ beg++ ];
+            const I4 lk = sv.link[ c ];
+            if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ c ], ray ) ) continue;
+            if( node_kind( lk ) == K_COMPOUND )
+            {
+                if( sp < COMPOUND_STACK ) { sb[ sp ] = beg; se[ sp ] = end; sp++; beg = lk.y; end = lk.y + lk.z; }
+                continue;
+            }
+            R a = obj_hit_noenv( sv, lk, c, ray, nor ? &n : nullptr, ctx );
+            if( a < min_a )
+            {
+                min_a = a;
+                if( nor ) *nor = n;
+                if( hit_obj ) *hit_obj = c;
+                if( a <= t_any ) return a;
+            }
+        }
+        if( sp == 0 ) break;
+        sp--; beg = sb[ sp ]; end = se[ sp ];
+    }
+    return min_a;
+}
+
+// compound_s_ray_trans_hit (compound.c:246-299): closest hit over the elements of a root compound
+// with the eps-merge of coincident surfaces into one (exit_obj, enter_obj) transition.
+template <typename R> ACN_HD R compound_trans_hit( const SceneView<R>& sv, int root, const Ray<R>& ray, Trans<R>* trans, HitCtx ctx )
+{
+    const R inf = Num<R>::inf();
+    const I4 rl = sv.link[ root ];
+    if( ( node_flags( rl ) & F_ENV ) && !envelope_hits( sv.env[ root ], ray ) ) return inf;
+    R min_a = inf;
+    for( int i = rl.y; i < rl.y + rl.z; i++ )
+    {
+        const int c = sv.children[ i ];
+        const I4 lk = sv.link[ c ];
+        V3<R> nor;
+        int hit_obj = c;
+        R a;
+        if( node_kind( lk ) == K_COMPOUND )
+        {
+            hit_obj = -1;
+            a = compound_ray_hit( sv, c, ray, &nor, &hit_obj, ctx, -inf );
+        }
+        else
+        {
+            if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ c ], ray ) ) continue;
+            a = obj_hit_noenv( sv, lk, c, ray, &nor, ctx );
+        }
+        if( a < inf )
+        {
+            if( a < min_a - sv.eps )
+            {
+                min_a = a;
+                if( dot( nor, ray.d ) > R( 0 ) ) { trans->exit_nor = nor;  trans->exit_obj = hit_obj; trans->enter_obj = -1; }
+                else                             { trans->exit_nor = -nor; trans->exit_obj = -1;      trans->enter_obj = hit_obj; }
+            }
+            else if( r_abs( a - min_a ) < sv.eps )
+            {
+                min_a = a < min_a ? a : min_a;
+                if( dot( nor, ray.d ) > R( 0 ) ) trans->exit_obj = hit_obj;
+                else                             trans->enter_obj = hit_obj;
+            }
+        }
+    }
+    return min_a;
+}
+
+// scene_s_trans_hit (scene.c:362-382): lights first, then matter, strictly smaller wins
+template <typename R> ACN_HD R scene_trans_hit( const SceneView<R>& sv, const Ray<R>& ray, Trans<R>* trans, HitCtx ctx )
+{
+    R min_a = Num<R>::inf();
+    Trans<R> tl;
+    tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( 0, 0, 0 );
+    R a = compound_trans_hit( sv, sv.light_root, ray, &tl, ctx );
+    if( a < min_a ) { min_a = a; *trans = tl; }
+    a = compound_trans_hit( sv, sv.matter_root, ray, &tl, ctx );
+    if( a < min_a ) { min_a = a; *trans = tl; }
+    return min_a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// obj_fov (objects.c:254-259): cone from pos that contains the whole light.
+// sphere objects.c:619-637; plane :520-527; pairs :1035-1044,1192-1201 (envelope_s_fov :70-88)
+// returns false for shapes without a fov function (rejected at upload for lights)
+// ---------------------------------------------------------------------------------------------
+template <typename R> ACN_HD bool obj_fov( const SceneView<R>& sv, int n, V3<R> pos, V3<R>* axis, R* cos_rs )
+{
+    const I4 lk = sv.link[ n ];
+    const int kind = node_kind( lk );
+    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
+    if( kind == K_SPHERE || ( ( kind == K_PAIR_INSIDE || kind == K_PAIR_OUTSIDE ) && ( node_flags( lk ) & F_ENV ) ) )
+    {
+        V3<R> c; R r;
+        if( kind == K_SPHERE ) { c = xyz( g0 ); r = g0.w; }
+        else { const R4<R> e = sv.env[ n ]; c = xyz( e ); r = e.w; }
+        V3<R> diff = c - pos;
+        R d2 = sqr( diff ), r2 = r * r;
+        *axis = unit( diff );
+        *cos_rs = d2 > r2 ? r_sqrt( R( 1 ) - r2 / d2 ) : R( -1 );
+        return true;
+    }
+    if( kind == K_PLANE )
+    {
+        V3<R> d = -xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
+        *axis = d;
+        *cos_rs = dot( xyz( g0 ) - pos, d ) > R( 0 ) ? R( 0 ) : R( 1 );
+        return true;
+    }
+    if( kind == K_PAIR_INSIDE || kind == K_PAIR_OUTSIDE )
+    {
+        *axis = unit( xyz( g0 ) - pos );
+        *cos_rs = R( 0 );
+        return true;
+    }
+    return false;
+}
+
+// obj_projection for the chess texture (objects.c:514-518,602-617,892-895)
+template <typename R> ACN_HD void obj_projection( const SceneView<R>& sv, int n, V3<R> pos, R* u, R* v )
+{
+    const int kind = node_kind( sv.link[ n ] );
+    const V3<R> c = xyz( sv.geo[ n * GEO_STRIDE ] );
+    const M3<R> rax = node_rax( sv, n );
+    if( kind == K_PLANE )
+    {
+        V3<R> p = pos - c;
+        *u = dot( p, rax.x ); *v = dot( p, rax.y );
+    }
+    else if( kind == K_SPHERE )
+    {
+        V3<R> r = unit( pos - c );
+        R x = dot( r, rax.x );
+        R y = dot( r, cross( rax.z, rax.x ) );
+        R z = r_min( r_max( dot( r, rax.z ), R( -1 ) ), R( 1 ) );
+        *u = r_atan2( x, y ); *v = r_asin( z );
+    }
+    else { *u = R( 0 ); *v = R( 0 ); }
+}
+
+} // namespace acn

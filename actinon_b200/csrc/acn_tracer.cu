@@ -1,0 +1,230 @@
+// acn_tracer.cu — C ABI of the device tracer (see include/actinon_b200.h) and the FP32 peak probe.
+// There is deliberately no CPU rendering path in this library: without a CUDA device every
+// tracer entry point fails with ACN_ERR_NO_DEVICE.
+#include "acn_tracer.cuh"
+
+#include <stdarg.h>
+#include <mutex>
+
+namespace acn {
+
+static thread_local char g_error[ 1024 ] = "";
+
+void set_error( const char* fmt, ... )
+{
+    va_list ap;
+    va_start( ap, fmt );
+    vsnprintf( g_error, sizeof( g_error ), fmt, ap );
+    va_end( ap );
+}
+
+int validate_flat_scene( const acn_flat_scene* fs )
+{
+    if( !fs || !fs->nodes || fs->n_nodes <= 0 ) { set_error( "flat scene: no nodes" ); return ACN_ERR_BAD_SCENE; }
+    if( fs->n_children < 0 || ( fs->n_children > 0 && !fs->children ) ) { set_error( "flat scene: bad child list" ); return ACN_ERR_BAD_SCENE; }
+    if( fs->n_materials < 0 || ( fs->n_materials > 0 && !fs->materials ) ) { set_error( "flat scene: bad material list" ); return ACN_ERR_BAD_SCENE; }
+    const int n = fs->n_nodes;
+    auto node_ok = [ & ]( int i ) { return i >= 0 && i < n; };
+    if( !node_ok( fs->light_root ) || !node_ok( fs->matter_root ) ||
+        fs->nodes[ fs->light_root ].kind != ACN_KIND_COMPOUND || fs->nodes[ fs->matter_root ].kind != ACN_KIND_COMPOUND )
+    {
+        set_error( "flat scene: light_root/matter_root must be compound nodes" ); return ACN_ERR_BAD_SCENE;
+    }
+    for( int i = 0; i < n; i++ )
+    {
+        const acn_flat_node& nd = fs->nodes[ i ];
+        if( nd.kind < 0 || nd.kind >= ACN_KIND_COUNT ) { set_error( "flat scene: node %d has unknown kind %d", i, nd.kind ); return ACN_ERR_BAD_SCENE; }
+        if( nd.kind == ACN_KIND_COMPOUND )
+        {
+            if( nd.child1 < 0 || nd.child0 < 0 || ( long long )nd.child0 + nd.child1 > fs->n_children )
+            { set_error( "flat scene: compound %d child range out of bounds", i ); return ACN_ERR_BAD_SCENE; }
+            for( int k = 0; k < nd.child1; k++ )
+            {
+                int c = fs->children[ nd.child0 + k ];
+                if( !node_ok( c ) || c == i ) { set_error( "flat scene: compound %d has bad child %d", i, c ); return ACN_ERR_BAD_SCENE; }
+            }
+        }
+        else
+        {
+            if( nd.material < 0 || nd.material >= fs->n_materials ) { set_error( "flat scene: node %d has bad material %d", i, nd.material ); return ACN_ERR_BAD_SCENE; }
+            const bool pair = nd.kind == ACN_KIND_PAIR_INSIDE || nd.kind == ACN_KIND_PAIR_OUTSIDE;
+            const bool unary = nd.kind == ACN_KIND_NEG || nd.kind == ACN_KIND_SCALE;
+            if( ( pair || unary ) && ( !node_ok( nd.child0 ) || nd.child0 == i || fs->nodes[ nd.child0 ].kind == ACN_KIND_COMPOUND ) )
+            { set_error( "flat scene: node %d has bad child0 %d", i, nd.child0 ); return ACN_ERR_BAD_SCENE; }
+            if( pair && ( !node_ok( nd.child1 ) || nd.child1 == i || fs->nodes[ nd.child1 ].kind == ACN_KIND_COMPOUND ) )
+            { set_error( "flat scene: node %d has bad child1 %d", i, nd.child1 ); return ACN_ERR_BAD_SCENE; }
+            if( ( nd.kind == ACN_KIND_DIST_SPHERE || nd.kind == ACN_KIND_DIST_TORUS ) && !( nd.tail[ 0 ] != 0 ) )
+            { set_error( "flat scene: distance object %d has inv_scale 0", i ); return ACN_ERR_BAD_SCENE; }
+        }
+    }
+    if( compound_depth( fs, fs->light_root, 0 ) > COMPOUND_STACK || compound_depth( fs, fs->matter_root, 0 ) > COMPOUND_STACK )
+    { set_error( "flat scene: compounds nested deeper than %d", ( int )COMPOUND_STACK ); return ACN_ERR_BAD_SCENE; }
+    if( csg_depth( fs, fs->light_root, 0 ) >= 64 || csg_depth( fs, fs->matter_root, 0 ) >= 64 )
+    { set_error( "flat scene: CSG nesting deeper than 63 (or cyclic)" ); return ACN_ERR_BAD_SCENE; }
+    const acn_flat_params& p = fs->params;
+    if( p.image_width <= 0 || p.image_height <= 1 ) { set_error( "flat scene: bad image size %dx%d", p.image_width, p.image_height ); return ACN_ERR_BAD_SCENE; }
+    if( p.direct_samples < 0 || p.path_samples < 0 || p.trace_depth < 0 ) { set_error( "flat scene: negative sample counts / depth" ); return ACN_ERR_BAD_SCENE; }
+    return ACN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 peak probe: 8 independent FFMA chains per thread, every SM saturated
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__( 256 ) k_fma_peak( float* out, int iters, float a, float b )
+{
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for( int i = 0; i < iters; i++ )
+    {
+        #pragma unroll
+        for( int u = 0; u < 16; u++ )
+        {
+            x0 = fmaf( x0, a, b ); x1 = fmaf( x1, a, b ); x2 = fmaf( x2, a, b ); x3 = fmaf( x3, a, b );
+            x4 = fmaf( x4, a, b ); x5 = fmaf( x5, a, b ); x6 = fmaf( x6, a, b ); x7 = fmaf( x7, a, b );
+        }
+    }
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if( s == 123.456f ) out[ 0 ] = s;
+}
+
+} // namespace acn
+
+using namespace acn;
+
+extern "C" {
+
+const char* acn_last_error( void ) { return g_error; }
+const char* acn_version( void ) { return "actinon_b200 0.1 (sm_100a wavefront tracer)"; }
+
+void acn_options_default( acn_options* opt )
+{
+    if( !opt ) return;
+    memset( opt, 0, sizeof( *opt ) );
+    opt->seed_mode = ACN_SEED_POSITION_HASH;
+    opt->precision = ACN_PRECISION_F32;
+    opt->eps = 0;
+    opt->wave_budget = 0;
+    opt->device = -1;
+}
+
+int acn_device_count( void )
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount( &n );
+    if( e != cudaSuccess || n <= 0 )
+    {
+        set_error( "no CUDA device: %s (this library has no CPU rendering path)", cudaGetErrorString( e ) );
+        cudaGetLastError();
+        return ACN_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+int acn_tracer_create( const acn_flat_scene* scene, const acn_options* opt, acn_tracer** out )
+{
+    if( !scene || !out ) { set_error( "acn_tracer_create: null argument" ); return ACN_ERR_INVALID_ARG; }
+    *out = nullptr;
+    acn_options o;
+    if( opt ) o = *opt; else acn_options_default( &o );
+    int rc = validate_flat_scene( scene );
+    if( rc ) return rc;
+    int nd = acn_device_count();
+    if( nd < 0 ) return nd;
+    int dev = o.device;
+    if( dev < 0 ) { if( cudaGetDevice( &dev ) != cudaSuccess ) dev = 0; }
+    if( dev >= nd ) { set_error( "device %d out of range (%d devices)", dev, nd ); return ACN_ERR_INVALID_ARG; }
+    TracerBase* t = nullptr;
+    if( o.precision == ACN_PRECISION_F64 )
+    {
+        Tracer<double>* tr = new Tracer<double>(); tr->device = dev; rc = tr->init( scene, &o ); t = tr;
+    }
+    else
+    {
+        Tracer<float>* tr = new Tracer<float>(); tr->device = dev; rc = tr->init( scene, &o ); t = tr;
+    }
+    if( rc ) { delete t; return rc; }
+    *out = reinterpret_cast<acn_tracer*>( t );
+    return ACN_OK;
+}
+
+void acn_tracer_destroy( acn_tracer* t )
+{
+    if( t ) delete reinterpret_cast<TracerBase*>( t );
+}
+
+int acn_render_samples_device( acn_tracer* t, const double* d_xy, uint64_t n, uint64_t index_base,
+                               float* d_rgb, void* stream, const volatile int* cancel, acn_stats* stats )
+{
+    if( !t || ( n && ( !d_xy || !d_rgb ) ) ) { set_error( "acn_render_samples_device: null argument" ); return ACN_ERR_INVALID_ARG; }
+    TracerBase* tb = reinterpret_cast<TracerBase*>( t );
+    cudaStream_t st = stream ? ( cudaStream_t )stream : tb->own_stream;
+    return tb->render( d_xy, n, index_base, d_rgb, st, cancel, stats );
+}
+
+int acn_render_samples( acn_tracer* t, const double* xy, uint64_t n, uint64_t index_base,
+                        float* rgb, const volatile int* cancel, acn_stats* stats )
+{
+    if( !t || ( n && ( !xy || !rgb ) ) ) { set_error( "acn_render_samples: null argument" ); return ACN_ERR_INVALID_ARG; }
+    TracerBase* tb = reinterpret_cast<TracerBase*>( t );
+    if( n == 0 ) { if( stats ) memset( stats, 0, sizeof( *stats ) ); return ACN_OK; }
+    ACN_CUDA( cudaSetDevice( tb->device ) );
+    if( tb->stage_cap < n )
+    {
+        cudaFree( tb->d_xy_stage ); cudaFree( tb->d_rgb_stage ); tb->d_xy_stage = nullptr; tb->d_rgb_stage = nullptr; tb->stage_cap = 0;
+        int rc;
+        if( ( rc = dev_alloc( &tb->d_xy_stage, ( size_t )n * 2 ) ) ) return rc;
+        if( ( rc = dev_alloc( &tb->d_rgb_stage, ( size_t )n * 3 ) ) ) return rc;
+        tb->stage_cap = n;
+    }
+    cudaStream_t st = tb->own_stream;
+    ACN_CUDA( cudaMemcpyAsync( tb->d_xy_stage, xy, ( size_t )n * 2 * sizeof( double ), cudaMemcpyHostToDevice, st ) );
+    int rc = tb->render( tb->d_xy_stage, n, index_base, tb->d_rgb_stage, st, cancel, stats );
+    if( rc ) return rc;
+    ACN_CUDA( cudaMemcpyAsync( rgb, tb->d_rgb_stage, ( size_t )n * 3 * sizeof( float ), cudaMemcpyDeviceToHost, st ) );
+    ACN_CUDA( cudaStreamSynchronize( st ) );
+    return ACN_OK;
+}
+
+int acn_accumulate_device( acn_tracer* t, const double* d_xy, const float* d_rgb, uint64_t n, float* d_accum, void* stream )
+{
+    if( !t || ( n && ( !d_xy || !d_rgb || !d_accum ) ) ) { set_error( "acn_accumulate_device: null argument" ); return ACN_ERR_INVALID_ARG; }
+    TracerBase* tb = reinterpret_cast<TracerBase*>( t );
+    if( n == 0 ) return ACN_OK;
+    ACN_CUDA( cudaSetDevice( tb->device ) );
+    cudaStream_t st = stream ? ( cudaStream_t )stream : tb->own_stream;
+    k_accumulate<<< grid_for( n, 256 ), 256, 0, st >>>( d_xy, d_rgb, n, tb->width, tb->height, d_accum );
+    ACN_CUDA( cudaGetLastError() );
+    if( !stream ) ACN_CUDA( cudaStreamSynchronize( st ) );
+    return ACN_OK;
+}
+
+double acn_measure_fp32_peak_tflops( int device )
+{
+    int nd = acn_device_count();
+    if( nd < 0 ) return ( double )nd;
+    if( device < 0 ) { if( cudaGetDevice( &device ) != cudaSuccess ) device = 0; }
+    if( cudaSetDevice( device ) != cudaSuccess ) return ( double )ACN_ERR_CUDA;
+    cudaDeviceProp pr;
+    if( cudaGetDeviceProperties( &pr, device ) != cudaSuccess ) return ( double )ACN_ERR_CUDA;
+    float* d = nullptr;
+    if( cudaMalloc( &d, 256 ) != cudaSuccess ) return ( double )ACN_ERR_OUT_OF_MEMORY;
+    const int blocks = pr.multiProcessorCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1; cudaEventCreate( &e0 ); cudaEventCreate( &e1 );
+    k_fma_peak<<< blocks, threads >>>( d, 64, 0.999f, 0.001f );       // warm-up
+    double best = 0;
+    for( int rep = 0; rep < 5; rep++ )
+    {
+        cudaEventRecord( e0 );
+        k_fma_peak<<< blocks, threads >>>( d, iters, 0.999f, 0.001f );
+        cudaEventRecord( e1 );
+        cudaEventSynchronize( e1 );
+        float ms = 0; cudaEventElapsedTime( &ms, e0, e1 );
+        double flops = 2.0 * 8 * 16 * ( double )iters * blocks * threads;
+        double tf = flops / ( ms * 1e-3 ) / 1e12;
+        if( tf > best ) best = tf;
+    }
+    cudaEventDestroy( e0 ); cudaEventDestroy( e1 ); cudaFree( d );
+    if( cudaGetLastError() != cudaSuccess ) return ( double )ACN_ERR_CUDA;
+    return best;
+}
+
+} // extern "C"

@@ -1,0 +1,1094 @@
+// acn_tracer.cuh — wavefront sample tracer for sm_100a (templated on the real type).
+//
+// Replaces lum_machine_s_func + scene_s_lum (reference src/scene.c:420-667,956-1013): the
+// reference's recursive, branching ray tree becomes three kinds of device work items
+//
+//   explicit rays   primary (generated from the camera in-kernel), Fresnel-reflection, chromatic
+//                   and refraction rays — SoA queue, 64 B/ray in f32
+//   tasks           diffuse hits (position, normal, Oren-Nayar terms, RGB throughput, RNG state,
+//                   sample counts) — 104 B/task; their direct_samples*lights shadow rays and
+//                   path_samples indirect rays are never materialised: lane i of a warp
+//                   regenerates child i from (task, i) with an O(1) LCG skip-ahead table
+//   contributions   atomically added to a per-sample RGB accumulator; gamma + clamp at the end
+//
+// All of scene_s_lum is linear in its children, so colour products and exit absorption fold into
+// a per-ray RGB throughput; the scalar intensity is carried separately because it drives sample
+// counts and termination (scene.c:428,553,593).
+//
+// Scheduling is depth-first in bulk: a wave pops at most `budget` work items from the top of the
+// ray stack (or tasks worth at most `budget` path children), and everything it spawns lands on
+// top, so the memory in flight stays bounded however large ds*ps*ps gets.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <string>
+
+#include "acn_geom.h"
+#include "../../include/actinon_b200.h"
+
+namespace acn {
+
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------
+// device-side scene tables
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct DMat
+{
+    R   color[ 3 ];
+    R   radiance;
+    R   refr;
+    R   fresnel01;      // (fresnel_reflectivity != 0 && n != 1) ? 1 : 0      scene.c:451
+    R   chroma;
+    R   diffuse;
+    R   on_a, on_b;     // scene.c:455-461
+    R   transp[ 3 ];
+    R   tex1[ 3 ], tex2[ 3 ], tex_scale;
+    int transparent;    // |transparency|^2 > 0                               scene.c:454
+    int tex_kind;
+};
+
+template <typename R> struct DLight
+{
+    int node;
+    R   pos[ 3 ];       // prp.pos of the light
+    R   color[ 3 ];     // obj_color( light, light.pos )                       scene.c:552
+    R   radiance;
+};
+
+template <typename R> struct DParams
+{
+    SceneView<R> sv;
+    const DMat<R>*   mats;
+    const DLight<R>* lights;
+    int   n_lights;
+    int   n_nodes, n_children;
+    int   width, height;
+    R     gamma;
+    V3<R> background;
+    V3<R> cam_pos, cam_rx, cam_ry, cam_rz;   // camera_rotation columns (scene.c:963-973)
+    R     focal;
+    int   trace_depth;
+    int   direct_samples, path_samples;
+    R     min_intensity;
+    R     max_path_length;
+    int   stage_bytes;                        // node table bytes staged into shared memory (0: none)
+    const u64* skipA;                         // LCG skip table: state after 2k steps = s*A[k] + C[k]
+    const u64* skipC;
+    int   skip_n;
+};
+
+// ---------------------------------------------------------------------------------------------
+// work-item storage
+// ---------------------------------------------------------------------------------------------
+enum { RC_PRIMARY = 0, RC_REFLECT = 1, RC_CHROMATIC = 2, RC_REFRACT = 3, RC_PATH = 4 };
+enum { RAYF_PROBE = 1 << 16 };     // child whose shading would return 0: only "hit anything?" matters
+
+template <typename R> struct RayBuf     // SoA
+{
+    R4<R>* o_i;     // origin.xyz, intensity
+    R4<R>* d_;      // dir.xyz, -
+    R4<R>* tp;      // throughput rgb, -
+    I4*    meta;    // depth | class<<8 | flags, sample, key lo, key hi
+};
+
+template <typename R> struct TaskBuf    // SoA
+{
+    R4<R>* pos_id;    // pos.xyz, diffuse_intensity
+    R4<R>* nrm_ci;    // surface.d (= -exit_nor), cos(theta_i)
+    R4<R>* prj_a;     // ray projection, on_a
+    R4<R>* tpc_b;     // throughput * surface colour, on_b
+    I4*    meta;      // sample, depth, n_direct, n_path
+    u64*   rv0;       // RNG state at the hit (scene.c:537)
+    u64*   key;       // ray-tree key (index-keyed seeding)
+    u64*   cum;       // inclusive running sum of n_path on the task stack
+};
+
+enum
+{
+    ST_PRIMARY = 0, ST_REFLECT, ST_CHROMATIC, ST_REFRACT, ST_PATH, ST_SHADOW, ST_LIGHT, ST_DIFFUSE, ST_COUNT
+};
+
+struct Counters
+{
+    unsigned long long rays_out;        // rays appended to the ray stack
+    unsigned long long tasks_new;       // tasks appended to the new-task scratch
+    unsigned long long tasks_new_path;  // of those, tasks with n_path > 0
+    unsigned long long task_stack;      // packed: count << 38 | sum n_path
+    unsigned long long stats[ ST_COUNT ];
+    unsigned long long plan_start;      // k_plan output
+    unsigned long long plan_cum;
+    int overflow;
+    int pad;
+};
+
+#define ACN_TASK_SHIFT 38
+#define ACN_TASK_MASK  ( ( 1ull << ACN_TASK_SHIFT ) - 1 )
+
+template <typename R> struct Wave       // everything a kernel needs
+{
+    DParams<R>  prm;
+    RayBuf<R>   rays_out;     // ray stack (append at rays_out_base + counter)
+    TaskBuf<R>  tasks_out;    // new-task scratch
+    Counters*   ctr;
+    R*          accum;        // per-sample RGB, 3 per sample (relative to sample_base)
+    unsigned long long rays_out_base, rays_cap;
+    unsigned long long tasks_cap;
+    unsigned long long sample_base;   // first sample index of this render call's chunk (for accum addressing)
+    u64         index_base;   // global index of sample 0 (index-keyed seeding)
+};
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float atomic_add_r( float* p, float v )   { return atomicAdd( p, v ); }
+__device__ __forceinline__ double atomic_add_r( double* p, double v ) { return atomicAdd( p, v ); }
+
+// warp-aggregated counter increment: one atomic per converged group
+__device__ __forceinline__ unsigned long long agg_inc( unsigned long long* ctr )
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if( g.thread_rank() == 0 ) base = atomicAdd( ctr, ( unsigned long long )g.size() );
+    return g.shfl( base, 0 ) + g.thread_rank();
+}
+
+__device__ __forceinline__ void agg_count( unsigned long long* ctr )
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    if( g.thread_rank() == 0 ) atomicAdd( ctr, ( unsigned long long )g.size() );
+}
+
+template <typename R> __device__ __forceinline__ void add_sample( const Wave<R>& w, int sample, V3<R> c )
+{
+    R* a = w.accum + 3ull * ( unsigned long long )sample;
+    atomic_add_r( a + 0, c.x );
+    atomic_add_r( a + 1, c.y );
+    atomic_add_r( a + 2, c.z );
+}
+
+// stage the node table into shared memory when it fits (C1/C2/C4: a few KB); big scenes stay in L2
+template <typename R> __device__ __forceinline__ void stage_scene( DParams<R>& prm, unsigned char* smem )
+{
+    if( prm.stage_bytes <= 0 ) return;
+    const int n = prm.n_nodes;
+    R4<R>* s_env  = reinterpret_cast<R4<R>*>( smem );
+    R4<R>* s_geo  = s_env + n;
+    I4*    s_link = reinterpret_cast<I4*>( s_geo + n * GEO_STRIDE );
+    int*   s_chl  = reinterpret_cast<int*>( s_link + n );
+    for( int i = threadIdx.x; i < n; i += blockDim.x ) { s_env[ i ] = prm.sv.env[ i ]; s_link[ i ] = prm.sv.link[ i ]; }
+    for( int i = threadIdx.x; i < n * GEO_STRIDE; i += blockDim.x ) s_geo[ i ] = prm.sv.geo[ i ];
+    for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_chl[ i ] = prm.sv.children[ i ];
+    __syncthreads();
+    prm.sv.env = s_env; prm.sv.geo = s_geo; prm.sv.link = s_link; prm.sv.children = s_chl;
+}
+
+// obj_color (objects.c:411-422) with txm_plain / txm_chess (textures.c:99-102,142-148)
+template <typename R> __device__ __forceinline__ V3<R> obj_color( const DParams<R>& prm, int node, V3<R> pos )
+{
+    const DMat<R>& m = prm.mats[ prm.sv.link[ node ].w ];
+    if( m.tex_kind == ACN_TEX_NONE )  return v3<R>( m.color[ 0 ], m.color[ 1 ], m.color[ 2 ] );
+    if( m.tex_kind == ACN_TEX_PLAIN ) return v3<R>( m.tex1[ 0 ], m.tex1[ 1 ], m.tex1[ 2 ] );
+    R u, v;
+    obj_projection( prm.sv, node, pos, &u, &v );
+    long long x = llrint( ( double )( u * m.tex_scale ) );
+    long long y = llrint( ( double )( v * m.tex_scale ) );
+    return ( ( x ^ y ) & 1 ) ? v3<R>( m.tex1[ 0 ], m.tex1[ 1 ], m.tex1[ 2 ] ) : v3<R>( m.tex2[ 0 ], m.tex2[ 1 ], m.tex2[ 2 ] );
+}
+
+template <typename R> __device__ __forceinline__ u64 skip2( const DParams<R>& prm, u64 s, unsigned long long k )
+{
+    if( k < ( unsigned long long )prm.skip_n ) return s * prm.skipA[ k ] + prm.skipC[ k ];
+    return lcg00_skip( s, 2ull * k );
+}
+
+template <typename R> __device__ __forceinline__ void emit_ray( const Wave<R>& w, V3<R> p, V3<R> d, R intensity, int depth,
+                                                              V3<R> tp, int cls, int sample, u64 key )
+{
+    int flags = 0;
+    if( depth == 0 || intensity < w.prm.min_intensity ) flags |= RAYF_PROBE;
+    unsigned long long slot = w.rays_out_base + agg_inc( &w.ctr->rays_out );
+    if( slot >= w.rays_cap ) { w.ctr->overflow = 1; return; }
+    R4<R> a; a.x = p.x; a.y = p.y; a.z = p.z; a.w = intensity;
+    R4<R> b; b.x = d.x; b.y = d.y; b.z = d.z; b.w = R( 0 );
+    R4<R> c; c.x = tp.x; c.y = tp.y; c.z = tp.z; c.w = R( 0 );
+    I4 m; m.x = depth | ( cls << 8 ) | flags; m.y = sample; m.z = ( int )( unsigned )( key & 0xFFFFFFFFull ); m.w = ( int )( unsigned )( key >> 32 );
+    w.rays_out.o_i[ slot ] = a; w.rays_out.d_[ slot ] = b; w.rays_out.tp[ slot ] = c; w.rays_out.meta[ slot ] = m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene_s_lum (scene.c:420-667) for one hit: emits child rays and at most one diffuse task.
+// ---------------------------------------------------------------------------------------------
+template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>& ray, R a, const Trans<R>& tr,
+                                                 int depth, R I, V3<R> tp, int sample, u64 key )
+{
+    const DParams<R>& prm = w.prm;
+    if( depth == 0 || I < prm.min_intensity ) return;                                    // scene.c:428
+    const V3<R> pos = madd( ray.p, ray.d, a );
+
+    const DMat<R>* me = tr.enter_obj >= 0 ? &prm.mats[ prm.sv.link[ tr.enter_obj ].w ] : nullptr;
+    if( me && me->radiance > R( 0 ) )                                                    // scene.c:432-437
+    {
+        R d2 = sqr( pos - xyz( prm.sv.geo[ tr.enter_obj * GEO_STRIDE ] ) );
+        R li = d2 > R( 0 ) ? me->radiance / d2 : Num<R>::mag();
+        add_sample( w, sample, mul( obj_color( prm, tr.enter_obj, pos ), tp ) * ( li * I ) );
+        agg_count( &w.ctr->stats[ ST_LIGHT ] );
+        return;
+    }
+
+    R nrel = R( 1 ), F = R( 0 ), C = R( 0 ), Dff = R( 0 ), on_a = R( 1 ), on_b = R( 0 );
+    bool T = false;
+    if( me )
+    {
+        nrel = me->refr; F = me->fresnel01; C = me->chroma; Dff = me->diffuse;
+        T = me->transparent != 0; on_a = me->on_a; on_b = me->on_b;
+    }
+    if( tr.exit_obj >= 0 )                                                               // scene.c:464-470, 656-664
+    {
+        const DMat<R>& mx = prm.mats[ prm.sv.link[ tr.exit_obj ].w ];
+        nrel /= mx.refr; F = R( 1 ); C = R( 0 ); Dff = R( 0 ); T = true;
+        if( a > R( 0 ) )
+        {
+            tp.x *= r_pow( mx.transp[ 0 ], a );
+            tp.y *= r_pow( mx.transp[ 1 ], a );
+            tp.z *= r_pow( mx.transp[ 2 ], a );
+        }
+    }
+
+    if( F > R( 0 ) && I >= prm.min_intensity )                                           // scene.c:473-495
+    {
+        R refl = fresnel_reflectance( ray.d, tr.exit_nor, nrel ) * F;
+        emit_ray( w, pos, reflect( ray.d, tr.exit_nor ), refl * I, depth - 1, tp, RC_REFLECT, sample, mix64( key, KEY_REFLECT ) );
+        I *= ( R( 1 ) - refl );
+    }
+
+    if( C > R( 0 ) && I >= prm.min_intensity )                                           // scene.c:498-523
+    {
+        V3<R> col = obj_color( prm, tr.enter_obj, pos );
+        emit_ray( w, pos, reflect( ray.d, tr.exit_nor ), C * I, depth - 1, mul( tp, col ), RC_CHROMATIC, sample, mix64( key, KEY_CHROMATIC ) );
+        I *= ( R( 1 ) - C );
+    }
+
+    if( tr.enter_obj >= 0 && I * Dff >= prm.min_intensity )                              // scene.c:526-630
+    {
+        const R Id = I * Dff;
+        const V3<R> nrm = -tr.exit_nor;
+        const R cos_i = dot( ray.d, tr.exit_nor );
+        const V3<R> prj = unit( ray.d - nrm * dot( ray.d, nrm ) );
+        u64 rv0 = prm.sv.seed_mode == SEED_POSITION_HASH
+                      ? random_seed( pos, ( u64 )3294479285ull ) + random_seed( nrm, ( u64 )3247146734ull )
+                      : mix64( key, KEY_DIFFUSE );
+        V3<R> col = obj_color( prm, tr.enter_obj, pos );
+        unsigned long long nd = ( unsigned long long )( ( double )prm.direct_samples * ( double )Id );   // scene.c:553
+        if( nd == 0 ) nd = 1;
+        unsigned long long np = 0;
+        if( prm.path_samples && depth > 10 )                                             // scene.c:584,593
+        {
+            np = ( unsigned long long )( ( double )prm.path_samples * ( double )Id );
+            if( np == 0 ) np = 1;
+        }
+        unsigned long long slot = agg_inc( &w.ctr->tasks_new );
+        if( np ) agg_count( &w.ctr->tasks_new_path );
+        if( slot < w.tasks_cap )
+        {
+            V3<R> tpc = mul( tp, col );
+            R4<R> q;
+            q.x = pos.x; q.y = pos.y; q.z = pos.z; q.w = Id;      w.tasks_out.pos_id[ slot ] = q;
+            q.x = nrm.x; q.y = nrm.y; q.z = nrm.z; q.w = cos_i;   w.tasks_out.nrm_ci[ slot ] = q;
+            q.x = prj.x; q.y = prj.y; q.z = prj.z; q.w = on_a;    w.tasks_out.prj_a[ slot ] = q;
+            q.x = tpc.x; q.y = tpc.y; q.z = tpc.z; q.w = on_b;    w.tasks_out.tpc_b[ slot ] = q;
+            I4 m; m.x = sample; m.y = depth; m.z = ( int )nd; m.w = ( int )np;
+            w.tasks_out.meta[ slot ] = m;
+            w.tasks_out.rv0[ slot ] = rv0;
+            w.tasks_out.key[ slot ] = key;
+        }
+        else w.ctr->overflow = 2;
+        I *= ( R( 1 ) - Dff );
+    }
+
+    if( T && I >= prm.min_intensity )                                                    // scene.c:633-653
+    {
+        emit_ray( w, madd( ray.p, ray.d, a + R( 2 ) * prm.sv.eps ), refract( ray.d, tr.exit_nor, nrel ), I, depth - 1, tp,
+                  RC_REFRACT, sample, mix64( key, KEY_REFRACT ) );
+    }
+}
+
+// trace one ray of the tree and shade its hit.
+//   cls != RC_PATH: scene_s_trans_hit (lights + matter), miss -> background * I  (scene.c:484-491 etc.)
+//   cls == RC_PATH: matter only; beyond max_path_length -> background * I        (scene.c:606-616)
+//   probe: the hit's shading would return 0 (depth 0 or I < Imin) — only "anything hit?" matters
+template <typename R> __device__ void trace_ray( const Wave<R>& w, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
+                                                 bool probe, int sample, u64 key )
+{
+    const DParams<R>& prm = w.prm;
+    const R inf = Num<R>::inf();
+    HitCtx ctx; ctx.key = key;
+    if( probe && cls != RC_PATH )
+    {
+        R a = compound_ray_hit<R>( prm.sv, prm.sv.light_root, ray, nullptr, nullptr, ctx, inf );
+        if( !( a < inf ) ) a = compound_ray_hit<R>( prm.sv, prm.sv.matter_root, ray, nullptr, nullptr, ctx, inf );
+        if( !( a < inf ) ) add_sample( w, sample, mul( prm.background, tp ) * I );
+        return;
+    }
+    if( probe )     // path child that cannot contribute on a hit: is anything closer than max_path_length?
+    {
+        R a = compound_ray_hit<R>( prm.sv, prm.sv.matter_root, ray, nullptr, nullptr, ctx, prm.max_path_length );
+        if( !( a < prm.max_path_length ) ) add_sample( w, sample, mul( prm.background, tp ) * I );
+        return;
+    }
+    Trans<R> tr;
+    tr.exit_obj = tr.enter_obj = -1; tr.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    R a;
+    if( cls == RC_PATH )
+    {
+        a = compound_trans_hit( prm.sv, prm.sv.matter_root, ray, &tr, ctx );
+        if( !( a < prm.max_path_length ) ) { add_sample( w, sample, mul( prm.background, tp ) * I ); return; }
+    }
+    else
+    {
+        a = scene_trans_hit( prm.sv, ray, &tr, ctx );
+        if( !( a < inf ) ) { add_sample( w, sample, mul( prm.background, tp ) * I ); return; }
+    }
+    shade_hit( w, ray, a, tr, depth, I, tp, sample, key );
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+#define ACN_BLOCK 128
+
+// camera rays (scene.c:976-990) fused with their first trace + shade
+template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+k_primary( Wave<R> w, const double* __restrict__ xy, unsigned long long first, unsigned long long count )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    stage_scene( w.prm, smem );
+    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= count ) return;
+    const DParams<R>& prm = w.prm;
+    const unsigned long long s = first + i;
+    const double mx = xy[ 2 * s ], my = xy[ 2 * s + 1 ];
+    const int unit_sz = prm.height >> 1;
+    const double unit_f = 1.0 / ( double )unit_sz;
+    const R z = ( R )( unit_f * ( ( double )unit_sz - my ) );
+    const R x = ( R )( unit_f * ( mx - ( double )( prm.width >> 1 ) ) );
+    V3<R> d = unit( v3<R>( x, prm.focal, z ) );
+    Ray<R> ray;
+    ray.p = prm.cam_pos;
+    ray.d = prm.cam_rx * d.x + prm.cam_ry * d.y + prm.cam_rz * d.z;
+    agg_count( &w.ctr->stats[ ST_PRIMARY ] );
+    trace_ray( w, ray, R( 1 ), prm.trace_depth, v3<R>( R( 1 ), R( 1 ), R( 1 ) ), RC_PRIMARY, false,
+               ( int )( s - w.sample_base ), mix64( w.index_base + s, 0x5EEDull ) );
+}
+
+// explicit rays popped from the ray stack
+template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+k_rays( Wave<R> w, RayBuf<R> in, unsigned long long count )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    stage_scene( w.prm, smem );
+    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= count ) return;
+    const R4<R> a = in.o_i[ i ], b = in.d_[ i ], c = in.tp[ i ];
+    const I4 m = in.meta[ i ];
+    Ray<R> ray; ray.p = xyz( a ); ray.d = xyz( b );
+    const int depth = m.x & 0xFF, cls = ( m.x >> 8 ) & 0xFF;
+    const u64 key = ( u64 )( unsigned )m.z | ( ( u64 )( unsigned )m.w << 32 );
+    agg_count( &w.ctr->stats[ cls ] );
+    trace_ray( w, ray, a.w, depth, xyz( c ), cls, ( m.x & RAYF_PROBE ) != 0, m.y, key );
+}
+
+// warp-cooperative expansion of 32 tasks: lane l of the warp owns flattened child index idx and
+// finds (task, child) by a 5-step search over the warp's prefix sums held in shared memory.
+struct WarpSlots { unsigned int cum[ 33 ]; };
+
+// direct lighting (scene.c:542-581): one lane per (task, light, sample)
+template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+k_direct( Wave<R> w, TaskBuf<R> in, unsigned long long count )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    __shared__ WarpSlots slots[ ACN_BLOCK / 32 ];
+    __shared__ R sums[ ACN_BLOCK / 32 ][ 32 ][ 3 ];
+    stage_scene( w.prm, smem );
+    const DParams<R>& prm = w.prm;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned long long t0 = ( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) + wid ) * 32ull;
+    if( t0 >= count ) return;
+    const unsigned long long my_t = t0 + lane;
+    const int L = prm.n_lights;
+    unsigned int cnt = 0;
+    if( my_t < count ) cnt = ( unsigned int )in.meta[ my_t ].z * ( unsigned int )L;
+    unsigned int inc = cnt;
+    #pragma unroll
+    for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( 0xFFFFFFFFu, inc, o ); if( lane >= o ) inc += v; }
+    WarpSlots& ws = slots[ wid ];
+    ws.cum[ lane + 1 ] = inc;
+    if( lane == 0 ) ws.cum[ 0 ] = 0;
+    sums[ wid ][ lane ][ 0 ] = R( 0 ); sums[ wid ][ lane ][ 1 ] = R( 0 ); sums[ wid ][ lane ][ 2 ] = R( 0 );
+    __syncwarp();
+    const unsigned int total = ws.cum[ 32 ];
+    unsigned long long n_shadow = 0;
+
+    for( unsigned int base = 0; base < total; base += 32 )
+    {
+        const unsigned int idx = base + lane;
+        if( idx < total )
+        {
+            int k = 0;
+            #pragma unroll
+            for( int s = 16; s > 0; s >>= 1 ) if( ws.cum[ k + s ] <= idx ) k += s;
+            const unsigned long long t = t0 + k;
+            const unsigned int r = idx - ws.cum[ k ];
+            const I4 m = in.meta[ t ];
+            const unsigned int nd = ( unsigned int )m.z;
+            const unsigned int li = r / nd, j = r - li * nd;
+            const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+            const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
+            const DLight<R>& lg = prm.lights[ li ];
+
+            V3<R> axis; R cos_rs;
+            obj_fov( prm.sv, lg.node, pos, &axis, &cos_rs );
+            const Basis<R> bs = basis_con_z( axis );
+            const R h = R( 1 ) - cos_rs;                                                 // areal_coverage, vectors.h:362
+            u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )li * nd + j );
+            Ray<R> out; out.p = pos;
+            out.d = from_basis( bs, sphere_cap<R>( &rv, h ) );
+            R wgt = dot( out.d, nrm );
+            if( wgt > R( 0 ) )
+            {
+                HitCtx ctx; ctx.key = 0;
+                n_shadow++;
+                R a = obj_ray_hit<R>( prm.sv, lg.node, out, nullptr, ctx );              // scene.c:564
+                if( a < Num<R>::inf() )
+                {
+                    if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, prj );
+                    n_shadow++;
+                    R sh = compound_ray_hit<R>( prm.sv, prm.sv.matter_root, out, nullptr, nullptr, ctx, a );   // scene.c:569
+                    if( sh > a )
+                    {
+                        V3<R> hp = madd( out.p, out.d, a );
+                        R d2 = sqr( hp - v3<R>( lg.pos[ 0 ], lg.pos[ 1 ], lg.pos[ 2 ] ) );
+                        R lint = d2 > R( 0 ) ? lg.radiance / d2 : Num<R>::mag();
+                        R f = lint * wgt * pi.w * ( R( 2 ) * h / ( R )nd );               // scene.c:574,579
+                        atomic_add_r( &sums[ wid ][ k ][ 0 ], lg.color[ 0 ] * f * tb.x );
+                        atomic_add_r( &sums[ wid ][ k ][ 1 ], lg.color[ 1 ] * f * tb.y );
+                        atomic_add_r( &sums[ wid ][ k ][ 2 ], lg.color[ 2 ] * f * tb.z );
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if( my_t < count )
+    {
+        const int sample = in.meta[ my_t ].x;
+        V3<R> c = v3<R>( sums[ wid ][ lane ][ 0 ], sums[ wid ][ lane ][ 1 ], sums[ wid ][ lane ][ 2 ] );
+        if( c.x != R( 0 ) || c.y != R( 0 ) || c.z != R( 0 ) ) add_sample( w, sample, c );
+    }
+    #pragma unroll
+    for( int o = 16; o > 0; o >>= 1 ) n_shadow += __shfl_down_sync( 0xFFFFFFFFu, n_shadow, o );
+    if( lane == 0 )
+    {
+        atomicAdd( &w.ctr->stats[ ST_SHADOW ], n_shadow );
+    }
+}
+
+// indirect rays (scene.c:584-621): one lane per (task, path sample); the child ray is generated,
+// traced and shaded in place, never stored.
+template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+k_path( Wave<R> w, TaskBuf<R> in, unsigned long long count )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    __shared__ WarpSlots slots[ ACN_BLOCK / 32 ];
+    stage_scene( w.prm, smem );
+    const DParams<R>& prm = w.prm;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned long long t0 = ( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) + wid ) * 32ull;
+    if( t0 >= count ) return;
+    const unsigned long long my_t = t0 + lane;
+    unsigned int cnt = 0;
+    if( my_t < count ) cnt = ( unsigned int )in.meta[ my_t ].w;
+    unsigned int inc = cnt;
+    #pragma unroll
+    for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( 0xFFFFFFFFu, inc, o ); if( lane >= o ) inc += v; }
+    WarpSlots& ws = slots[ wid ];
+    ws.cum[ lane + 1 ] = inc;
+    if( lane == 0 ) ws.cum[ 0 ] = 0;
+    __syncwarp();
+    const unsigned int total = ws.cum[ 32 ];
+    const int L = prm.n_lights;
+
+    for( unsigned int base = 0; base < total; base += 32 )
+    {
+        const unsigned int idx = base + lane;
+        if( idx >= total ) continue;
+        int k = 0;
+        #pragma unroll
+        for( int s = 16; s > 0; s >>= 1 ) if( ws.cum[ k + s ] <= idx ) k += s;
+        const unsigned long long t = t0 + k;
+        const unsigned int i = idx - ws.cum[ k ];
+        const I4 m = in.meta[ t ];
+        const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+        const V3<R> nrm = xyz( nc );
+        const Basis<R> bs = basis_con_z( nrm );
+        u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )L * ( unsigned int )m.z + i );
+        Ray<R> out; out.p = xyz( pi );
+        out.d = from_basis( bs, sphere_cap<R>( &rv, R( 1 ) ) );
+        R wgt = dot( out.d, nrm );
+        if( wgt <= R( 0 ) ) continue;                                                    // scene.c:600
+        if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, xyz( pa ) );
+        agg_count( &w.ctr->stats[ ST_PATH ] );
+        const R scale = R( 2 ) / ( R )( unsigned int )m.w;                               // scene.c:620
+        const R ci = wgt * pi.w;
+        const bool probe = ( m.y - 10 ) == 0 || ci < prm.min_intensity;
+        trace_ray( w, out, ci, m.y - 10, xyz( tb ) * scale, RC_PATH, probe, m.x, mix64( in.key[ t ], KEY_PATH0 + i ) );
+    }
+}
+
+// keeps the tasks that still have path work: new-task scratch -> task stack, with the running sum
+// of n_path stored alongside so that a later wave can be cut at an exact child budget
+template <typename R> __global__ void __launch_bounds__( 256 )
+k_keep( TaskBuf<R> in, unsigned long long count, TaskBuf<R> stack, unsigned long long stack_cap, Counters* ctr )
+{
+    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned int np = 0;
+    if( i < count ) np = ( unsigned int )in.meta[ i ].w;
+    const unsigned int mask = __ballot_sync( 0xFFFFFFFFu, np > 0 );
+    if( mask == 0 ) return;
+    unsigned int inc = np;
+    #pragma unroll
+    for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( 0xFFFFFFFFu, inc, o ); if( lane >= o ) inc += v; }
+    const unsigned int total = __shfl_sync( 0xFFFFFFFFu, inc, 31 );
+    unsigned long long base = 0;
+    if( lane == 0 ) base = atomicAdd( &ctr->task_stack, ( ( unsigned long long )__popc( mask ) << ACN_TASK_SHIFT ) | total );
+    base = __shfl_sync( 0xFFFFFFFFu, base, 0 );
+    if( np == 0 ) return;
+    const unsigned long long slot = ( base >> ACN_TASK_SHIFT ) + __popc( mask & ( ( 1u << lane ) - 1 ) );
+    if( slot >= stack_cap ) { ctr->overflow = 3; return; }
+    stack.pos_id[ slot ] = in.pos_id[ i ]; stack.nrm_ci[ slot ] = in.nrm_ci[ i ];
+    stack.prj_a[ slot ]  = in.prj_a[ i ];  stack.tpc_b[ slot ]  = in.tpc_b[ i ];
+    stack.meta[ slot ] = in.meta[ i ]; stack.rv0[ slot ] = in.rv0[ i ]; stack.key[ slot ] = in.key[ i ];
+    stack.cum[ slot ] = ( base & ACN_TASK_MASK ) + inc;
+}
+
+// finds the first task of the top slice of the stack whose path children fit the budget
+__global__ void k_plan( const u64* cum, unsigned long long n_tasks, unsigned long long budget, Counters* ctr )
+{
+    if( threadIdx.x != 0 || blockIdx.x != 0 ) return;
+    const unsigned long long top = cum[ n_tasks - 1 ];
+    // smallest s such that top - cum[s-1] <= budget  (cum[-1] := base of the stack, 0)
+    unsigned long long lo = 0, hi = n_tasks - 1;     // always take at least the top task
+    while( lo < hi )
+    {
+        unsigned long long mid = ( lo + hi ) >> 1;
+        unsigned long long before = mid ? cum[ mid - 1 ] : 0;
+        if( top - before <= budget ) hi = mid; else lo = mid + 1;
+    }
+    ctr->plan_start = lo;
+    ctr->plan_cum = lo ? cum[ lo - 1 ] : 0;
+}
+
+// cl_s_sat (vectors.h:372-384, scene.c:1010): pow(c, gamma) then clamp, per sample
+template <typename R> __global__ void k_finish( const R* accum, unsigned long long n, R gamma, float* rgb )
+{
+    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= n * 3 ) return;
+    R v = r_pow( accum[ i ], gamma );
+    v = v > R( 0 ) ? ( v < R( 1 ) ? v : R( 1 ) ) : R( 0 );
+    rgb[ i ] = ( float )v;
+}
+
+// lum_image_s_push (scene.c:804-813) on the device
+__global__ void k_accumulate( const double* xy, const float* rgb, unsigned long long n, int width, int height, float* accum )
+{
+    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= n ) return;
+    int x = ( int )xy[ 2 * i ], y = ( int )xy[ 2 * i + 1 ];
+    if( x < 0 || x >= width || y < 0 || y >= height ) return;
+    float* a = accum + 4ull * ( ( unsigned long long )y * width + x );
+    atomicAdd( a + 0, rgb[ 3 * i + 0 ] );
+    atomicAdd( a + 1, rgb[ 3 * i + 1 ] );
+    atomicAdd( a + 2, rgb[ 3 * i + 2 ] );
+    atomicAdd( a + 3, 1.0f );
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side of the tracer
+// ---------------------------------------------------------------------------------------------
+struct TracerBase
+{
+    virtual ~TracerBase() {}
+    virtual int render( const double* d_xy, uint64_t n, uint64_t index_base, float* d_rgb, cudaStream_t st,
+                        const volatile int* cancel, acn_stats* stats ) = 0;
+    int width = 0, height = 0, device = 0;
+    cudaStream_t own_stream = nullptr;
+    // staging for the host-pointer entry point
+    double* d_xy_stage = nullptr; float* d_rgb_stage = nullptr; uint64_t stage_cap = 0;
+};
+
+void set_error( const char* fmt, ... );
+
+#define ACN_CUDA( call ) do { cudaError_t e__ = ( call ); if( e__ != cudaSuccess ) { \
+    set_error( "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString( e__ ) ); return ACN_ERR_CUDA; } } while( 0 )
+
+template <typename T> static int dev_alloc( T** p, size_t n )
+{
+    cudaError_t e = cudaMalloc( ( void** )p, n * sizeof( T ) );
+    if( e != cudaSuccess ) { set_error( "cudaMalloc(%zu bytes) failed: %s", n * sizeof( T ), cudaGetErrorString( e ) ); return ACN_ERR_OUT_OF_MEMORY; }
+    return ACN_OK;
+}
+
+template <typename R> static int alloc_rays( RayBuf<R>& b, size_t n )
+{
+    int rc;
+    if( ( rc = dev_alloc( &b.o_i, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.d_, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.tp, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.meta, n ) ) ) return rc;
+    return ACN_OK;
+}
+template <typename R> static void free_rays( RayBuf<R>& b ) { cudaFree( b.o_i ); cudaFree( b.d_ ); cudaFree( b.tp ); cudaFree( b.meta ); }
+
+template <typename R> static int alloc_tasks( TaskBuf<R>& b, size_t n )
+{
+    int rc;
+    if( ( rc = dev_alloc( &b.pos_id, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.nrm_ci, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.prj_a, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.tpc_b, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.meta, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.rv0, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.key, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.cum, n ) ) ) return rc;
+    return ACN_OK;
+}
+template <typename R> static void free_tasks( TaskBuf<R>& b )
+{
+    cudaFree( b.pos_id ); cudaFree( b.nrm_ci ); cudaFree( b.prj_a ); cudaFree( b.tpc_b );
+    cudaFree( b.meta ); cudaFree( b.rv0 ); cudaFree( b.key ); cudaFree( b.cum );
+}
+
+template <typename R> struct Tracer : TracerBase
+{
+    DParams<R> prm;
+    // device copies of the scene tables
+    R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr;
+    DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
+    u64* d_skipA = nullptr; u64* d_skipC = nullptr;
+    // queues
+    RayBuf<R>  ray_stack, ray_cur;
+    TaskBuf<R> task_stack, task_cur, task_new;
+    uint64_t   ray_cap = 0, task_stack_cap = 0, budget = 0;
+    Counters*  d_ctr = nullptr;
+    Counters*  h_ctr = nullptr;       // pinned
+    R*         d_accum = nullptr; uint64_t accum_cap = 0;
+    int        smem_bytes = 0;
+    int        max_csg_depth = 0;
+
+    ~Tracer() override
+    {
+        cudaSetDevice( device );
+        cudaFree( d_env ); cudaFree( d_link ); cudaFree( d_geo ); cudaFree( d_children );
+        cudaFree( d_mats ); cudaFree( d_lights ); cudaFree( d_skipA ); cudaFree( d_skipC );
+        free_rays( ray_stack ); free_rays( ray_cur );
+        free_tasks( task_stack ); free_tasks( task_cur ); free_tasks( task_new );
+        cudaFree( d_ctr ); if( h_ctr ) cudaFreeHost( h_ctr );
+        cudaFree( d_accum ); cudaFree( d_xy_stage ); cudaFree( d_rgb_stage );
+        if( own_stream ) cudaStreamDestroy( own_stream );
+    }
+
+    int init( const acn_flat_scene* fs, const acn_options* opt );
+    int render( const double* d_xy, uint64_t n, uint64_t index_base, float* d_rgb, cudaStream_t st,
+                const volatile int* cancel, acn_stats* stats ) override;
+
+    Wave<R> make_wave( uint64_t rays_base, uint64_t index_base )
+    {
+        Wave<R> w;
+        w.prm = prm; w.rays_out = ray_stack; w.tasks_out = task_new; w.ctr = d_ctr; w.accum = d_accum;
+        w.rays_out_base = rays_base; w.rays_cap = ray_cap; w.tasks_cap = budget;
+        w.sample_base = 0; w.index_base = index_base;
+        return w;
+    }
+};
+
+// depth of the CSG recursion below node n (for the device stack size)
+static int csg_depth( const acn_flat_scene* fs, int n, int guard )
+{
+    if( guard > 64 ) return 64;
+    const acn_flat_node& nd = fs->nodes[ n ];
+    switch( nd.kind )
+    {
+        case ACN_KIND_PAIR_INSIDE: case ACN_KIND_PAIR_OUTSIDE:
+        {
+            int a = csg_depth( fs, nd.child0, guard + 1 ), b = csg_depth( fs, nd.child1, guard + 1 );
+            return 1 + ( a > b ? a : b );
+        }
+        case ACN_KIND_NEG: case ACN_KIND_SCALE: return 1 + csg_depth( fs, nd.child0, guard + 1 );
+        case ACN_KIND_COMPOUND:
+        {
+            int m = 0;
+            for( int i = 0; i < nd.child1; i++ ) { int d = csg_depth( fs, fs->children[ nd.child0 + i ], guard + 1 ); if( d > m ) m = d; }
+            return m;
+        }
+        default: return 0;
+    }
+}
+
+static int compound_depth( const acn_flat_scene* fs, int n, int guard )
+{
+    if( guard > 64 ) return 64;
+    const acn_flat_node& nd = fs->nodes[ n ];
+    if( nd.kind != ACN_KIND_COMPOUND ) return 0;
+    int m = 0;
+    for( int i = 0; i < nd.child1; i++ ) { int d = compound_depth( fs, fs->children[ nd.child0 + i ], guard + 1 ); if( d > m ) m = d; }
+    return 1 + m;
+}
+
+int validate_flat_scene( const acn_flat_scene* fs );   // acn_tracer.cu
+
+template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_options* opt )
+{
+    int rc = validate_flat_scene( fs );
+    if( rc ) return rc;
+    const acn_flat_params& p = fs->params;
+    width = p.image_width; height = p.image_height;
+    const int n = fs->n_nodes;
+
+    // ---- pack the node table
+    std::vector<R4<R>> env( n ), geo( ( size_t )n * GEO_STRIDE );
+    std::vector<I4> link( n );
+    double scale = 0;
+    for( int k = 0; k < 3; k++ ) scale = fmax( scale, fabs( p.camera_position[ k ] ) );
+    for( int i = 0; i < n; i++ )
+    {
+        const acn_flat_node& nd = fs->nodes[ i ];
+        int flags = 0;
+        if( nd.has_envelope ) flags |= F_ENV;
+        if( nd.surface_roughness > 0 && nd.kind != ACN_KIND_COMPOUND ) flags |= F_ROUGH;
+        env[ i ].x = ( R )nd.env_pos[ 0 ]; env[ i ].y = ( R )nd.env_pos[ 1 ]; env[ i ].z = ( R )nd.env_pos[ 2 ];
+        env[ i ].w = nd.has_envelope ? ( R )nd.env_radius : ( R )-1;
+        link[ i ].x = nd.kind | ( flags << 8 ); link[ i ].y = nd.child0; link[ i ].z = nd.child1; link[ i ].w = nd.material;
+        R4<R>* g = &geo[ ( size_t )i * GEO_STRIDE ];
+        g[ 0 ].x = ( R )nd.pos[ 0 ]; g[ 0 ].y = ( R )nd.pos[ 1 ]; g[ 0 ].z = ( R )nd.pos[ 2 ]; g[ 0 ].w = ( R )nd.tail[ 0 ];
+        for( int r = 0; r < 3; r++ )
+        {
+            g[ 1 + r ].x = ( R )nd.rax[ 3 * r + 0 ]; g[ 1 + r ].y = ( R )nd.rax[ 3 * r + 1 ]; g[ 1 + r ].z = ( R )nd.rax[ 3 * r + 2 ];
+            g[ 1 + r ].w = ( R )nd.tail[ 1 + r ];
+        }
+        g[ 4 ].x = ( R )nd.surface_roughness; g[ 4 ].y = g[ 4 ].z = g[ 4 ].w = ( R )0;
+        if( nd.kind != ACN_KIND_COMPOUND && nd.kind != ACN_KIND_PLANE )
+            for( int k = 0; k < 3; k++ ) scale = fmax( scale, fabs( nd.pos[ k ] ) );
+    }
+
+    // ---- shell thickness: the reference's absolute 1e-6 is sub-ulp in FP32 at scene scale ~10, so the
+    // f32 path widens it to 64 ulp of the scene scale (DESIGN.md "eps")
+    double eps = opt->eps;
+    if( !( eps > 0 ) )
+    {
+        eps = 1E-6;
+        if( sizeof( R ) == 4 ) eps = fmax( 1E-6, 64.0 * 1.1920929E-7 * fmax( scale, 1E-3 ) );
+    }
+
+    cudaError_t ce = cudaSetDevice( device );
+    if( ce != cudaSuccess ) { set_error( "cudaSetDevice(%d): %s", device, cudaGetErrorString( ce ) ); return ACN_ERR_NO_DEVICE; }
+    ACN_CUDA( cudaStreamCreateWithFlags( &own_stream, cudaStreamNonBlocking ) );
+
+    if( ( rc = dev_alloc( &d_env, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_link, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_geo, ( size_t )n * GEO_STRIDE ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_children, ( size_t )( fs->n_children > 0 ? fs->n_children : 1 ) ) ) ) return rc;
+    ACN_CUDA( cudaMemcpy( d_env, env.data(), n * sizeof( R4<R> ), cudaMemcpyHostToDevice ) );
+    ACN_CUDA( cudaMemcpy( d_link, link.data(), n * sizeof( I4 ), cudaMemcpyHostToDevice ) );
+    ACN_CUDA( cudaMemcpy( d_geo, geo.data(), ( size_t )n * GEO_STRIDE * sizeof( R4<R> ), cudaMemcpyHostToDevice ) );
+    if( fs->n_children > 0 ) ACN_CUDA( cudaMemcpy( d_children, fs->children, fs->n_children * sizeof( int ), cudaMemcpyHostToDevice ) );
+
+    // ---- materials
+    std::vector<DMat<R>> mats( fs->n_materials > 0 ? fs->n_materials : 1 );
+    for( int i = 0; i < fs->n_materials; i++ )
+    {
+        const acn_flat_material& fm = fs->materials[ i ];
+        DMat<R>& m = mats[ i ];
+        for( int k = 0; k < 3; k++ ) { m.color[ k ] = ( R )fm.color[ k ]; m.transp[ k ] = ( R )fm.transparency[ k ]; m.tex1[ k ] = ( R )fm.tex_color1[ k ]; m.tex2[ k ] = ( R )fm.tex_color2[ k ]; }
+        m.radiance = ( R )fm.radiance; m.refr = ( R )fm.refractive_index;
+        m.fresnel01 = ( fm.fresnel_reflectivity != 0 && fm.refractive_index != 1.0 ) ? ( R )1 : ( R )0;
+        m.chroma = ( R )fm.chromatic_reflectivity; m.diffuse = ( R )fm.diffuse_reflectivity;
+        double oa = 1, ob = 0;
+        if( fm.sigma > 0 ) { double s2 = fm.sigma * fm.sigma; oa = 1.0 - 0.5 * s2 / ( s2 + 0.33 ); ob = 0.45 * s2 / ( s2 + 0.09 ); }
+        m.on_a = ( R )oa; m.on_b = ( R )ob;
+        m.transparent = ( fm.transparency[ 0 ] * fm.transparency[ 0 ] + fm.transparency[ 1 ] * fm.transparency[ 1 ] + fm.transparency[ 2 ] * fm.transparency[ 2 ] ) > 0;
+        m.tex_kind = fm.texture_kind; m.tex_scale = ( R )fm.tex_scale;
+    }
+    if( ( rc = dev_alloc( &d_mats, mats.size() ) ) ) return rc;
+    ACN_CUDA( cudaMemcpy( d_mats, mats.data(), mats.size() * sizeof( DMat<R> ), cudaMemcpyHostToDevice ) );
+
+    // ---- lights = elements of the light compound (scene.c:542-552)
+    const acn_flat_node& lroot = fs->nodes[ fs->light_root ];
+    std::vector<DLight<R>> lights( lroot.child1 > 0 ? lroot.child1 : 1 );
+    {
+        // host view (double) for evaluating obj_color( light, light.pos ) once
+        std::vector<R4<double>> henv( n ), hgeo( ( size_t )n * GEO_STRIDE );
+        for( int i = 0; i < n; i++ )
+        {
+            henv[ i ].x = env[ i ].x; henv[ i ].y = env[ i ].y; henv[ i ].z = env[ i ].z; henv[ i ].w = env[ i ].w;
+            for( int k = 0; k < GEO_STRIDE; k++ )
+            {
+                const R4<R>& s = geo[ ( size_t )i * GEO_STRIDE + k ]; R4<double>& d = hgeo[ ( size_t )i * GEO_STRIDE + k ];
+                d.x = s.x; d.y = s.y; d.z = s.z; d.w = s.w;
+            }
+        }
+        SceneView<double> hv; hv.env = henv.data(); hv.geo = hgeo.data(); hv.link = link.data(); hv.children = fs->children;
+        hv.eps = eps; hv.light_root = fs->light_root; hv.matter_root = fs->matter_root; hv.seed_mode = 0;
+        for( int i = 0; i < lroot.child1; i++ )
+        {
+            const int ln = fs->children[ lroot.child0 + i ];
+            const acn_flat_node& nd = fs->nodes[ ln ];
+            if( !( nd.kind == ACN_KIND_SPHERE || nd.kind == ACN_KIND_PLANE || nd.kind == ACN_KIND_PAIR_INSIDE || nd.kind == ACN_KIND_PAIR_OUTSIDE ) )
+            {
+                set_error( "light %d (node %d, kind %d) has no fov function (reference objects.c:254-259 would abort)", i, ln, nd.kind );
+                return ACN_ERR_UNSUPPORTED;
+            }
+            const acn_flat_material& fm = fs->materials[ nd.material ];
+            DLight<R>& lg = lights[ i ];
+            lg.node = ln; lg.radiance = ( R )fm.radiance;
+            double col[ 3 ] = { fm.color[ 0 ], fm.color[ 1 ], fm.color[ 2 ] };
+            if( fm.texture_kind == ACN_TEX_PLAIN ) { for( int k = 0; k < 3; k++ ) col[ k ] = fm.tex_color1[ k ]; }
+            else if( fm.texture_kind == ACN_TEX_CHESS )
+            {
+                double u, v;
+                obj_projection<double>( hv, ln, v3<double>( nd.pos[ 0 ], nd.pos[ 1 ], nd.pos[ 2 ] ), &u, &v );
+                long long x = llrint( u * fm.tex_scale ), y = llrint( v * fm.tex_scale );
+                for( int k = 0; k < 3; k++ ) col[ k ] = ( ( x ^ y ) & 1 ) ? fm.tex_color1[ k ] : fm.tex_color2[ k ];
+            }
+            for( int k = 0; k < 3; k++ ) { lg.pos[ k ] = ( R )nd.pos[ k ]; lg.color[ k ] = ( R )col[ k ]; }
+        }
+    }
+    if( ( rc = dev_alloc( &d_lights, lights.size() ) ) ) return rc;
+    ACN_CUDA( cudaMemcpy( d_lights, lights.data(), lights.size() * sizeof( DLight<R> ), cudaMemcpyHostToDevice ) );
+
+    // ---- LCG skip table: state after 2k steps
+    const int skip_n = 1 << 14;
+    {
+        std::vector<u64> A( skip_n ), C( skip_n );
+        u64 a2 = ACN_LCG00_A * ACN_LCG00_A, c2 = ACN_LCG00_C * ( ACN_LCG00_A + 1 );
+        u64 a = 1, c = 0;
+        for( int k = 0; k < skip_n; k++ ) { A[ k ] = a; C[ k ] = c; c = c * a2 + c2; a *= a2; }
+        if( ( rc = dev_alloc( &d_skipA, skip_n ) ) ) return rc;
+        if( ( rc = dev_alloc( &d_skipC, skip_n ) ) ) return rc;
+        ACN_CUDA( cudaMemcpy( d_skipA, A.data(), skip_n * sizeof( u64 ), cudaMemcpyHostToDevice ) );
+        ACN_CUDA( cudaMemcpy( d_skipC, C.data(), skip_n * sizeof( u64 ), cudaMemcpyHostToDevice ) );
+    }
+
+    // ---- params
+    prm.sv.env = d_env; prm.sv.link = d_link; prm.sv.geo = d_geo; prm.sv.children = d_children;
+    prm.sv.eps = ( R )eps; prm.sv.light_root = fs->light_root; prm.sv.matter_root = fs->matter_root;
+    prm.sv.seed_mode = opt->seed_mode;
+    prm.mats = d_mats; prm.lights = d_lights; prm.n_lights = lroot.child1;
+    prm.n_nodes = n; prm.n_children = fs->n_children;
+    prm.width = p.image_width; prm.height = p.image_height;
+    prm.gamma = ( R )p.gamma;
+    prm.background = v3<R>( ( R )p.background_color[ 0 ], ( R )p.background_color[ 1 ], ( R )p.background_color[ 2 ] );
+    {   // camera_rotation (scene.c:963-973), in double on the host
+        V3<double> view = v3<double>( p.camera_view_direction[ 0 ], p.camera_view_direction[ 1 ], p.camera_view_direction[ 2 ] );
+        V3<double> top  = v3<double>( p.camera_top_direction[ 0 ], p.camera_top_direction[ 1 ], p.camera_top_direction[ 2 ] );
+        V3<double> ry = unit( view );
+        V3<double> rz = von( ry, unit( top ) );
+        V3<double> rx = cross( ry, rz );
+        prm.cam_rx = v3<R>( ( R )rx.x, ( R )rx.y, ( R )rx.z );
+        prm.cam_ry = v3<R>( ( R )ry.x, ( R )ry.y, ( R )ry.z );
+        prm.cam_rz = v3<R>( ( R )rz.x, ( R )rz.y, ( R )rz.z );
+        prm.cam_pos = v3<R>( ( R )p.camera_position[ 0 ], ( R )p.camera_position[ 1 ], ( R )p.camera_position[ 2 ] );
+    }
+    prm.focal = ( R )p.camera_focal_length;
+    prm.trace_depth = p.trace_depth > 255 ? 255 : p.trace_depth;
+    prm.direct_samples = p.direct_samples; prm.path_samples = p.path_samples;
+    prm.min_intensity = ( R )p.trace_min_intensity;
+    prm.max_path_length = ( R )p.max_path_length;
+    prm.skipA = d_skipA; prm.skipC = d_skipC; prm.skip_n = skip_n;
+
+    // shared-memory staging of the node table
+    size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + sizeof( I4 ) ) + ( size_t )fs->n_children * sizeof( int );
+    smem_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
+    prm.stage_bytes = smem_bytes;
+    if( smem_bytes > 40 * 1024 )
+    {
+        ACN_CUDA( cudaFuncSetAttribute( k_primary<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( k_rays<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( k_direct<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( k_path<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+    }
+
+    // device stack for the CSG recursion (obj_ray_hit <-> pair_hit <-> obj_side)
+    max_csg_depth = 0;
+    { int a = csg_depth( fs, fs->light_root, 0 ), b = csg_depth( fs, fs->matter_root, 0 ); max_csg_depth = a > b ? a : b; }
+    {
+        size_t want = 2048 + ( size_t )max_csg_depth * ( sizeof( R ) == 4 ? 640 : 1024 );
+        size_t cur = 0;
+        cudaDeviceGetLimit( &cur, cudaLimitStackSize );
+        if( cur < want ) ACN_CUDA( cudaDeviceSetLimit( cudaLimitStackSize, want ) );
+    }
+
+    // ---- queues
+    budget = opt->wave_budget > 0 ? ( uint64_t )opt->wave_budget : ( 1ull << 21 );
+    ray_cap = budget * 24;
+    task_stack_cap = budget * 6;
+    if( ( rc = alloc_rays( ray_stack, ray_cap ) ) ) return rc;
+    if( ( rc = alloc_rays( ray_cur, budget ) ) ) return rc;
+    if( ( rc = alloc_tasks( task_stack, task_stack_cap ) ) ) return rc;
+    if( ( rc = alloc_tasks( task_cur, task_stack_cap ) ) ) return rc;
+    if( ( rc = alloc_tasks( task_new, budget ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_ctr, 1 ) ) ) return rc;
+    ACN_CUDA( cudaMallocHost( ( void** )&h_ctr, sizeof( Counters ) ) );
+    return ACN_OK;
+}
+
+static inline unsigned grid_for( uint64_t n, unsigned block ) { return ( unsigned )( ( n + block - 1 ) / block ); }
+
+template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uint64_t index_base, float* d_rgb, cudaStream_t st,
+                                             const volatile int* cancel, acn_stats* stats )
+{
+    ACN_CUDA( cudaSetDevice( device ) );
+    if( stats ) memset( stats, 0, sizeof( *stats ) );
+    if( n == 0 ) return ACN_OK;
+    if( n > 0x7FFFFFFFull ) { set_error( "at most 2^31-1 samples per call" ); return ACN_ERR_INVALID_ARG; }
+    if( accum_cap < n )
+    {
+        cudaFree( d_accum ); d_accum = nullptr; accum_cap = 0;
+        int rc = dev_alloc( &d_accum, ( size_t )n * 3 );
+        if( rc ) return rc;
+        accum_cap = n;
+    }
+    cudaEvent_t ev0, ev1;
+    ACN_CUDA( cudaEventCreate( &ev0 ) ); ACN_CUDA( cudaEventCreate( &ev1 ) );
+    ACN_CUDA( cudaEventRecord( ev0, st ) );
+    ACN_CUDA( cudaMemsetAsync( d_accum, 0, ( size_t )n * 3 * sizeof( R ), st ) );
+    ACN_CUDA( cudaMemsetAsync( d_ctr, 0, sizeof( Counters ), st ) );
+
+    uint64_t launches = 0, waves = 0;
+    uint64_t nr = 0;                 // rays on the stack
+    uint64_t nt = 0, nt_cum = 0;     // tasks on the stack, their total path children
+    unsigned long long stat_sum[ ST_COUNT ] = { 0 };
+    int result = ACN_OK;
+
+    // after every wave: direct lighting of the new tasks, keep those with path work, read the counters
+    auto post_wave = [ & ]( uint64_t rays_base ) -> int
+    {
+        ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
+        ACN_CUDA( cudaStreamSynchronize( st ) );
+        if( h_ctr->overflow ) { set_error( "wavefront queue overflow (code %d): raise acn_options.wave_budget", h_ctr->overflow ); return ACN_ERR_OUT_OF_MEMORY; }
+        const uint64_t new_tasks = h_ctr->tasks_new, new_path = h_ctr->tasks_new_path;
+        stat_sum[ ST_DIFFUSE ] += new_tasks;
+        nr = rays_base + h_ctr->rays_out;
+        if( new_tasks )
+        {
+            Wave<R> w = make_wave( nr, index_base );
+            const unsigned warps = ( unsigned )( ( new_tasks + 31 ) / 32 );
+            k_direct<R><<< grid_for( warps, ACN_BLOCK / 32 ), ACN_BLOCK, smem_bytes, st >>>( w, task_new, new_tasks );
+            launches++;
+            if( new_path )
+            {
+                k_keep<R><<< grid_for( new_tasks, 256 ), 256, 0, st >>>( task_new, new_tasks, task_stack, task_stack_cap, d_ctr );
+                launches++;
+            }
+            ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
+            ACN_CUDA( cudaStreamSynchronize( st ) );
+            if( h_ctr->overflow ) { set_error( "wavefront queue overflow (code %d): raise acn_options.wave_budget", h_ctr->overflow ); return ACN_ERR_OUT_OF_MEMORY; }
+            nt = h_ctr->task_stack >> ACN_TASK_SHIFT;
+            nt_cum = h_ctr->task_stack & ACN_TASK_MASK;
+        }
+        // reset the per-wave counters (stats keep accumulating on the device)
+        ACN_CUDA( cudaMemsetAsync( d_ctr, 0, offsetof( Counters, task_stack ), st ) );
+        waves++;
+        return ACN_OK;
+    };
+
+    for( uint64_t first = 0; first < n && result == ACN_OK; first += budget )
+    {
+        const uint64_t cnt = ( n - first < budget ) ? n - first : budget;
+        {
+            Wave<R> w = make_wave( 0, index_base );
+            k_primary<R><<< grid_for( cnt, ACN_BLOCK ), ACN_BLOCK, smem_bytes, st >>>( w, d_xy, first, cnt );
+            launches++;
+            if( ( result = post_wave( 0 ) ) ) break;
+        }
+        while( nr > 0 || nt > 0 )
+        {
+            if( cancel && *cancel ) { result = ACN_ERR_CANCELLED; break; }
+            if( nr > 0 )
+            {
+                // pop the top `take` rays into ray_cur
+                const uint64_t take = nr < budget ? nr : budget;
+                const uint64_t base = nr - take;
+                ACN_CUDA( cudaMemcpyAsync( ray_cur.o_i, ray_stack.o_i + base, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( ray_cur.d_, ray_stack.d_ + base, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( ray_cur.tp, ray_stack.tp + base, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( ray_cur.meta, ray_stack.meta + base, take * sizeof( I4 ), cudaMemcpyDeviceToDevice, st ) );
+                Wave<R> w = make_wave( base, index_base );
+                k_rays<R><<< grid_for( take, ACN_BLOCK ), ACN_BLOCK, smem_bytes, st >>>( w, ray_cur, take );
+                launches++;
+                if( ( result = post_wave( base ) ) ) break;
+            }
+            else
+            {
+                // cut the top of the task stack at an exact budget of path children
+                uint64_t start = 0, cum_before = 0;
+                if( nt_cum > budget )
+                {
+                    k_plan<<< 1, 32, 0, st >>>( task_stack.cum, nt, budget, d_ctr );
+                    launches++;
+                    ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
+                    ACN_CUDA( cudaStreamSynchronize( st ) );
+                    start = h_ctr->plan_start; cum_before = h_ctr->plan_cum;
+                }
+                const uint64_t take = nt - start;
+                // the popped slice moves to task_cur; the stack counter is rewound to the cut
+                ACN_CUDA( cudaMemcpyAsync( task_cur.pos_id, task_stack.pos_id + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( task_cur.nrm_ci, task_stack.nrm_ci + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( task_cur.prj_a, task_stack.prj_a + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( task_cur.tpc_b, task_stack.tpc_b + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( task_cur.meta, task_stack.meta + start, take * sizeof( I4 ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( task_cur.rv0, task_stack.rv0 + start, take * sizeof( u64 ), cudaMemcpyDeviceToDevice, st ) );
+                ACN_CUDA( cudaMemcpyAsync( task_cur.key, task_stack.key + start, take * sizeof( u64 ), cudaMemcpyDeviceToDevice, st ) );
+                nt = start; nt_cum = cum_before;
+                h_ctr->task_stack = ( ( unsigned long long )nt << ACN_TASK_SHIFT ) | nt_cum;
+                ACN_CUDA( cudaMemcpyAsync( &d_ctr->task_stack, &h_ctr->task_stack, sizeof( unsigned long long ), cudaMemcpyHostToDevice, st ) );
+                Wave<R> w = make_wave( 0, index_base );
+                const unsigned warps = ( unsigned )( ( take + 31 ) / 32 );
+                k_path<R><<< grid_for( warps, ACN_BLOCK / 32 ), ACN_BLOCK, smem_bytes, st >>>( w, task_cur, take );
+                launches++;
+                if( ( result = post_wave( 0 ) ) ) break;
+            }
+        }
+    }
+
+    if( result == ACN_OK )
+    {
+        k_finish<R><<< grid_for( n * 3, 256 ), 256, 0, st >>>( d_accum, n, prm.gamma, d_rgb );
+        launches++;
+    }
+    ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
+    ACN_CUDA( cudaEventRecord( ev1, st ) );
+    ACN_CUDA( cudaStreamSynchronize( st ) );
+    cudaError_t le = cudaGetLastError();
+    if( le != cudaSuccess ) { set_error( "kernel failure: %s", cudaGetErrorString( le ) ); result = ACN_ERR_CUDA; }
+    float ms = 0; cudaEventElapsedTime( &ms, ev0, ev1 );
+    cudaEventDestroy( ev0 ); cudaEventDestroy( ev1 );
+    for( int i = 0; i < ST_COUNT; i++ ) if( i != ST_DIFFUSE ) stat_sum[ i ] = h_ctr->stats[ i ];
+    if( stats )
+    {
+        stats->samples = n;
+        stats->rays_primary = stat_sum[ ST_PRIMARY ]; stats->rays_reflection = stat_sum[ ST_REFLECT ];
+        stats->rays_chromatic = stat_sum[ ST_CHROMATIC ]; stats->rays_refraction = stat_sum[ ST_REFRACT ];
+        stats->rays_path = stat_sum[ ST_PATH ]; stats->rays_shadow = stat_sum[ ST_SHADOW ];
+        stats->rays_light = stat_sum[ ST_LIGHT ]; stats->diffuse_hits = stat_sum[ ST_DIFFUSE ];
+        stats->kernel_launches = launches; stats->waves = waves; stats->device_ms = ms;
+    }
+    return result;
+}
+
+} // namespace acn
