@@ -149,13 +149,19 @@ template <typename R> ACN_HD R prim_hit( const SceneView<R>& sv, int kind, int n
         R a;
         if( f != R( 0 ) )
         {
+            // s*s - q cancels catastrophically in FP32 when the origin is far from the quadric
+            // (both terms ~ |p|^2): re-expand the quadratic around the point of closest approach
+            // pm = p + t0*d, where its coefficients are of the size of the object.
             R fi = R( 1 ) / f;
-            R s = fs * fi, q = fq * fi;
+            R t0 = -fs * fi;
+            V3<R> pm = madd( p, d, t0 );
+            R s = dot( ad, pm ) * fi;                                                  // ~ 0
+            R q = ( qa * pm.x * pm.x + qb * pm.y * pm.y + qc * pm.z * pm.z + qr ) * fi;
             R r = s * s - q;
             if( r < R( 0 ) ) return inf;
             r = r_sqrt( r );
-            a = -s - r;
-            if( a < R( 0 ) ) a = -s + r;
+            a = t0 - s - r;
+            if( a < R( 0 ) ) a = t0 - s + r;
             if( a < R( 0 ) ) return inf;
         }
         else
@@ -217,11 +223,28 @@ template <typename R> ACN_HD R prim_hit( const SceneView<R>& sv, int kind, int n
             if( nor )
             {
                 V3<R> p = madd( lp, ld, offs1 );
-                R d0 = dist_fn( kind, ex_radius, p );
                 V3<R> g;
-                g.x = ( dist_fn( kind, ex_radius, v3<R>( p.x + eps, p.y, p.z ) ) - d0 ) / eps;
-                g.y = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y + eps, p.z ) ) - d0 ) / eps;
-                g.z = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y, p.z + eps ) ) - d0 ) / eps;
+                if( sizeof( R ) == 8 )
+                {
+                    // the reference's forward differences with step eps (objects.c:947-953)
+                    R d0 = dist_fn( kind, ex_radius, p );
+                    g.x = ( dist_fn( kind, ex_radius, v3<R>( p.x + eps, p.y, p.z ) ) - d0 ) / eps;
+                    g.y = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y + eps, p.z ) ) - d0 ) / eps;
+                    g.z = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y, p.z + eps ) ) - d0 ) / eps;
+                }
+                else
+                {
+                    // FP32: a difference quotient over eps would carry ~1e-3 rounding noise; both
+                    // distance functions have a closed-form gradient, which the quotient approximates
+                    // to O(eps) — use it.  torus: unit vector from the nearest point of the core circle.
+                    g = p;
+                    if( kind == K_DIST_TORUS )
+                    {
+                        R f = r_sqrt( p.x * p.x + p.y * p.y );
+                        R fi = f > R( 0 ) ? R( 1 ) / f : R( 1 );
+                        g = v3<R>( p.x - p.x * fi, p.y - p.y * fi, p.z );
+                    }
+                }
                 *nor = unit( tmlv( rax, g ) );
             }
             return offs0 + offs1 / inv_scale - eps;
