@@ -584,3 +584,42 @@ def render_image(scene: Scene, tracer: Optional[Tracer] = None, passes: Optional
     if own:
         tracer.close()
     return img, total
+
+
+# ----------------------------------------------------------------------------------------------
+# flat-scene files: the flattened form of a scripted scene as a compressed .npz (own format)
+# ----------------------------------------------------------------------------------------------
+class _OwnedFlat:
+    """Keeps the ctypes buffers of a FlatScene loaded from disk alive."""
+
+
+def save_flat(flat: FlatScene, path: str, name: str = ""):
+    fs = flat.struct
+    nodes = np.frombuffer(C.string_at(fs.nodes, C.sizeof(FlatNode) * fs.n_nodes), dtype=np.uint8)
+    mats = np.frombuffer(C.string_at(fs.materials, C.sizeof(FlatMaterial) * fs.n_materials), dtype=np.uint8)
+    children = np.ctypeslib.as_array(fs.children, shape=(max(fs.n_children, 1),))[: fs.n_children].copy()
+    params = np.frombuffer(C.string_at(C.byref(fs.params), C.sizeof(FlatParams)), dtype=np.uint8)
+    np.savez_compressed(path, nodes=nodes, materials=mats, children=children.astype(np.int32), params=params,
+                        roots=np.array([fs.light_root, fs.matter_root], dtype=np.int32),
+                        sizes=np.array([C.sizeof(FlatNode), C.sizeof(FlatMaterial), C.sizeof(FlatParams)], dtype=np.int32),
+                        name=np.array(name))
+
+
+def load_flat(path: str) -> FlatScene:
+    z = np.load(path)
+    assert list(z["sizes"]) == [C.sizeof(FlatNode), C.sizeof(FlatMaterial), C.sizeof(FlatParams)], "flat-scene ABI changed"
+    own = _OwnedFlat()
+    n_nodes = z["nodes"].size // C.sizeof(FlatNode)
+    n_mats = z["materials"].size // C.sizeof(FlatMaterial)
+    own.nodes = (FlatNode * n_nodes).from_buffer_copy(z["nodes"].tobytes())
+    own.mats = (FlatMaterial * max(n_mats, 1)).from_buffer_copy(z["materials"].tobytes().ljust(C.sizeof(FlatMaterial), b"\0"))
+    ch = z["children"].astype(np.int32)
+    own.children = (C.c_int32 * max(len(ch), 1))(*ch.tolist())
+    own.fs = FlatSceneStruct()
+    C.memmove(C.byref(own.fs.params), z["params"].tobytes(), C.sizeof(FlatParams))
+    own.fs.n_nodes, own.fs.n_children, own.fs.n_materials = n_nodes, len(ch), n_mats
+    own.fs.light_root, own.fs.matter_root = int(z["roots"][0]), int(z["roots"][1])
+    own.fs.nodes = C.cast(own.nodes, C.POINTER(FlatNode))
+    own.fs.children = C.cast(own.children, C.POINTER(C.c_int32))
+    own.fs.materials = C.cast(own.mats, C.POINTER(FlatMaterial))
+    return FlatScene(C.pointer(own.fs), own)

@@ -155,3 +155,21 @@ def csg_zoo(width=160, height=120, direct_samples=6, path_samples=0) -> Scene:
     for o in (l1, l2, floor, cube, lens, bell, egg, ring, cmp):
         sc.push(o)
     return sc
+
+
+def load(name: str, **overrides):
+    """Loads scenes/<name>.npz (a scripted reference scene flattened by tools/make_scenes.py) and applies
+    render-parameter overrides (image_width=..., direct_samples=..., ...).  Returns a FlatScene."""
+    import os
+    from . import api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    flat = api.load_flat(os.path.join(root, "scenes", name + ".npz"))
+    prm = flat.params
+    for k, v in overrides.items():
+        cur = getattr(prm, k)
+        if hasattr(cur, "__len__"):
+            for i in range(len(cur)):
+                cur[i] = float(v[i])
+        else:
+            setattr(prm, k, v)
+    return flat
