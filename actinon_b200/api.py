@@ -24,6 +24,7 @@ SEED_POSITION_HASH = 0
 SEED_INDEX_KEYED = 1
 PRECISION_F32 = 0
 PRECISION_F64 = 1
+CSG_AUTO, CSG_INTERVALS, CSG_MARCH = 0, 1, 2
 
 (KIND_COMPOUND, KIND_PLANE, KIND_SPHERE, KIND_SQUAROID, KIND_DIST_SPHERE, KIND_DIST_TORUS,
  KIND_PAIR_INSIDE, KIND_PAIR_OUTSIDE, KIND_NEG, KIND_SCALE) = range(10)
@@ -82,12 +83,13 @@ class FlatSceneStruct(C.Structure):
 class Options(C.Structure):
     _fields_ = [
         ("seed_mode", C.c_int32), ("precision", C.c_int32), ("eps", C.c_double),
-        ("wave_budget", C.c_int64), ("device", C.c_int32), ("reserved", C.c_int32),
+        ("wave_budget", C.c_int64), ("device", C.c_int32), ("csg_mode", C.c_int32),
     ]
 
-    def __init__(self, seed_mode=SEED_POSITION_HASH, precision=PRECISION_F32, eps=0.0, wave_budget=0, device=-1):
+    def __init__(self, seed_mode=SEED_POSITION_HASH, precision=PRECISION_F32, eps=0.0, wave_budget=0, device=-1, csg_mode=0):
         super().__init__()
         self.seed_mode, self.precision, self.eps, self.wave_budget, self.device = seed_mode, precision, eps, wave_budget, device
+        self.csg_mode = csg_mode
 
 
 class Stats(C.Structure):
@@ -96,7 +98,7 @@ class Stats(C.Structure):
         ("rays_chromatic", C.c_uint64), ("rays_refraction", C.c_uint64), ("rays_path", C.c_uint64),
         ("rays_shadow", C.c_uint64), ("rays_light", C.c_uint64), ("diffuse_hits", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("waves", C.c_uint64), ("device_ms", C.c_double),
-        ("reserved", C.c_double * 4),
+        ("kernel_ms", C.c_double * 4), ("kernel_launches_by_class", C.c_uint64 * 4),
     ]
 
     @property
@@ -105,7 +107,9 @@ class Stats(C.Structure):
                 + self.rays_path + self.rays_shadow)
 
     def as_dict(self) -> dict:
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("kernel_")}
+        d["kernel_ms"] = list(self.kernel_ms)
+        d["kernel_launches_by_class"] = list(self.kernel_launches_by_class)
         d["rays"] = self.rays
         return d
 
@@ -574,7 +578,7 @@ def render_image(scene: Scene, tracer: Optional[Tracer] = None, passes: Optional
         img.push(xy, rgb)
         st = tracer.last_stats
         for k, _ in Stats._fields_:
-            if k != "reserved":
+            if not k.startswith("kernel_"):
                 setattr(total, k, getattr(total, k) + getattr(st, k))
         if pnm_path:
             h = img.write_pnm(pnm_path)

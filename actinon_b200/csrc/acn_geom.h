@@ -31,6 +31,8 @@ enum { F_ENV = 1, F_ROUGH = 2 };
 enum { GEO_STRIDE = 5 };
 enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
 enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
+enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5 };   // instr = op | node << 4; CSG_ENV is followed by a skip count
+enum { CSG_K = 8, CSG_S = 8 };   // events per interval list, lists on the evaluation stack
 
 template <typename R> struct SceneView
 {
@@ -38,6 +40,9 @@ template <typename R> struct SceneView
     const I4*    link;
     const R4<R>* geo;
     const int*   children;
+    const int*   prog;      // postfix CSG programs (interval evaluator), see csg_fast_hit
+    const int*   prog_ref;  // per node: [2n] start into prog, [2n+1] length (0: no program -> reference march)
+    const int*   parent;    // per node: CSG parent (-1 at the top of an object)
     R   eps;            // shell thickness (f3_eps, vectors.h:33)
     int light_root;
     int matter_root;
@@ -330,11 +335,205 @@ template <typename R> ACN_HDN R pair_hit( const SceneView<R>& sv, int o1, int o2
     return inf;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CSG by interval lists.  The reference finds the first boundary of A&B / A|B by an alternating
+// march over the children (objects.c:1052-1094,1209-1251), re-tracing whole subtrees for every
+// rejected candidate: O(n^2) ray tests for an n-leaf solid and hopelessly divergent on a GPU.
+// The same first boundary comes out of classifying the ray against every leaf ONCE:
+//   * a leaf yields its state at the origin and its (<= 2) crossings for t > 0;
+//   * '!' complements, '&' intersects, '|' unites the in/out state sequences (merge of two short
+//     sorted lists, keeping only the crossings where the combined state flips);
+//   * a node's envelope clips its inside-set (obj_side reports "outside" beyond the own envelope,
+//     objects.c:365-370, also for negations) with VIRTUAL crossings that are never reported as hits
+//     (obj_ray_hit only returns shape crossings), and gates the whole subtree (objects.c:264).
+// A crossing of leaf X survives to the root exactly when every sibling on the way up is in the state
+// the pair demands — the reference's acceptance test.  Programs are postfix, ordered so that the
+// deeper operand is evaluated first (stack depth = Strahler number of the tree).
+// Supported leaves: plane, sphere, squaroid.  Objects with distance-field or scale nodes keep the
+// reference march.
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct IvStack
+{
+    R   t[ CSG_S ][ CSG_K ];
+    int id[ CSG_S ][ CSG_K ];
+    int n[ CSG_S ];
+    int s0[ CSG_S ];     // 1: inside at the ray origin
+    R   t_valid;         // crossings beyond this parameter are unreliable (a list overflowed CSG_K)
+};
+
+// crossings of a sphere for t > 0 and the state at the origin
+template <typename R> ACN_HD int sphere_events( V3<R> c, R r, const Ray<R>& ray, int* s0, R* t )
+{
+    V3<R> p = ray.p - c;
+    R s = dot( p, ray.d );
+    R q = sqr( p ) - r * r;
+    V3<R> l = p - ray.d * s;
+    R disc = r * r - sqr( l );
+    *s0 = q > R( 0 ) ? 0 : 1;
+    if( disc < R( 0 ) ) return 0;
+    R sq = r_sqrt( disc );
+    if( q > R( 0 ) )
+    {
+        if( !( s < R( 0 ) ) ) return 0;
+        t[ 0 ] = -s - sq; t[ 1 ] = -s + sq;
+        return 2;
+    }
+    if( s < R( 0 ) || q < R( 0 ) ) { t[ 0 ] = -s + sq; return 1; }
+    return 0;
+}
+
+template <typename R> ACN_HD int leaf_events( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, int* s0, R* t )
+{
+    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
+    const V3<R> pos = xyz( g0 );
+    if( kind == K_SPHERE ) return sphere_events( pos, g0.w, ray, s0, t );
+    if( kind == K_PLANE )
+    {
+        V3<R> nz = xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
+        R g = dot( ray.p - pos, nz );
+        R dn = dot( nz, ray.d );
+        *s0 = g > R( 0 ) ? 0 : 1;
+        if( dn == R( 0 ) ) return 0;
+        R t0 = -g / dn;
+        if( t0 > R( 0 ) ) { t[ 0 ] = t0; return 1; }
+        return 0;
+    }
+    // squaroid
+    const M3<R> rax = node_rax( sv, n );
+    const R qa = g0.w, qb = sv.geo[ n * GEO_STRIDE + 1 ].w, qc = sv.geo[ n * GEO_STRIDE + 2 ].w, qr = sv.geo[ n * GEO_STRIDE + 3 ].w;
+    V3<R> p = mlv( rax, ray.p - pos );
+    V3<R> d = mlv( rax, ray.d );
+    V3<R> ad = v3<R>( qa * d.x, qb * d.y, qc * d.z );
+    R f = dot( ad, d ), fs = dot( ad, p );
+    R fq = qa * p.x * p.x + qb * p.y * p.y + qc * p.z * p.z + qr;
+    *s0 = fq > R( 0 ) ? 0 : 1;
+    if( f == R( 0 ) ) return 0;
+    R fi = R( 1 ) / f;
+    R t0 = -fs * fi;
+    V3<R> pm = madd( p, d, t0 );
+    R s = dot( ad, pm ) * fi;
+    R q = ( qa * pm.x * pm.x + qb * pm.y * pm.y + qc * pm.z * pm.z + qr ) * fi;
+    R r = s * s - q;
+    if( r < R( 0 ) ) return 0;
+    r = r_sqrt( r );
+    R ta = t0 - s - r, tb = t0 - s + r;
+    int c = 0;
+    if( ta >= R( 0 ) ) t[ c++ ] = ta;
+    if( tb >= R( 0 ) ) t[ c++ ] = tb;
+    return c;
+}
+
+// outward normal of a leaf at ray parameter t (the unshortened crossing), as its fp_ray_hit reports it
+template <typename R> ACN_HD V3<R> leaf_normal( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, R t )
+{
+    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
+    const V3<R> pos = xyz( g0 );
+    if( kind == K_PLANE ) return xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
+    if( kind == K_SPHERE ) return unit( madd( ray.p - pos, ray.d, t - sv.eps ) );
+    const M3<R> rax = node_rax( sv, n );
+    V3<R> p = mlv( rax, ray.p - pos );
+    V3<R> d = mlv( rax, ray.d );
+    V3<R> x = madd( p, d, t );
+    return unit( tmlv( rax, v3<R>( x.x * g0.w, x.y * sv.geo[ n * GEO_STRIDE + 1 ].w, x.z * sv.geo[ n * GEO_STRIDE + 2 ].w ) ) );
+}
+
+// combine the two topmost lists: op_and ? intersection : union
+template <typename R> ACN_HD void iv_merge( IvStack<R>& st, int a, int b, bool op_and )
+{
+    R   ot[ CSG_K ];
+    int oi[ CSG_K ];
+    int sa = st.s0[ a ], sb = st.s0[ b ];
+    int s = op_and ? ( sa & sb ) : ( sa | sb );
+    const int s_init = s;
+    const int na = st.n[ a ], nb = st.n[ b ];
+    int i = 0, j = 0, o = 0;
+    while( i < na || j < nb )
+    {
+        bool take_a = j >= nb || ( i < na && st.t[ a ][ i ] <= st.t[ b ][ j ] );
+        R t; int id;
+        if( take_a ) { t = st.t[ a ][ i ]; id = st.id[ a ][ i ]; i++; sa ^= 1; }
+        else         { t = st.t[ b ][ j ]; id = st.id[ b ][ j ]; j++; sb ^= 1; }
+        int s2 = op_and ? ( sa & sb ) : ( sa | sb );
+        if( s2 != s ) { if( o < CSG_K ) { ot[ o ] = t; oi[ o ] = id; } o++; s = s2; }
+    }
+    if( o > CSG_K ) { o = CSG_K; st.t_valid = r_min( st.t_valid, ot[ CSG_K - 1 ] ); }   // exact up to the last kept crossing
+    st.s0[ a ] = s_init; st.n[ a ] = o;
+    for( int k = 0; k < o; k++ ) { st.t[ a ][ k ] = ot[ k ]; st.id[ a ][ k ] = oi[ k ]; }
+}
+
+template <typename R> ACN_NOINLINE R csg_fast_hit( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+{
+    IvStack<R> st;
+    st.t_valid = Num<R>::inf();
+    int sp = 0;
+    const int start = sv.prog_ref[ 2 * root ], len = sv.prog_ref[ 2 * root + 1 ];
+    for( int pc = start; pc < start + len; pc++ )
+    {
+        const int ins = sv.prog[ pc ];
+        const int op = ins & 15, n = ins >> 4;
+        if( op == CSG_LEAF )
+        {
+            R t[ 2 ]; int s0;
+            const int c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, t );
+            st.s0[ sp ] = s0; st.n[ sp ] = c;
+            for( int k = 0; k < c; k++ ) { st.t[ sp ][ k ] = t[ k ]; st.id[ sp ][ k ] = n; }
+            sp++;
+        }
+        else if( op == CSG_NEG ) st.s0[ sp - 1 ] ^= 1;
+        else if( op == CSG_AND || op == CSG_OR ) { iv_merge( st, sp - 2, sp - 1, op == CSG_AND ); sp--; }
+        else if( op == CSG_ENV )
+        {
+            const int skip = sv.prog[ ++pc ];
+            if( !envelope_hits( sv.env[ n ], ray ) ) { st.s0[ sp ] = 0; st.n[ sp ] = 0; sp++; pc += skip; }
+        }
+        else    // CSG_CLIP: inside-set limited to the own envelope, with virtual crossings
+        {
+            const R4<R> e = sv.env[ n ];
+            R t[ 2 ]; int s0;
+            const int c = sphere_events( xyz( e ), e.w, ray, &s0, t );
+            st.s0[ sp ] = s0; st.n[ sp ] = c;
+            for( int k = 0; k < c; k++ ) { st.t[ sp ][ k ] = t[ k ]; st.id[ sp ][ k ] = -1; }
+            iv_merge( st, sp - 1, sp, true );
+        }
+    }
+    // first real crossing
+    for( int k = 0; k < st.n[ 0 ]; k++ )
+    {
+        const int leaf = st.id[ 0 ][ k ];
+        if( leaf < 0 ) continue;
+        const R t = st.t[ 0 ][ k ];
+        if( t > st.t_valid ) break;
+        const R a = t - sv.eps;
+        if( nor )
+        {
+            V3<R> nn = leaf_normal( sv, node_kind( sv.link[ leaf ] ), leaf, ray, t );
+            // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
+            for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
+            {
+                const I4 lk = sv.link[ m ];
+                if( node_kind( lk ) == K_NEG ) nn = -nn;
+                if( node_flags( lk ) & F_ROUGH ) roughen( sv, m, ray, a, &nn, ctx );
+            }
+            if( node_kind( sv.link[ root ] ) == K_NEG ) nn = -nn;
+            *nor = nn;
+        }
+        return a;
+    }
+    if( st.t_valid < Num<R>::inf() ) return R( -2 ) * Num<R>::mag();     // overflow: the caller falls back to the reference march
+    return Num<R>::inf();
+}
+
 // fp_ray_hit dispatch without the own-envelope test and without roughness
 template <typename R> ACN_HD R shape_hit( const SceneView<R>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     const int kind = node_kind( lk );
     if( kind <= K_DIST_TORUS ) return prim_hit( sv, kind, n, ray, nor );
+    if( sv.prog_ref && sv.prog_ref[ 2 * n + 1 ] > 0 )
+    {
+        R a = csg_fast_hit( sv, n, ray, nor, ctx );
+        if( a > -Num<R>::mag() ) return a;
+    }
     if( kind == K_PAIR_INSIDE )  return pair_hit( sv, lk.y, lk.z, -1, ray, nor, ctx );
     if( kind == K_PAIR_OUTSIDE ) return pair_hit( sv, lk.y, lk.z, +1, ray, nor, ctx );
     if( kind == K_NEG )                                                                  // objects.c:1329-1339

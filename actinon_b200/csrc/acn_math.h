@@ -12,9 +12,11 @@
 #if defined(__CUDACC__)
 #define ACN_HD  __host__ __device__ __forceinline__
 #define ACN_HDN __host__ __device__
+#define ACN_NOINLINE __host__ __device__ __noinline__
 #else
 #define ACN_HD  inline
 #define ACN_HDN
+#define ACN_NOINLINE
 #endif
 
 namespace acn {

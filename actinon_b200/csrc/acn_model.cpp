@@ -309,6 +309,7 @@ struct HostView
             g[ 4 ].x = nd.surface_roughness; g[ 4 ].y = g[ 4 ].z = g[ 4 ].w = 0;
         }
         sv.env = env.data(); sv.geo = geo.data(); sv.link = link.data(); sv.children = children.empty() ? nullptr : children.data();
+        sv.prog = nullptr; sv.prog_ref = nullptr; sv.parent = nullptr;
         sv.eps = eps; sv.light_root = 0; sv.matter_root = 0; sv.seed_mode = acn::SEED_POSITION_HASH;
     }
 };

@@ -104,6 +104,7 @@ void acn_options_default( acn_options* opt )
     opt->eps = 0;
     opt->wave_budget = 0;
     opt->device = -1;
+    opt->csg_mode = ACN_CSG_AUTO;
 }
 
 int acn_device_count( void )

@@ -67,7 +67,7 @@ template <typename R> struct DParams
     const DMat<R>*   mats;
     const DLight<R>* lights;
     int   n_lights;
-    int   n_nodes, n_children;
+    int   n_nodes, n_children, n_prog;
     int   width, height;
     R     gamma;
     V3<R> background;
@@ -77,6 +77,7 @@ template <typename R> struct DParams
     int   direct_samples, path_samples;
     R     min_intensity;
     R     max_path_length;
+    R     eps_rel;                            // per-ray shell thickness = max( sv.eps, eps_rel * |origin|_inf ); 0: constant
     int   stage_bytes;                        // node table bytes staged into shared memory (0: none)
     const u64* skipA;                         // LCG skip table: state after 2k steps = s*A[k] + C[k]
     const u64* skipC;
@@ -181,11 +182,20 @@ template <typename R> __device__ __forceinline__ void stage_scene( DParams<R>& p
     R4<R>* s_geo  = s_env + n;
     I4*    s_link = reinterpret_cast<I4*>( s_geo + n * GEO_STRIDE );
     int*   s_chl  = reinterpret_cast<int*>( s_link + n );
-    for( int i = threadIdx.x; i < n; i += blockDim.x ) { s_env[ i ] = prm.sv.env[ i ]; s_link[ i ] = prm.sv.link[ i ]; }
+    int*   s_pref = s_chl + prm.n_children;
+    int*   s_par  = s_pref + 2 * n;
+    int*   s_prog = s_par + n;
+    for( int i = threadIdx.x; i < n; i += blockDim.x )
+    {
+        s_env[ i ] = prm.sv.env[ i ]; s_link[ i ] = prm.sv.link[ i ];
+        s_pref[ 2 * i ] = prm.sv.prog_ref[ 2 * i ]; s_pref[ 2 * i + 1 ] = prm.sv.prog_ref[ 2 * i + 1 ]; s_par[ i ] = prm.sv.parent[ i ];
+    }
     for( int i = threadIdx.x; i < n * GEO_STRIDE; i += blockDim.x ) s_geo[ i ] = prm.sv.geo[ i ];
     for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_chl[ i ] = prm.sv.children[ i ];
+    for( int i = threadIdx.x; i < prm.n_prog; i += blockDim.x ) s_prog[ i ] = prm.sv.prog[ i ];
     __syncthreads();
     prm.sv.env = s_env; prm.sv.geo = s_geo; prm.sv.link = s_link; prm.sv.children = s_chl;
+    prm.sv.prog_ref = s_pref; prm.sv.parent = s_par; prm.sv.prog = s_prog;
 }
 
 // obj_color (objects.c:411-422) with txm_plain / txm_chess (textures.c:99-102,142-148)
@@ -199,6 +209,16 @@ template <typename R> __device__ __forceinline__ V3<R> obj_color( const DParams<
     long long x = llrint( ( double )( u * m.tex_scale ) );
     long long y = llrint( ( double )( v * m.tex_scale ) );
     return ( ( x ^ y ) & 1 ) ? v3<R>( m.tex1[ 0 ], m.tex1[ 1 ], m.tex1[ 2 ] ) : v3<R>( m.tex2[ 0 ], m.tex2[ 1 ], m.tex2[ 2 ] );
+}
+
+// The reference's shell thickness is an absolute 1e-6 in FP64.  In FP32 a hit distance carries an error
+// of a few ulp of the ray origin's magnitude, so the product path scales the shell with the origin
+// (16 ulp) and never goes below the reference's 1e-6; see DESIGN.md "eps".
+template <typename R> __device__ __forceinline__ SceneView<R> ray_view( const DParams<R>& prm, V3<R> o )
+{
+    SceneView<R> sv = prm.sv;
+    if( prm.eps_rel > R( 0 ) ) sv.eps = r_max( sv.eps, prm.eps_rel * r_max( r_max( r_abs( o.x ), r_abs( o.y ) ), r_abs( o.z ) ) );
+    return sv;
 }
 
 template <typename R> __device__ __forceinline__ u64 skip2( const DParams<R>& prm, u64 s, unsigned long long k )
@@ -224,7 +244,7 @@ template <typename R> __device__ __forceinline__ void emit_ray( const Wave<R>& w
 // ---------------------------------------------------------------------------------------------
 // scene_s_lum (scene.c:420-667) for one hit: emits child rays and at most one diffuse task.
 // ---------------------------------------------------------------------------------------------
-template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>& ray, R a, const Trans<R>& tr,
+template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>& ray, R a, R hit_eps, const Trans<R>& tr,
                                                  int depth, R I, V3<R> tp, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
@@ -313,7 +333,7 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
 
     if( T && I >= prm.min_intensity )                                                    // scene.c:633-653
     {
-        emit_ray( w, madd( ray.p, ray.d, a + R( 2 ) * prm.sv.eps ), refract( ray.d, tr.exit_nor, nrel ), I, depth - 1, tp,
+        emit_ray( w, madd( ray.p, ray.d, a + R( 2 ) * hit_eps ), refract( ray.d, tr.exit_nor, nrel ), I, depth - 1, tp,
                   RC_REFRACT, sample, mix64( key, KEY_REFRACT ) );
     }
 }
@@ -328,16 +348,17 @@ template <typename R> __device__ void trace_ray( const Wave<R>& w, const Ray<R>&
     const DParams<R>& prm = w.prm;
     const R inf = Num<R>::inf();
     HitCtx ctx; ctx.key = key;
+    const SceneView<R> sv = ray_view( prm, ray.p );
     if( probe && cls != RC_PATH )
     {
-        R a = compound_ray_hit<R>( prm.sv, prm.sv.light_root, ray, nullptr, nullptr, ctx, inf );
-        if( !( a < inf ) ) a = compound_ray_hit<R>( prm.sv, prm.sv.matter_root, ray, nullptr, nullptr, ctx, inf );
+        R a = compound_ray_hit<R>( sv, sv.light_root, ray, nullptr, nullptr, ctx, inf );
+        if( !( a < inf ) ) a = compound_ray_hit<R>( sv, sv.matter_root, ray, nullptr, nullptr, ctx, inf );
         if( !( a < inf ) ) add_sample( w, sample, mul( prm.background, tp ) * I );
         return;
     }
     if( probe )     // path child that cannot contribute on a hit: is anything closer than max_path_length?
     {
-        R a = compound_ray_hit<R>( prm.sv, prm.sv.matter_root, ray, nullptr, nullptr, ctx, prm.max_path_length );
+        R a = compound_ray_hit<R>( sv, sv.matter_root, ray, nullptr, nullptr, ctx, prm.max_path_length );
         if( !( a < prm.max_path_length ) ) add_sample( w, sample, mul( prm.background, tp ) * I );
         return;
     }
@@ -346,15 +367,18 @@ template <typename R> __device__ void trace_ray( const Wave<R>& w, const Ray<R>&
     R a;
     if( cls == RC_PATH )
     {
-        a = compound_trans_hit( prm.sv, prm.sv.matter_root, ray, &tr, ctx );
+        a = compound_trans_hit( sv, sv.matter_root, ray, &tr, ctx );
         if( !( a < prm.max_path_length ) ) { add_sample( w, sample, mul( prm.background, tp ) * I ); return; }
     }
     else
     {
-        a = scene_trans_hit( prm.sv, ray, &tr, ctx );
+        a = scene_trans_hit( sv, ray, &tr, ctx );
         if( !( a < inf ) ) { add_sample( w, sample, mul( prm.background, tp ) * I ); return; }
     }
-    shade_hit( w, ray, a, tr, depth, I, tp, sample, key );
+    // the hit distance itself is only good to a few ulp of its magnitude: keep the shading point that far in front
+    const R hit_eps = r_max( sv.eps, prm.eps_rel * a );
+    a -= hit_eps - sv.eps;
+    shade_hit( w, ray, a, hit_eps, tr, depth, I, tp, sample, key );
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -451,8 +475,9 @@ k_direct( Wave<R> w, TaskBuf<R> in, unsigned long long count )
             const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
             const DLight<R>& lg = prm.lights[ li ];
 
+            const SceneView<R> sv = ray_view( prm, pos );
             V3<R> axis; R cos_rs;
-            obj_fov( prm.sv, lg.node, pos, &axis, &cos_rs );
+            obj_fov( sv, lg.node, pos, &axis, &cos_rs );
             const Basis<R> bs = basis_con_z( axis );
             const R h = R( 1 ) - cos_rs;                                                 // areal_coverage, vectors.h:362
             u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )li * nd + j );
@@ -463,12 +488,12 @@ k_direct( Wave<R> w, TaskBuf<R> in, unsigned long long count )
             {
                 HitCtx ctx; ctx.key = 0;
                 n_shadow++;
-                R a = obj_ray_hit<R>( prm.sv, lg.node, out, nullptr, ctx );              // scene.c:564
+                R a = obj_ray_hit<R>( sv, lg.node, out, nullptr, ctx );              // scene.c:564
                 if( a < Num<R>::inf() )
                 {
                     if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, prj );
                     n_shadow++;
-                    R sh = compound_ray_hit<R>( prm.sv, prm.sv.matter_root, out, nullptr, nullptr, ctx, a );   // scene.c:569
+                    R sh = compound_ray_hit<R>( sv, sv.matter_root, out, nullptr, nullptr, ctx, a );   // scene.c:569
                     if( sh > a )
                     {
                         V3<R> hp = madd( out.p, out.d, a );
@@ -679,6 +704,7 @@ template <typename R> struct Tracer : TracerBase
     DParams<R> prm;
     // device copies of the scene tables
     R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr;
+    int* d_prog = nullptr; int* d_prog_ref = nullptr; int* d_parent = nullptr; int n_prog = 0;
     DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
     // queues
@@ -695,6 +721,7 @@ template <typename R> struct Tracer : TracerBase
     {
         cudaSetDevice( device );
         cudaFree( d_env ); cudaFree( d_link ); cudaFree( d_geo ); cudaFree( d_children );
+        cudaFree( d_prog ); cudaFree( d_prog_ref ); cudaFree( d_parent );
         cudaFree( d_mats ); cudaFree( d_lights ); cudaFree( d_skipA ); cudaFree( d_skipC );
         free_rays( ray_stack ); free_rays( ray_cur );
         free_tasks( task_stack ); free_tasks( task_cur ); free_tasks( task_new );
@@ -750,6 +777,97 @@ static int compound_depth( const acn_flat_scene* fs, int n, int guard )
     return 1 + m;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// postfix programs for the interval CSG evaluator (acn_geom.h: csg_fast_hit)
+// ---------------------------------------------------------------------------------------------
+struct CsgBuilder
+{
+    const acn_flat_scene* fs;
+    std::vector<int> prog, prog_ref, parent;
+
+    static bool is_leaf( int k ) { return k == ACN_KIND_PLANE || k == ACN_KIND_SPHERE || k == ACN_KIND_SQUAROID; }
+    static bool is_pair( int k ) { return k == ACN_KIND_PAIR_INSIDE || k == ACN_KIND_PAIR_OUTSIDE; }
+
+    bool eligible( int n, int guard ) const
+    {
+        if( guard > 64 ) return false;
+        const acn_flat_node& nd = fs->nodes[ n ];
+        if( is_leaf( nd.kind ) ) return true;
+        if( is_pair( nd.kind ) ) return eligible( nd.child0, guard + 1 ) && eligible( nd.child1, guard + 1 );
+        if( nd.kind == ACN_KIND_NEG ) return eligible( nd.child0, guard + 1 );
+        return false;
+    }
+
+    // lists needed on the evaluation stack (Sethi-Ullman); a clipped node needs one more for its envelope
+    int need( int n, bool root ) const
+    {
+        const acn_flat_node& nd = fs->nodes[ n ];
+        int v = 1;
+        if( is_pair( nd.kind ) ) { int a = need( nd.child0, false ), b = need( nd.child1, false ); v = a == b ? a + 1 : ( a > b ? a : b ); }
+        else if( nd.kind == ACN_KIND_NEG ) v = need( nd.child0, false );
+        if( nd.has_envelope && !root && v < 2 ) v = 2;
+        return v;
+    }
+
+    void emit( int n, bool root )
+    {
+        const acn_flat_node& nd = fs->nodes[ n ];
+        const bool clip = nd.has_envelope && !root;
+        size_t skip_slot = 0;
+        if( clip ) { prog.push_back( CSG_ENV | ( n << 4 ) ); skip_slot = prog.size(); prog.push_back( 0 ); }
+        if( is_leaf( nd.kind ) ) prog.push_back( CSG_LEAF | ( n << 4 ) );
+        else if( nd.kind == ACN_KIND_NEG ) { parent[ nd.child0 ] = n; emit( nd.child0, false ); prog.push_back( CSG_NEG | ( n << 4 ) ); }
+        else
+        {
+            parent[ nd.child0 ] = n; parent[ nd.child1 ] = n;
+            int a = nd.child0, b = nd.child1;
+            if( need( b, false ) > need( a, false ) ) { int t = a; a = b; b = t; }     // deeper operand first
+            emit( a, false ); emit( b, false );
+            prog.push_back( ( nd.kind == ACN_KIND_PAIR_INSIDE ? CSG_AND : CSG_OR ) | ( n << 4 ) );
+        }
+        if( clip ) { prog.push_back( CSG_CLIP | ( n << 4 ) ); prog[ skip_slot ] = ( int )( prog.size() - 1 - skip_slot ); }
+    }
+
+    void set_parents( int n, int guard )
+    {
+        if( guard > 64 ) return;
+        const acn_flat_node& nd = fs->nodes[ n ];
+        if( is_pair( nd.kind ) ) { parent[ nd.child0 ] = n; parent[ nd.child1 ] = n; set_parents( nd.child0, guard + 1 ); set_parents( nd.child1, guard + 1 ); }
+        else if( nd.kind == ACN_KIND_NEG || nd.kind == ACN_KIND_SCALE ) { parent[ nd.child0 ] = n; set_parents( nd.child0, guard + 1 ); }
+    }
+
+    void visit_compound( int c, int guard, bool enable )
+    {
+        if( guard > 64 ) return;
+        const acn_flat_node& cn = fs->nodes[ c ];
+        for( int i = 0; i < cn.child1; i++ )
+        {
+            const int n = fs->children[ cn.child0 + i ];
+            const acn_flat_node& nd = fs->nodes[ n ];
+            if( nd.kind == ACN_KIND_COMPOUND ) { visit_compound( n, guard + 1, enable ); continue; }
+            set_parents( n, 0 );
+            if( enable && ( is_pair( nd.kind ) || nd.kind == ACN_KIND_NEG ) && eligible( n, 0 ) && need( n, true ) <= CSG_S && prog_ref[ 2 * n + 1 ] == 0 )
+            {
+                prog_ref[ 2 * n ] = ( int )prog.size();
+                emit( n, true );
+                prog_ref[ 2 * n + 1 ] = ( int )prog.size() - prog_ref[ 2 * n ];
+            }
+        }
+    }
+
+    void build( const acn_flat_scene* scene, bool enable )
+    {
+        fs = scene;
+        prog.clear();
+        prog_ref.assign( ( size_t )fs->n_nodes * 2, 0 );
+        parent.assign( fs->n_nodes, -1 );
+        visit_compound( fs->light_root, 0, enable );
+        visit_compound( fs->matter_root, 0, enable );
+        if( prog.empty() ) prog.push_back( 0 );
+    }
+};
+
 int validate_flat_scene( const acn_flat_scene* fs );   // acn_tracer.cu
 
 template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_options* opt )
@@ -786,14 +904,15 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             for( int k = 0; k < 3; k++ ) scale = fmax( scale, fabs( nd.pos[ k ] ) );
     }
 
-    // ---- shell thickness: the reference's absolute 1e-6 is sub-ulp in FP32 at scene scale ~10, so the
-    // f32 path widens it to 64 ulp of the scene scale (DESIGN.md "eps")
-    double eps = opt->eps;
+    // ---- shell thickness: the reference's absolute 1e-6 (f64 and as the f32 floor); the f32 path adds a
+    // per-ray term of 16 ulp of the ray origin (ray_view) and of the hit distance (trace_ray)
+    double eps = opt->eps, eps_rel = 0;
     if( !( eps > 0 ) )
     {
         eps = 1E-6;
-        if( sizeof( R ) == 4 ) eps = fmax( 1E-6, 64.0 * 1.1920929E-7 * fmax( scale, 1E-3 ) );
+        if( sizeof( R ) == 4 ) eps_rel = 16.0 * 1.1920929E-7;
     }
+    ( void )scale;
 
     cudaError_t ce = cudaSetDevice( device );
     if( ce != cudaSuccess ) { set_error( "cudaSetDevice(%d): %s", device, cudaGetErrorString( ce ) ); return ACN_ERR_NO_DEVICE; }
@@ -807,6 +926,20 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     ACN_CUDA( cudaMemcpy( d_link, link.data(), n * sizeof( I4 ), cudaMemcpyHostToDevice ) );
     ACN_CUDA( cudaMemcpy( d_geo, geo.data(), ( size_t )n * GEO_STRIDE * sizeof( R4<R> ), cudaMemcpyHostToDevice ) );
     if( fs->n_children > 0 ) ACN_CUDA( cudaMemcpy( d_children, fs->children, fs->n_children * sizeof( int ), cudaMemcpyHostToDevice ) );
+
+    // ---- CSG interval programs
+    {
+        const bool fast = opt->csg_mode == ACN_CSG_INTERVALS || ( opt->csg_mode == ACN_CSG_AUTO && sizeof( R ) == 4 );
+        CsgBuilder cb;
+        cb.build( fs, fast );
+        n_prog = ( int )cb.prog.size();
+        if( ( rc = dev_alloc( &d_prog, cb.prog.size() ) ) ) return rc;
+        if( ( rc = dev_alloc( &d_prog_ref, cb.prog_ref.size() ) ) ) return rc;
+        if( ( rc = dev_alloc( &d_parent, cb.parent.size() ) ) ) return rc;
+        ACN_CUDA( cudaMemcpy( d_prog, cb.prog.data(), cb.prog.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
+        ACN_CUDA( cudaMemcpy( d_prog_ref, cb.prog_ref.data(), cb.prog_ref.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
+        ACN_CUDA( cudaMemcpy( d_parent, cb.parent.data(), cb.parent.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
+    }
 
     // ---- materials
     std::vector<DMat<R>> mats( fs->n_materials > 0 ? fs->n_materials : 1 );
@@ -843,6 +976,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             }
         }
         SceneView<double> hv; hv.env = henv.data(); hv.geo = hgeo.data(); hv.link = link.data(); hv.children = fs->children;
+        hv.prog = nullptr; hv.prog_ref = nullptr; hv.parent = nullptr;
         hv.eps = eps; hv.light_root = fs->light_root; hv.matter_root = fs->matter_root; hv.seed_mode = 0;
         for( int i = 0; i < lroot.child1; i++ )
         {
@@ -886,6 +1020,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
 
     // ---- params
     prm.sv.env = d_env; prm.sv.link = d_link; prm.sv.geo = d_geo; prm.sv.children = d_children;
+    prm.sv.prog = d_prog; prm.sv.prog_ref = d_prog_ref; prm.sv.parent = d_parent; prm.n_prog = n_prog;
     prm.sv.eps = ( R )eps; prm.sv.light_root = fs->light_root; prm.sv.matter_root = fs->matter_root;
     prm.sv.seed_mode = opt->seed_mode;
     prm.mats = d_mats; prm.lights = d_lights; prm.n_lights = lroot.child1;
@@ -909,10 +1044,11 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     prm.direct_samples = p.direct_samples; prm.path_samples = p.path_samples;
     prm.min_intensity = ( R )p.trace_min_intensity;
     prm.max_path_length = ( R )p.max_path_length;
+    prm.eps_rel = ( R )eps_rel;
     prm.skipA = d_skipA; prm.skipC = d_skipC; prm.skip_n = skip_n;
 
     // shared-memory staging of the node table
-    size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + sizeof( I4 ) ) + ( size_t )fs->n_children * sizeof( int );
+    size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + sizeof( I4 ) + 3 * sizeof( int ) ) + ( size_t )( fs->n_children + n_prog ) * sizeof( int );
     smem_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
     prm.stage_bytes = smem_bytes;
     if( smem_bytes > 40 * 1024 )
@@ -927,7 +1063,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     max_csg_depth = 0;
     { int a = csg_depth( fs, fs->light_root, 0 ), b = csg_depth( fs, fs->matter_root, 0 ); max_csg_depth = a > b ? a : b; }
     {
-        size_t want = 2048 + ( size_t )max_csg_depth * ( sizeof( R ) == 4 ? 640 : 1024 );
+        size_t want = 8192 + ( size_t )max_csg_depth * ( sizeof( R ) == 4 ? 1024 : 1792 );
         size_t cur = 0;
         cudaDeviceGetLimit( &cur, cudaLimitStackSize );
         if( cur < want ) ACN_CUDA( cudaDeviceSetLimit( cudaLimitStackSize, want ) );
@@ -970,6 +1106,13 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     ACN_CUDA( cudaMemsetAsync( d_ctr, 0, sizeof( Counters ), st ) );
 
     uint64_t launches = 0, waves = 0;
+    // optional per-kernel timing (ACN_PROFILE_KERNELS=1): events around the launches of each kernel class
+    struct KProf { bool on = false; cudaEvent_t a[ 4 ], b[ 4 ]; bool used[ 4 ] = { false, false, false, false }; double ms[ 4 ] = { 0, 0, 0, 0 }; unsigned long long cnt[ 4 ] = { 0, 0, 0, 0 }; } kp;
+    { const char* e = getenv( "ACN_PROFILE_KERNELS" ); kp.on = e && e[ 0 ] == '1'; }
+    if( kp.on ) for( int c = 0; c < 4; c++ ) { cudaEventCreate( &kp.a[ c ] ); cudaEventCreate( &kp.b[ c ] ); }
+    auto kp_begin = [ & ]( int c ) { if( kp.on ) cudaEventRecord( kp.a[ c ], st ); };
+    auto kp_end = [ & ]( int c ) { if( kp.on ) { cudaEventRecord( kp.b[ c ], st ); kp.used[ c ] = true; } };
+    auto kp_collect = [ & ]() { if( kp.on ) for( int c = 0; c < 4; c++ ) if( kp.used[ c ] ) { float m = 0; cudaEventElapsedTime( &m, kp.a[ c ], kp.b[ c ] ); kp.ms[ c ] += m; kp.cnt[ c ]++; kp.used[ c ] = false; } };
     uint64_t nr = 0;                 // rays on the stack
     uint64_t nt = 0, nt_cum = 0;     // tasks on the stack, their total path children
     unsigned long long stat_sum[ ST_COUNT ] = { 0 };
@@ -980,6 +1123,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     {
         ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
         ACN_CUDA( cudaStreamSynchronize( st ) );
+        kp_collect();
         if( h_ctr->overflow ) { set_error( "wavefront queue overflow (code %d): raise acn_options.wave_budget", h_ctr->overflow ); return ACN_ERR_OUT_OF_MEMORY; }
         const uint64_t new_tasks = h_ctr->tasks_new, new_path = h_ctr->tasks_new_path;
         stat_sum[ ST_DIFFUSE ] += new_tasks;
@@ -988,7 +1132,9 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         {
             Wave<R> w = make_wave( nr, index_base );
             const unsigned warps = ( unsigned )( ( new_tasks + 31 ) / 32 );
+            kp_begin( 3 );
             k_direct<R><<< grid_for( warps, ACN_BLOCK / 32 ), ACN_BLOCK, smem_bytes, st >>>( w, task_new, new_tasks );
+            kp_end( 3 );
             launches++;
             if( new_path )
             {
@@ -997,6 +1143,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
             }
             ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
             ACN_CUDA( cudaStreamSynchronize( st ) );
+            kp_collect();
             if( h_ctr->overflow ) { set_error( "wavefront queue overflow (code %d): raise acn_options.wave_budget", h_ctr->overflow ); return ACN_ERR_OUT_OF_MEMORY; }
             nt = h_ctr->task_stack >> ACN_TASK_SHIFT;
             nt_cum = h_ctr->task_stack & ACN_TASK_MASK;
@@ -1012,7 +1159,9 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         const uint64_t cnt = ( n - first < budget ) ? n - first : budget;
         {
             Wave<R> w = make_wave( 0, index_base );
+            kp_begin( 0 );
             k_primary<R><<< grid_for( cnt, ACN_BLOCK ), ACN_BLOCK, smem_bytes, st >>>( w, d_xy, first, cnt );
+            kp_end( 0 );
             launches++;
             if( ( result = post_wave( 0 ) ) ) break;
         }
@@ -1029,7 +1178,9 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
                 ACN_CUDA( cudaMemcpyAsync( ray_cur.tp, ray_stack.tp + base, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
                 ACN_CUDA( cudaMemcpyAsync( ray_cur.meta, ray_stack.meta + base, take * sizeof( I4 ), cudaMemcpyDeviceToDevice, st ) );
                 Wave<R> w = make_wave( base, index_base );
+                kp_begin( 1 );
                 k_rays<R><<< grid_for( take, ACN_BLOCK ), ACN_BLOCK, smem_bytes, st >>>( w, ray_cur, take );
+                kp_end( 1 );
                 launches++;
                 if( ( result = post_wave( base ) ) ) break;
             }
@@ -1059,7 +1210,9 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
                 ACN_CUDA( cudaMemcpyAsync( &d_ctr->task_stack, &h_ctr->task_stack, sizeof( unsigned long long ), cudaMemcpyHostToDevice, st ) );
                 Wave<R> w = make_wave( 0, index_base );
                 const unsigned warps = ( unsigned )( ( take + 31 ) / 32 );
+                kp_begin( 2 );
                 k_path<R><<< grid_for( warps, ACN_BLOCK / 32 ), ACN_BLOCK, smem_bytes, st >>>( w, task_cur, take );
+                kp_end( 2 );
                 launches++;
                 if( ( result = post_wave( 0 ) ) ) break;
             }
@@ -1087,7 +1240,9 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         stats->rays_path = stat_sum[ ST_PATH ]; stats->rays_shadow = stat_sum[ ST_SHADOW ];
         stats->rays_light = stat_sum[ ST_LIGHT ]; stats->diffuse_hits = stat_sum[ ST_DIFFUSE ];
         stats->kernel_launches = launches; stats->waves = waves; stats->device_ms = ms;
+        for( int c = 0; c < 4; c++ ) { stats->kernel_ms[ c ] = kp.ms[ c ]; stats->kernel_launches_by_class[ c ] = kp.cnt[ c ]; }
     }
+    if( kp.on ) for( int c = 0; c < 4; c++ ) { cudaEventDestroy( kp.a[ c ] ); cudaEventDestroy( kp.b[ c ] ); }
     return result;
 }
 

@@ -149,6 +149,13 @@ enum
 
 enum { ACN_PRECISION_F32 = 0, ACN_PRECISION_F64 = 1 /* validation only */ };
 
+enum
+{
+    ACN_CSG_AUTO      = 0,  /* intervals in f32, reference march in f64 (bit-for-bit validation)      */
+    ACN_CSG_INTERVALS = 1,  /* classify the ray against every leaf once, combine interval lists       */
+    ACN_CSG_MARCH     = 2   /* the reference's alternating march (objects.c:1052-1094,1209-1251)      */
+};
+
 typedef struct acn_options
 {
     int32_t seed_mode;        /* ACN_SEED_*                                                         */
@@ -157,7 +164,7 @@ typedef struct acn_options
                                  f64, scene-scale aware in f32                      */
     int64_t wave_budget;      /* max rays in flight per wavefront iteration; <=0: default           */
     int32_t device;           /* CUDA device ordinal; <0: current device                            */
-    int32_t reserved;
+    int32_t csg_mode;         /* ACN_CSG_*: how composite objects are intersected                   */
 } acn_options;
 
 /* counters filled per render call: rays by class */
@@ -175,7 +182,10 @@ typedef struct acn_stats
     uint64_t kernel_launches;    /* CUDA kernels launched by this call                              */
     uint64_t waves;              /* wavefront iterations                                            */
     double   device_ms;          /* CUDA-event time of the device work of this call                 */
-    double   reserved[4];
+    /* per-kernel CUDA-event times, filled when the environment has ACN_PROFILE_KERNELS=1
+       (index 0 primary, 1 explicit rays, 2 path children, 3 direct lighting) */
+    double   kernel_ms[4];
+    uint64_t kernel_launches_by_class[4];
 } acn_stats;
 
 typedef struct acn_tracer acn_tracer;   /* opaque: device copy of one scene + queues */

@@ -70,7 +70,10 @@ static const double sf_per_event[ C_COUNT ] =
     0, 0, 0, 0, 0, 0, 0, 0
 };
 
-struct counters_t { uint64_t c[ C_COUNT ]; };
+// counters are kept per phase of the ray tree so that FLOPs can be attributed to the tracer's kernels:
+// 0 primary rays, 1 reflection/chromatic/refraction rays, 2 path rays, 3 direct-light loop
+enum { PH_PRIMARY = 0, PH_SPEC = 1, PH_PATH = 2, PH_DIRECT = 3, PH_COUNT = 4 };
+struct counters_t { uint64_t c[ PH_COUNT ][ C_COUNT ]; };
 
 // ---------------------------------------------------------------------------------------------
 // v3d_s / m3d_s
@@ -197,9 +200,9 @@ struct oscene_t
     ~oscene_t() { for( obj_t* o : objs ) delete o; for( cmp_t* c : cmps ) delete c; }
 };
 
-struct ctx_t { const oscene_t* sc; counters_t* cnt; double eps; double inf; };
+struct ctx_t { const oscene_t* sc; counters_t* cnt; double eps; double inf; int phase; };
 
-#define CNT( ctx, k ) ( ( ctx )->cnt->c[ k ]++ )
+#define CNT( ctx, k ) ( ( ctx )->cnt->c[ ( ctx )->phase ][ k ]++ )
 
 static obj_t* build_obj( oscene_t* sc, const acn_flat_scene* fs, int i )
 {
@@ -720,11 +723,13 @@ static v3d scene_lum( ctx_t* cx, const ray_t* ray, double offs, trans_t* trans, 
         out.p = pos;
         double reflectance = fresnel_reflection( ray->d, trans->exit_nor, trans_refractive_index, &out.d ) * fresnel_reflectivity;
         u3_t ckey = mix64( key, KEY_REFLECT );
+        const int ph_save = cx->phase; cx->phase = PH_SPEC;
         trans_t trans_l; memset( &trans_l, 0, sizeof( trans_l ) );
         double a;
         v3d lum_l;
         if( ( a = scene_trans_hit( cx, &out, &trans_l, ckey ) ) < cx->inf ) lum_l = scene_lum( cx, &out, a, &trans_l, depth - 1, reflectance * intensity, ckey );
         else lum_l = mlf( bg, reflectance * intensity );
+        cx->phase = ph_save;
         lum = add( lum, lum_l );
         intensity *= ( 1.0 - reflectance );
     }
@@ -737,11 +742,13 @@ static v3d scene_lum( ctx_t* cx, const ray_t* ray, double offs, trans_t* trans, 
         out.p = pos;
         out.d = reflection( ray->d, trans->exit_nor );
         u3_t ckey = mix64( key, KEY_CHROMATIC );
+        const int ph_save = cx->phase; cx->phase = PH_SPEC;
         trans_t trans_l; memset( &trans_l, 0, sizeof( trans_l ) );
         double a;
         v3d lum_l;
         if( ( a = scene_trans_hit( cx, &out, &trans_l, ckey ) ) < cx->inf ) lum_l = scene_lum( cx, &out, a, &trans_l, depth - 1, chromatic_reflectivity * intensity, ckey );
         else lum_l = mlf( bg, chromatic_reflectivity * intensity );
+        cx->phase = ph_save;
         v3d cl = obj_color( trans->enter_obj, pos );
         lum = add( lum, mld( lum_l, cl ) );
         intensity *= ( 1.0 - chromatic_reflectivity );
@@ -762,6 +769,8 @@ static v3d scene_lum( ctx_t* cx, const ray_t* ray, double offs, trans_t* trans, 
                       : mix64( key, KEY_DIFFUSE );
 
         v3d lum_l = { 0, 0, 0 };
+        const int ph_hit = cx->phase;
+        cx->phase = PH_DIRECT;
 
         for( size_t i = 0; i < scene->light->el.size(); i++ )
         {
@@ -802,9 +811,12 @@ static v3d scene_lum( ctx_t* cx, const ray_t* ray, double offs, trans_t* trans, 
             lum_l = add( lum_l, mlf( cl_sum, 2.0 * cyl_hgt / direct_samples ) );
         }
 
+        cx->phase = ph_hit;
+
         // path tracing
         if( prm->path_samples && depth > 10 )
         {
+            cx->phase = PH_PATH;
             v3d cl_sum = { 0, 0, 0 };
             ray_t out = surface;
             m3d out_con = m_transposed( m_con_z( surface.d ) );
@@ -827,6 +839,7 @@ static v3d scene_lum( ctx_t* cx, const ray_t* ray, double offs, trans_t* trans, 
                 else cl_sum = add( cl_sum, mlf( bg, weight * diffuse_intensity ) );
             }
             lum_l = add( lum_l, mlf( cl_sum, 2.0 / path_samples ) );
+            cx->phase = ph_hit;
         }
 
         v3d cl = obj_color( trans->enter_obj, pos );
@@ -842,11 +855,13 @@ static v3d scene_lum( ctx_t* cx, const ray_t* ray, double offs, trans_t* trans, 
         out.p = ray_pos( ray, offs + 2.0 * cx->eps );
         fresnel_refraction( ray->d, trans->exit_nor, trans_refractive_index, &out.d );
         u3_t ckey = mix64( key, KEY_REFRACT );
+        const int ph_save = cx->phase; cx->phase = PH_SPEC;
         trans_t trans_l; memset( &trans_l, 0, sizeof( trans_l ) );
         double a;
         v3d lum_l;
         if( ( a = scene_trans_hit( cx, &out, &trans_l, ckey ) ) < cx->inf ) lum_l = scene_lum( cx, &out, a, &trans_l, depth - 1, intensity, ckey );
         else lum_l = mlf( bg, intensity );
+        cx->phase = ph_save;
         lum = add( lum, lum_l );
     }
 
@@ -886,7 +901,7 @@ static void machine_func( machine_t* o, counters_t* cnt )
 {
     const oscene_t* sc = o->sc;
     const acn_flat_params* prm = &sc->prm;
-    ctx_t cx; cx.sc = sc; cx.cnt = cnt; cx.eps = sc->eps; cx.inf = INFINITY;
+    ctx_t cx; cx.sc = sc; cx.cnt = cnt; cx.eps = sc->eps; cx.inf = INFINITY; cx.phase = PH_PRIMARY;
     uint64_t width = prm->image_width, height = prm->image_height;
     uint64_t unit_sz = ( height >> 1 );
     double unit_f = 1.0 / unit_sz;
@@ -936,7 +951,7 @@ double oracle_sf_per_event( int k ) { return ( k >= 0 && k < C_COUNT ) ? sf_per_
 // pre-gamma linear radiance.  counters: uint64[C_COUNT] summed over threads.  returns wall seconds
 // in *seconds.
 int oracle_render( const acn_flat_scene* fs, const double* xy, uint64_t n, uint64_t index_base, int seed_mode, double eps,
-                   int threads, double* rgb, double* lin, uint64_t* counters, double* seconds )
+                   int threads, double* rgb, double* lin, uint64_t* counters, double* seconds, double* phase_flops )
 {
     if( !fs || ( n && ( !xy || !rgb ) ) ) return -1;
     oscene_t sc;
@@ -964,7 +979,15 @@ int oracle_render( const acn_flat_scene* fs, const double* xy, uint64_t n, uint6
     if( seconds ) *seconds = std::chrono::duration<double>( t1 - t0 ).count();
     if( counters )
     {
-        for( int k = 0; k < C_COUNT; k++ ) { counters[ k ] = 0; for( int i = 0; i < threads; i++ ) counters[ k ] += cnt[ i ].c[ k ]; }
+        for( int k = 0; k < C_COUNT; k++ ) { counters[ k ] = 0; for( int i = 0; i < threads; i++ ) for( int ph = 0; ph < PH_COUNT; ph++ ) counters[ k ] += cnt[ i ].c[ ph ][ k ]; }
+    }
+    if( phase_flops )
+    {
+        for( int ph = 0; ph < PH_COUNT; ph++ )
+        {
+            phase_flops[ ph ] = 0;
+            for( int k = 0; k < C_COUNT; k++ ) for( int i = 0; i < threads; i++ ) phase_flops[ ph ] += ( double )cnt[ i ].c[ ph ][ k ] * flops_per_event[ k ];
+        }
     }
     return 0;
 }
@@ -988,7 +1011,7 @@ int oracle_accumulate( const double* xy, const double* rgb, uint64_t n, int widt
 double oracle_sphere_ray_hit( const double pos[ 3 ], double r, const double rp[ 3 ], const double rd[ 3 ], double eps, double nor[ 3 ] )
 {
     counters_t c; memset( &c, 0, sizeof( c ) );
-    ctx_t cx; cx.sc = NULL; cx.cnt = &c; cx.eps = eps; cx.inf = INFINITY;
+    ctx_t cx; cx.sc = NULL; cx.cnt = &c; cx.eps = eps; cx.inf = INFINITY; cx.phase = 0;
     ray_t ray = { V( rp[ 0 ], rp[ 1 ], rp[ 2 ] ), V( rd[ 0 ], rd[ 1 ], rd[ 2 ] ) };
     v3d n = V( 0, 0, 0 );
     double a = sphere_ray_hit( &cx, V( pos[ 0 ], pos[ 1 ], pos[ 2 ] ), r, &ray, &n );
@@ -998,7 +1021,7 @@ double oracle_sphere_ray_hit( const double pos[ 3 ], double r, const double rp[ 
 double oracle_plane_ray_hit( const double pos[ 3 ], const double pn[ 3 ], const double rp[ 3 ], const double rd[ 3 ], double eps )
 {
     counters_t c; memset( &c, 0, sizeof( c ) );
-    ctx_t cx; cx.sc = NULL; cx.cnt = &c; cx.eps = eps; cx.inf = INFINITY;
+    ctx_t cx; cx.sc = NULL; cx.cnt = &c; cx.eps = eps; cx.inf = INFINITY; cx.phase = 0;
     ray_t ray = { V( rp[ 0 ], rp[ 1 ], rp[ 2 ] ), V( rd[ 0 ], rd[ 1 ], rd[ 2 ] ) };
     return plane_ray_hit( &cx, V( pos[ 0 ], pos[ 1 ], pos[ 2 ] ), V( pn[ 0 ], pn[ 1 ], pn[ 2 ] ), &ray, NULL );
 }

@@ -41,7 +41,7 @@ class Oracle:
         L = self.lib
         L.oracle_render.restype = C.c_int
         L.oracle_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_int,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
         L.oracle_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
         L.oracle_counter_count.restype = C.c_int
         L.oracle_flops_per_event.restype = C.c_double
@@ -76,10 +76,11 @@ class Oracle:
         lin = np.zeros((n, 3), dtype=np.float64) if want_linear else None
         cnt = np.zeros(self.n_counters, dtype=np.uint64)
         sec = C.c_double(0)
+        phase = np.zeros(4, dtype=np.float64)
         if threads is None:
             threads = os.cpu_count() or 1
         rc = self.lib.oracle_render(C.cast(flat.ptr, C.c_void_p), xy.ctypes.data, n, index_base, seed_mode, eps, threads,
-                                    rgb.ctypes.data, lin.ctypes.data if lin is not None else None, cnt.ctypes.data, C.byref(sec))
+                                    rgb.ctypes.data, lin.ctypes.data if lin is not None else None, cnt.ctypes.data, C.byref(sec), phase.ctypes.data)
         if rc != 0:
             raise RuntimeError(f"oracle_render failed: {rc}")
         counters = {k: int(v) for k, v in zip(COUNTER_NAMES, cnt)}
@@ -89,6 +90,8 @@ class Oracle:
             "sf_ops": float((cnt.astype(np.float64) * self.sf_per_event).sum()),
             "rays": int(sum(counters[k] for k in ("rays_primary", "rays_reflect", "rays_chromatic", "rays_refract", "rays_path", "rays_shadow"))),
             "linear": lin,
+            # algorithmic FLOPs by phase of the ray tree = by tracer kernel: primary, spec rays, path rays, direct loop
+            "phase_flops": {"primary": phase[0], "rays": phase[1], "path": phase[2], "direct": phase[3]},
         }
         return rgb, info
 
