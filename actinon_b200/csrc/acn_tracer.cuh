@@ -110,43 +110,63 @@ template <typename R> struct TaskBuf    // SoA
     u64*   cum;       // inclusive running sum of n_path on the task stack
 };
 
+
 enum
 {
     ST_PRIMARY = 0, ST_REFLECT, ST_CHROMATIC, ST_REFRACT, ST_PATH, ST_SHADOW, ST_LIGHT, ST_DIFFUSE, ST_COUNT
 };
 
-struct Counters
-{
-    unsigned long long rays_out;        // rays appended to the ray stack
-    unsigned long long tasks_new;       // tasks appended to the new-task scratch
-    unsigned long long tasks_new_path;  // of those, tasks with n_path > 0
-    unsigned long long task_stack;      // packed: count << 38 | sum n_path
-    unsigned long long stats[ ST_COUNT ];
-    unsigned long long plan_start;      // k_plan output
-    unsigned long long plan_cum;
-    int overflow;
-    int pad;
-};
-
 #define ACN_TASK_SHIFT 38
 #define ACN_TASK_MASK  ( ( 1ull << ACN_TASK_SHIFT ) - 1 )
+#define ACN_NONE64     ( ~0ull )
+
+// Device-resident scheduler state.  The host never sizes a launch from it: every kernel runs on a
+// fixed persistent grid and takes its work range from the plan k_sched wrote, so a whole wavefront
+// iteration is enqueued without a host round trip (the host only polls `done` every few iterations).
+struct Sched
+{
+    // stacks
+    unsigned long long nr;              // rays on the ray stack
+    unsigned long long nt, nt_cum;      // tasks on the task stack, their outstanding path children
+    // plan of the current iteration
+    unsigned long long ray_base;        // new rays are appended at ray_stack[ ray_base + rays_out++ ]
+    unsigned long long ray_take;        // rays popped into ray_cur for k_rays
+    unsigned long long path_blk_lo, path_blk_hi;   // 32-child blocks of the task stack traced by k_path
+    unsigned long long path_c_hi;       // first child index beyond the stack top
+    unsigned long long path_nt;         // stack height seen by k_path (window bound)
+    unsigned long long fix_slot, fix_cum;   // partially consumed task: cum[ fix_slot ] = fix_cum after k_path
+    unsigned long long prim_first, prim_count;
+    // work cursors of the persistent kernels (units: chunks)
+    unsigned long long cur_pop, cur_rays, cur_path, cur_index, cur_direct, cur_primary;
+    // per-iteration outputs
+    unsigned long long rays_out;        // rays appended
+    unsigned long long tasks_new;       // diffuse hits appended to the new-task scratch
+    unsigned long long dl_packed;       // direct list: entries << 38 | shadow children
+    unsigned long long task_stack;      // task stack: height << 38 | outstanding path children
+    // status
+    unsigned long long waves;
+    unsigned long long stats[ ST_COUNT ];
+    int done;
+    int overflow;
+};
 
 template <typename R> struct Wave       // everything a kernel needs
 {
     DParams<R>  prm;
-    RayBuf<R>   rays_out;     // ray stack (append at rays_out_base + counter)
+    RayBuf<R>   rays_out;     // ray stack
     TaskBuf<R>  tasks_out;    // new-task scratch
-    Counters*   ctr;
-    R*          accum;        // per-sample RGB, 3 per sample (relative to sample_base)
-    unsigned long long rays_out_base, rays_cap;
+    Sched*      sc;
+    R*          accum;        // per-sample RGB, 3 per sample
+    unsigned long long rays_cap;
     unsigned long long tasks_cap;
-    unsigned long long sample_base;   // first sample index of this render call's chunk (for accum addressing)
     u64         index_base;   // global index of sample 0 (index-keyed seeding)
 };
 
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
+#define ACN_FULL 0xFFFFFFFFu
+
 __device__ __forceinline__ float atomic_add_r( float* p, float v )   { return atomicAdd( p, v ); }
 __device__ __forceinline__ double atomic_add_r( double* p, double v ) { return atomicAdd( p, v ); }
 
@@ -163,6 +183,49 @@ __device__ __forceinline__ void agg_count( unsigned long long* ctr )
 {
     cg::coalesced_group g = cg::coalesced_threads();
     if( g.thread_rank() == 0 ) atomicAdd( ctr, ( unsigned long long )g.size() );
+}
+
+// whole-warp sum of a per-lane count, added to a global counter by lane 0
+__device__ __forceinline__ void warp_count( unsigned long long* ctr, unsigned long long v, int lane )
+{
+    #pragma unroll
+    for( int o = 16; o > 0; o >>= 1 ) v += __shfl_down_sync( ACN_FULL, v, o );
+    if( lane == 0 && v ) atomicAdd( ctr, v );
+}
+
+// persistent-warp work fetch: `per` consecutive units per atomic
+__device__ __forceinline__ unsigned long long warp_fetch( unsigned long long* cursor, unsigned long long per, int lane )
+{
+    unsigned long long b = 0;
+    if( lane == 0 ) b = atomicAdd( cursor, per );
+    return __shfl_sync( ACN_FULL, b, 0 );
+}
+
+// lanes hold the inclusive running counts of 32 consecutive list entries (ACN_NONE64 beyond the list):
+// number of entries whose count is <= idx, i.e. the entry that owns child idx
+__device__ __forceinline__ int window_find( unsigned long long incl, unsigned long long idx )
+{
+    int j = 0;
+    #pragma unroll
+    for( int s = 16; s > 0; s >>= 1 )
+    {
+        const unsigned long long v = __shfl_sync( ACN_FULL, incl, j + s - 1 );
+        if( v <= idx ) j += s;
+    }
+    return j;
+}
+
+// sum over runs of equal keys (keys are non-decreasing over the lanes); valid at the first lane of a run
+template <typename T> __device__ __forceinline__ T seg_sum( T v, int key, int lane )
+{
+    #pragma unroll
+    for( int o = 1; o < 32; o <<= 1 )
+    {
+        const T   v2 = __shfl_down_sync( ACN_FULL, v, o );
+        const int k2 = __shfl_down_sync( ACN_FULL, key, o );
+        if( lane + o < 32 && k2 == key ) v += v2;
+    }
+    return v;
 }
 
 template <typename R> __device__ __forceinline__ void add_sample( const Wave<R>& w, int sample, V3<R> c )
@@ -232,8 +295,8 @@ template <typename R> __device__ __forceinline__ void emit_ray( const Wave<R>& w
 {
     int flags = 0;
     if( depth == 0 || intensity < w.prm.min_intensity ) flags |= RAYF_PROBE;
-    unsigned long long slot = w.rays_out_base + agg_inc( &w.ctr->rays_out );
-    if( slot >= w.rays_cap ) { w.ctr->overflow = 1; return; }
+    unsigned long long slot = w.sc->ray_base + agg_inc( &w.sc->rays_out );
+    if( slot >= w.rays_cap ) { w.sc->overflow = 1; return; }
     R4<R> a; a.x = p.x; a.y = p.y; a.z = p.z; a.w = intensity;
     R4<R> b; b.x = d.x; b.y = d.y; b.z = d.z; b.w = R( 0 );
     R4<R> c; c.x = tp.x; c.y = tp.y; c.z = tp.z; c.w = R( 0 );
@@ -257,7 +320,7 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
         R d2 = sqr( pos - xyz( prm.sv.geo[ tr.enter_obj * GEO_STRIDE ] ) );
         R li = d2 > R( 0 ) ? me->radiance / d2 : Num<R>::mag();
         add_sample( w, sample, mul( obj_color( prm, tr.enter_obj, pos ), tp ) * ( li * I ) );
-        agg_count( &w.ctr->stats[ ST_LIGHT ] );
+        agg_count( &w.sc->stats[ ST_LIGHT ] );
         return;
     }
 
@@ -312,8 +375,7 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
             np = ( unsigned long long )( ( double )prm.path_samples * ( double )Id );
             if( np == 0 ) np = 1;
         }
-        unsigned long long slot = agg_inc( &w.ctr->tasks_new );
-        if( np ) agg_count( &w.ctr->tasks_new_path );
+        unsigned long long slot = agg_inc( &w.sc->tasks_new );
         if( slot < w.tasks_cap )
         {
             V3<R> tpc = mul( tp, col );
@@ -327,7 +389,7 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
             w.tasks_out.rv0[ slot ] = rv0;
             w.tasks_out.key[ slot ] = key;
         }
-        else w.ctr->overflow = 2;
+        else w.sc->overflow = 2;
         I *= ( R( 1 ) - Dff );
     }
 
@@ -338,11 +400,12 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
     }
 }
 
-// trace one ray of the tree and shade its hit.
-//   cls != RC_PATH: scene_s_trans_hit (lights + matter), miss -> background * I  (scene.c:484-491 etc.)
-//   cls == RC_PATH: matter only; beyond max_path_length -> background * I        (scene.c:606-616)
+// trace one ray of the tree and shade its hit; returns true when the ray leaves the scene, in which
+// case the caller owes the sample  background * tp * I  (scene.c:484-491, 613-616)
+//   cls != RC_PATH: scene_s_trans_hit (lights + matter)
+//   cls == RC_PATH: matter only; "leaves" = nothing closer than max_path_length        (scene.c:606-616)
 //   probe: the hit's shading would return 0 (depth 0 or I < Imin) — only "anything hit?" matters
-template <typename R> __device__ void trace_ray( const Wave<R>& w, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
+template <typename R> __device__ bool trace_ray( const Wave<R>& w, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
                                                  bool probe, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
@@ -353,14 +416,12 @@ template <typename R> __device__ void trace_ray( const Wave<R>& w, const Ray<R>&
     {
         R a = compound_ray_hit<R>( sv, sv.light_root, ray, nullptr, nullptr, ctx, inf );
         if( !( a < inf ) ) a = compound_ray_hit<R>( sv, sv.matter_root, ray, nullptr, nullptr, ctx, inf );
-        if( !( a < inf ) ) add_sample( w, sample, mul( prm.background, tp ) * I );
-        return;
+        return !( a < inf );
     }
     if( probe )     // path child that cannot contribute on a hit: is anything closer than max_path_length?
     {
         R a = compound_ray_hit<R>( sv, sv.matter_root, ray, nullptr, nullptr, ctx, prm.max_path_length );
-        if( !( a < prm.max_path_length ) ) add_sample( w, sample, mul( prm.background, tp ) * I );
-        return;
+        return !( a < prm.max_path_length );
     }
     Trans<R> tr;
     tr.exit_obj = tr.enter_obj = -1; tr.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
@@ -368,255 +429,395 @@ template <typename R> __device__ void trace_ray( const Wave<R>& w, const Ray<R>&
     if( cls == RC_PATH )
     {
         a = compound_trans_hit( sv, sv.matter_root, ray, &tr, ctx );
-        if( !( a < prm.max_path_length ) ) { add_sample( w, sample, mul( prm.background, tp ) * I ); return; }
+        if( !( a < prm.max_path_length ) ) return true;
     }
     else
     {
         a = scene_trans_hit( sv, ray, &tr, ctx );
-        if( !( a < inf ) ) { add_sample( w, sample, mul( prm.background, tp ) * I ); return; }
+        if( !( a < inf ) ) return true;
     }
     // the hit distance itself is only good to a few ulp of its magnitude: keep the shading point that far in front
     const R hit_eps = r_max( sv.eps, prm.eps_rel * a );
     a -= hit_eps - sv.eps;
     shade_hit( w, ray, a, hit_eps, tr, depth, I, tp, sample, key );
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernels
+// kernels — all persistent: fixed grid, warps fetch chunks of work through a cursor in Sched
 // ---------------------------------------------------------------------------------------------
 #define ACN_BLOCK 128
+#define ACN_CHUNK 4        // 32-item groups per cursor fetch
+
+enum { SCHED_PRIMARY = 0, SCHED_WAVE = 1 };
+
+// one thread: closes the books of the previous iteration and plans the next one
+__global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, unsigned long long budget,
+                         unsigned long long ray_min, int mode, unsigned long long prim_first, unsigned long long prim_count )
+{
+    if( threadIdx.x != 0 || blockIdx.x != 0 ) return;
+    // ---- previous iteration
+    unsigned long long nr = s->ray_base + s->rays_out;
+    unsigned long long nt = s->task_stack >> ACN_TASK_SHIFT, nt_cum = s->task_stack & ACN_TASK_MASK;
+    s->stats[ ST_DIFFUSE ] += s->tasks_new;
+    if( s->rays_out | s->tasks_new | s->ray_take | ( s->path_blk_hi - s->path_blk_lo ) | s->prim_count ) s->waves++;
+    s->rays_out = 0; s->tasks_new = 0; s->dl_packed = 0;
+    s->cur_pop = s->cur_rays = s->cur_path = s->cur_index = s->cur_direct = s->cur_primary = 0;
+    // ---- plan
+    unsigned long long ray_take = 0, blk_lo = 0, blk_hi = 0, fix_slot = ACN_NONE64, fix_cum = 0;
+    s->path_nt = nt; s->path_c_hi = nt_cum;
+    s->prim_first = prim_first; s->prim_count = 0;
+    if( mode == SCHED_PRIMARY )
+    {
+        s->prim_count = prim_count; s->done = 0;
+    }
+    else
+    {
+        const bool path_avail = nt_cum > 0;
+        if( nr > 0 && ( nr >= ray_min || !path_avail ) ) ray_take = nr < budget ? nr : budget;
+        if( path_avail )
+        {
+            const unsigned long long c_lo = nt_cum > budget ? ( ( nt_cum - budget ) & ~31ull ) : 0ull;
+            blk_lo = c_lo >> 5; blk_hi = ( nt_cum + 31 ) >> 5;
+            const unsigned long long t0 = pdir[ blk_lo ];                // the task that owns child c_lo
+            const unsigned long long excl = t0 ? cum[ t0 - 1 ] : 0ull;
+            const bool partial = excl < c_lo;                            // its low children stay on the stack
+            if( partial ) { fix_slot = t0; fix_cum = c_lo; }
+            nt = t0 + ( partial ? 1 : 0 ); nt_cum = c_lo;
+            s->task_stack = ( nt << ACN_TASK_SHIFT ) | nt_cum;
+        }
+        if( ray_take == 0 && !path_avail ) s->done = 1;
+    }
+    if( s->overflow ) { s->done = 1; ray_take = 0; blk_lo = blk_hi = 0; fix_slot = ACN_NONE64; s->prim_count = 0; }
+    s->nr = nr - ray_take; s->nt = nt; s->nt_cum = nt_cum;
+    s->ray_base = nr - ray_take; s->ray_take = ray_take;
+    s->path_blk_lo = blk_lo; s->path_blk_hi = blk_hi;
+    s->fix_slot = fix_slot; s->fix_cum = fix_cum;
+}
+
+// pops the top ray_take rays of the stack into the current-wave buffer
+template <typename R> __global__ void __launch_bounds__( 256 )
+k_pop( const Sched* __restrict__ s, RayBuf<R> stack, RayBuf<R> cur )
+{
+    const unsigned long long n = s->ray_take, base = s->ray_base;
+    for( unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x; i < n; i += ( unsigned long long )gridDim.x * blockDim.x )
+    {
+        cur.o_i[ i ] = stack.o_i[ base + i ]; cur.d_[ i ] = stack.d_[ base + i ];
+        cur.tp[ i ] = stack.tp[ base + i ];   cur.meta[ i ] = stack.meta[ base + i ];
+    }
+}
 
 // camera rays (scene.c:976-990) fused with their first trace + shade
 template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
-k_primary( Wave<R> w, const double* __restrict__ xy, unsigned long long first, unsigned long long count )
+k_primary( Wave<R> w, const double* __restrict__ xy )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
+    const unsigned long long first = w.sc->prim_first, count = w.sc->prim_count;
+    if( count == 0 || w.sc->overflow ) return;
     stage_scene( w.prm, smem );
-    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
-    if( i >= count ) return;
     const DParams<R>& prm = w.prm;
-    const unsigned long long s = first + i;
-    const double mx = xy[ 2 * s ], my = xy[ 2 * s + 1 ];
-    const int unit_sz = prm.height >> 1;
-    const double unit_f = 1.0 / ( double )unit_sz;
-    const R z = ( R )( unit_f * ( ( double )unit_sz - my ) );
-    const R x = ( R )( unit_f * ( mx - ( double )( prm.width >> 1 ) ) );
-    V3<R> d = unit( v3<R>( x, prm.focal, z ) );
-    Ray<R> ray;
-    ray.p = prm.cam_pos;
-    ray.d = prm.cam_rx * d.x + prm.cam_ry * d.y + prm.cam_rz * d.z;
-    agg_count( &w.ctr->stats[ ST_PRIMARY ] );
-    trace_ray( w, ray, R( 1 ), prm.trace_depth, v3<R>( R( 1 ), R( 1 ), R( 1 ) ), RC_PRIMARY, false,
-               ( int )( s - w.sample_base ), mix64( w.index_base + s, 0x5EEDull ) );
+    const int lane = threadIdx.x & 31;
+    unsigned long long n_rays = 0;
+    for( ;; )
+    {
+        const unsigned long long c0 = warp_fetch( &w.sc->cur_primary, 32ull * ACN_CHUNK, lane );
+        if( c0 >= count ) break;
+        for( int g = 0; g < ACN_CHUNK; g++ )
+        {
+            const unsigned long long i = c0 + 32ull * g + lane;
+            if( i >= count ) continue;
+            const unsigned long long s = first + i;
+            const double mx = xy[ 2 * s ], my = xy[ 2 * s + 1 ];
+            const int unit_sz = prm.height >> 1;
+            const double unit_f = 1.0 / ( double )unit_sz;
+            const R z = ( R )( unit_f * ( ( double )unit_sz - my ) );
+            const R x = ( R )( unit_f * ( mx - ( double )( prm.width >> 1 ) ) );
+            V3<R> d = unit( v3<R>( x, prm.focal, z ) );
+            Ray<R> ray;
+            ray.p = prm.cam_pos;
+            ray.d = prm.cam_rx * d.x + prm.cam_ry * d.y + prm.cam_rz * d.z;
+            n_rays++;
+            const V3<R> one = v3<R>( R( 1 ), R( 1 ), R( 1 ) );
+            if( trace_ray( w, ray, R( 1 ), prm.trace_depth, one, RC_PRIMARY, false, ( int )s, mix64( w.index_base + s, 0x5EEDull ) ) )
+                add_sample( w, ( int )s, prm.background );
+        }
+    }
+    warp_count( &w.sc->stats[ ST_PRIMARY ], n_rays, lane );
 }
 
 // explicit rays popped from the ray stack
 template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
-k_rays( Wave<R> w, RayBuf<R> in, unsigned long long count )
+k_rays( Wave<R> w, RayBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
+    const unsigned long long count = w.sc->ray_take;
+    if( count == 0 || w.sc->overflow ) return;
     stage_scene( w.prm, smem );
-    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
-    if( i >= count ) return;
-    const R4<R> a = in.o_i[ i ], b = in.d_[ i ], c = in.tp[ i ];
-    const I4 m = in.meta[ i ];
-    Ray<R> ray; ray.p = xyz( a ); ray.d = xyz( b );
-    const int depth = m.x & 0xFF, cls = ( m.x >> 8 ) & 0xFF;
-    const u64 key = ( u64 )( unsigned )m.z | ( ( u64 )( unsigned )m.w << 32 );
-    agg_count( &w.ctr->stats[ cls ] );
-    trace_ray( w, ray, a.w, depth, xyz( c ), cls, ( m.x & RAYF_PROBE ) != 0, m.y, key );
+    const int lane = threadIdx.x & 31;
+    unsigned int n_refl = 0, n_chro = 0, n_refr = 0;
+    for( ;; )
+    {
+        const unsigned long long c0 = warp_fetch( &w.sc->cur_rays, 32ull * ACN_CHUNK, lane );
+        if( c0 >= count ) break;
+        for( int g = 0; g < ACN_CHUNK; g++ )
+        {
+            const unsigned long long i = c0 + 32ull * g + lane;
+            if( i >= count ) continue;
+            const R4<R> a = in.o_i[ i ], b = in.d_[ i ], c = in.tp[ i ];
+            const I4 m = in.meta[ i ];
+            Ray<R> ray; ray.p = xyz( a ); ray.d = xyz( b );
+            const int depth = m.x & 0xFF, cls = ( m.x >> 8 ) & 0xFF;
+            const u64 key = ( u64 )( unsigned )m.z | ( ( u64 )( unsigned )m.w << 32 );
+            n_refl += cls == RC_REFLECT; n_chro += cls == RC_CHROMATIC; n_refr += cls == RC_REFRACT;
+            if( trace_ray( w, ray, a.w, depth, xyz( c ), cls, ( m.x & RAYF_PROBE ) != 0, m.y, key ) )
+                add_sample( w, m.y, mul( w.prm.background, xyz( c ) ) * a.w );
+        }
+    }
+    warp_count( &w.sc->stats[ ST_REFLECT ], n_refl, lane );
+    warp_count( &w.sc->stats[ ST_CHROMATIC ], n_chro, lane );
+    warp_count( &w.sc->stats[ ST_REFRACT ], n_refr, lane );
 }
 
-// warp-cooperative expansion of 32 tasks: lane l of the warp owns flattened child index idx and
-// finds (task, child) by a 5-step search over the warp's prefix sums held in shared memory.
-struct WarpSlots { unsigned int cum[ 33 ]; };
+// Lists of work entries with implicit children.  An entry owns the children [ excl, incl ) of a global
+// child index space; dir[ b ] names the entry that owns child 32*b, so a warp that takes block b finds
+// the owners of its 32 children inside a window of 32 consecutive entries (every entry has >= 1 child).
+struct ListWindow { unsigned long long incl, excl0; unsigned int e0; };
 
-// direct lighting (scene.c:542-581): one lane per (task, light, sample)
+__device__ __forceinline__ ListWindow list_window( const u64* __restrict__ cum, const unsigned int* __restrict__ dir,
+                                                   unsigned long long blk, unsigned long long n_entries, int lane )
+{
+    ListWindow lw;
+    lw.e0 = dir[ blk ];
+    const unsigned long long e = ( unsigned long long )lw.e0 + lane;
+    lw.incl = e < n_entries ? cum[ e ] : ACN_NONE64;
+    unsigned long long x = 0;
+    if( lane == 0 && lw.e0 > 0 ) x = cum[ lw.e0 - 1 ];
+    lw.excl0 = __shfl_sync( ACN_FULL, x, 0 );
+    return lw;
+}
+
+// direct lighting (scene.c:542-581): one lane per (task, light, sample); the shadow rays exist only
+// as (entry, child index) and are regenerated from the task with an O(1) LCG skip-ahead
 template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
-k_direct( Wave<R> w, TaskBuf<R> in, unsigned long long count )
+k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
+          const unsigned int* __restrict__ dl_dir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
-    __shared__ WarpSlots slots[ ACN_BLOCK / 32 ];
-    __shared__ R sums[ ACN_BLOCK / 32 ][ 32 ][ 3 ];
+    const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
+    if( total == 0 || w.sc->overflow ) return;
     stage_scene( w.prm, smem );
     const DParams<R>& prm = w.prm;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned long long t0 = ( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) + wid ) * 32ull;
-    if( t0 >= count ) return;
-    const unsigned long long my_t = t0 + lane;
-    const int L = prm.n_lights;
-    unsigned int cnt = 0;
-    if( my_t < count ) cnt = ( unsigned int )in.meta[ my_t ].z * ( unsigned int )L;
-    unsigned int inc = cnt;
-    #pragma unroll
-    for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( 0xFFFFFFFFu, inc, o ); if( lane >= o ) inc += v; }
-    WarpSlots& ws = slots[ wid ];
-    ws.cum[ lane + 1 ] = inc;
-    if( lane == 0 ) ws.cum[ 0 ] = 0;
-    sums[ wid ][ lane ][ 0 ] = R( 0 ); sums[ wid ][ lane ][ 1 ] = R( 0 ); sums[ wid ][ lane ][ 2 ] = R( 0 );
-    __syncwarp();
-    const unsigned int total = ws.cum[ 32 ];
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_blocks = ( total + 31 ) >> 5;
     unsigned long long n_shadow = 0;
-
-    for( unsigned int base = 0; base < total; base += 32 )
+    for( ;; )
     {
-        const unsigned int idx = base + lane;
-        if( idx < total )
+        const unsigned long long b0 = warp_fetch( &w.sc->cur_direct, ACN_CHUNK, lane );
+        if( b0 >= n_blocks ) break;
+        for( unsigned long long blk = b0; blk < b0 + ACN_CHUNK && blk < n_blocks; blk++ )
         {
-            int k = 0;
-            #pragma unroll
-            for( int s = 16; s > 0; s >>= 1 ) if( ws.cum[ k + s ] <= idx ) k += s;
-            const unsigned long long t = t0 + k;
-            const unsigned int r = idx - ws.cum[ k ];
-            const I4 m = in.meta[ t ];
-            const unsigned int nd = ( unsigned int )m.z;
-            const unsigned int li = r / nd, j = r - li * nd;
-            const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
-            const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
-            const DLight<R>& lg = prm.lights[ li ];
-
-            const SceneView<R> sv = ray_view( prm, pos );
-            V3<R> axis; R cos_rs;
-            obj_fov( sv, lg.node, pos, &axis, &cos_rs );
-            const Basis<R> bs = basis_con_z( axis );
-            const R h = R( 1 ) - cos_rs;                                                 // areal_coverage, vectors.h:362
-            u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )li * nd + j );
-            Ray<R> out; out.p = pos;
-            out.d = from_basis( bs, sphere_cap<R>( &rv, h ) );
-            R wgt = dot( out.d, nrm );
-            if( wgt > R( 0 ) )
+            const ListWindow lw = list_window( dl_cum, dl_dir, blk, n_entries, lane );
+            const unsigned long long idx = ( blk << 5 ) + lane;
+            const bool live = idx < total;
+            const int j = window_find( lw.incl, live ? idx : ( blk << 5 ) );
+            const unsigned long long prev = __shfl_sync( ACN_FULL, lw.incl, ( j + 31 ) & 31 );
+            V3<R> sum = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+            int sample = -1;
+            if( live )
             {
-                HitCtx ctx; ctx.key = 0;
-                n_shadow++;
-                R a = obj_ray_hit<R>( sv, lg.node, out, nullptr, ctx );              // scene.c:564
-                if( a < Num<R>::inf() )
+                const unsigned long long r = idx - ( j ? prev : lw.excl0 );
+                const unsigned int t = dl_slot[ lw.e0 + j ];
+                const I4 m = in.meta[ t ];
+                sample = m.x;
+                const unsigned int nd = ( unsigned int )m.z;
+                const unsigned int li = ( unsigned int )( r / nd ), jj = ( unsigned int )( r - ( unsigned long long )li * nd );
+                const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+                const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
+                const DLight<R>& lg = prm.lights[ li ];
+
+                const SceneView<R> sv = ray_view( prm, pos );
+                V3<R> axis; R cos_rs;
+                obj_fov( sv, lg.node, pos, &axis, &cos_rs );
+                const Basis<R> bs = basis_con_z( axis );
+                const R h = R( 1 ) - cos_rs;                                                 // areal_coverage, vectors.h:362
+                u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )li * nd + jj );
+                Ray<R> out; out.p = pos;
+                out.d = from_basis( bs, sphere_cap<R>( &rv, h ) );
+                R wgt = dot( out.d, nrm );
+                if( wgt > R( 0 ) )
                 {
-                    if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, prj );
+                    HitCtx ctx; ctx.key = 0;
                     n_shadow++;
-                    R sh = compound_ray_hit<R>( sv, sv.matter_root, out, nullptr, nullptr, ctx, a );   // scene.c:569
-                    if( sh > a )
+                    R a = obj_ray_hit<R>( sv, lg.node, out, nullptr, ctx );              // scene.c:564
+                    if( a < Num<R>::inf() )
                     {
-                        V3<R> hp = madd( out.p, out.d, a );
-                        R d2 = sqr( hp - v3<R>( lg.pos[ 0 ], lg.pos[ 1 ], lg.pos[ 2 ] ) );
-                        R lint = d2 > R( 0 ) ? lg.radiance / d2 : Num<R>::mag();
-                        R f = lint * wgt * pi.w * ( R( 2 ) * h / ( R )nd );               // scene.c:574,579
-                        atomic_add_r( &sums[ wid ][ k ][ 0 ], lg.color[ 0 ] * f * tb.x );
-                        atomic_add_r( &sums[ wid ][ k ][ 1 ], lg.color[ 1 ] * f * tb.y );
-                        atomic_add_r( &sums[ wid ][ k ][ 2 ], lg.color[ 2 ] * f * tb.z );
+                        if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, prj );
+                        n_shadow++;
+                        R sh = compound_ray_hit<R>( sv, sv.matter_root, out, nullptr, nullptr, ctx, a );   // scene.c:569
+                        if( sh > a )
+                        {
+                            V3<R> hp = madd( out.p, out.d, a );
+                            R d2 = sqr( hp - v3<R>( lg.pos[ 0 ], lg.pos[ 1 ], lg.pos[ 2 ] ) );
+                            R lint = d2 > R( 0 ) ? lg.radiance / d2 : Num<R>::mag();
+                            R f = lint * wgt * pi.w * ( R( 2 ) * h / ( R )nd );               // scene.c:574,579
+                            sum = v3<R>( lg.color[ 0 ] * f * tb.x, lg.color[ 1 ] * f * tb.y, lg.color[ 2 ] * f * tb.z );
+                        }
                     }
                 }
             }
+            __syncwarp();
+            // one atomic triple per task segment of the block instead of one per shadow ray
+            const int key = live ? j : -1;
+            sum.x = seg_sum( sum.x, key, lane ); sum.y = seg_sum( sum.y, key, lane ); sum.z = seg_sum( sum.z, key, lane );
+            const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
+            if( live && ( lane == 0 || kprev != key ) && ( sum.x != R( 0 ) || sum.y != R( 0 ) || sum.z != R( 0 ) ) ) add_sample( w, sample, sum );
         }
     }
-    __syncwarp();
-    if( my_t < count )
-    {
-        const int sample = in.meta[ my_t ].x;
-        V3<R> c = v3<R>( sums[ wid ][ lane ][ 0 ], sums[ wid ][ lane ][ 1 ], sums[ wid ][ lane ][ 2 ] );
-        if( c.x != R( 0 ) || c.y != R( 0 ) || c.z != R( 0 ) ) add_sample( w, sample, c );
-    }
-    #pragma unroll
-    for( int o = 16; o > 0; o >>= 1 ) n_shadow += __shfl_down_sync( 0xFFFFFFFFu, n_shadow, o );
-    if( lane == 0 )
-    {
-        atomicAdd( &w.ctr->stats[ ST_SHADOW ], n_shadow );
-    }
+    warp_count( &w.sc->stats[ ST_SHADOW ], n_shadow, lane );
 }
 
 // indirect rays (scene.c:584-621): one lane per (task, path sample); the child ray is generated,
 // traced and shaded in place, never stored.
 template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
-k_path( Wave<R> w, TaskBuf<R> in, unsigned long long count )
+k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
-    __shared__ WarpSlots slots[ ACN_BLOCK / 32 ];
+    const unsigned long long blk_lo = w.sc->path_blk_lo, blk_hi = w.sc->path_blk_hi;
+    if( blk_hi <= blk_lo || w.sc->overflow ) return;
+    const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
     stage_scene( w.prm, smem );
     const DParams<R>& prm = w.prm;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned long long t0 = ( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) + wid ) * 32ull;
-    if( t0 >= count ) return;
-    const unsigned long long my_t = t0 + lane;
-    unsigned int cnt = 0;
-    if( my_t < count ) cnt = ( unsigned int )in.meta[ my_t ].w;
-    unsigned int inc = cnt;
-    #pragma unroll
-    for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( 0xFFFFFFFFu, inc, o ); if( lane >= o ) inc += v; }
-    WarpSlots& ws = slots[ wid ];
-    ws.cum[ lane + 1 ] = inc;
-    if( lane == 0 ) ws.cum[ 0 ] = 0;
-    __syncwarp();
-    const unsigned int total = ws.cum[ 32 ];
-    const int L = prm.n_lights;
-
-    for( unsigned int base = 0; base < total; base += 32 )
-    {
-        const unsigned int idx = base + lane;
-        if( idx >= total ) continue;
-        int k = 0;
-        #pragma unroll
-        for( int s = 16; s > 0; s >>= 1 ) if( ws.cum[ k + s ] <= idx ) k += s;
-        const unsigned long long t = t0 + k;
-        const unsigned int i = idx - ws.cum[ k ];
-        const I4 m = in.meta[ t ];
-        const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
-        const V3<R> nrm = xyz( nc );
-        const Basis<R> bs = basis_con_z( nrm );
-        u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )L * ( unsigned int )m.z + i );
-        Ray<R> out; out.p = xyz( pi );
-        out.d = from_basis( bs, sphere_cap<R>( &rv, R( 1 ) ) );
-        R wgt = dot( out.d, nrm );
-        if( wgt <= R( 0 ) ) continue;                                                    // scene.c:600
-        if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, xyz( pa ) );
-        agg_count( &w.ctr->stats[ ST_PATH ] );
-        const R scale = R( 2 ) / ( R )( unsigned int )m.w;                               // scene.c:620
-        const R ci = wgt * pi.w;
-        const bool probe = ( m.y - 10 ) == 0 || ci < prm.min_intensity;
-        trace_ray( w, out, ci, m.y - 10, xyz( tb ) * scale, RC_PATH, probe, m.x, mix64( in.key[ t ], KEY_PATH0 + i ) );
-    }
-}
-
-// keeps the tasks that still have path work: new-task scratch -> task stack, with the running sum
-// of n_path stored alongside so that a later wave can be cut at an exact child budget
-template <typename R> __global__ void __launch_bounds__( 256 )
-k_keep( TaskBuf<R> in, unsigned long long count, TaskBuf<R> stack, unsigned long long stack_cap, Counters* ctr )
-{
-    unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    unsigned int np = 0;
-    if( i < count ) np = ( unsigned int )in.meta[ i ].w;
-    const unsigned int mask = __ballot_sync( 0xFFFFFFFFu, np > 0 );
-    if( mask == 0 ) return;
-    unsigned int inc = np;
-    #pragma unroll
-    for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( 0xFFFFFFFFu, inc, o ); if( lane >= o ) inc += v; }
-    const unsigned int total = __shfl_sync( 0xFFFFFFFFu, inc, 31 );
-    unsigned long long base = 0;
-    if( lane == 0 ) base = atomicAdd( &ctr->task_stack, ( ( unsigned long long )__popc( mask ) << ACN_TASK_SHIFT ) | total );
-    base = __shfl_sync( 0xFFFFFFFFu, base, 0 );
-    if( np == 0 ) return;
-    const unsigned long long slot = ( base >> ACN_TASK_SHIFT ) + __popc( mask & ( ( 1u << lane ) - 1 ) );
-    if( slot >= stack_cap ) { ctr->overflow = 3; return; }
-    stack.pos_id[ slot ] = in.pos_id[ i ]; stack.nrm_ci[ slot ] = in.nrm_ci[ i ];
-    stack.prj_a[ slot ]  = in.prj_a[ i ];  stack.tpc_b[ slot ]  = in.tpc_b[ i ];
-    stack.meta[ slot ] = in.meta[ i ]; stack.rv0[ slot ] = in.rv0[ i ]; stack.key[ slot ] = in.key[ i ];
-    stack.cum[ slot ] = ( base & ACN_TASK_MASK ) + inc;
+    const int L = prm.n_lights;
+    const unsigned long long n_blocks = blk_hi - blk_lo;
+    unsigned long long n_path = 0;
+    for( ;; )
+    {
+        const unsigned long long b0 = warp_fetch( &w.sc->cur_path, ACN_CHUNK, lane );
+        if( b0 >= n_blocks ) break;
+        for( unsigned long long bb = b0; bb < b0 + ACN_CHUNK && bb < n_blocks; bb++ )
+        {
+            const unsigned long long blk = blk_lo + bb;
+            const ListWindow lw = list_window( in.cum, pdir, blk, n_entries, lane );
+            const unsigned long long idx = ( blk << 5 ) + lane;
+            const bool live = idx < c_hi;
+            const int j = window_find( lw.incl, live ? idx : ( blk << 5 ) );
+            const unsigned long long prev = __shfl_sync( ACN_FULL, lw.incl, ( j + 31 ) & 31 );
+            R miss = R( 0 );
+            V3<R> tpm = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+            int sample = -1;
+            if( live )
+            {
+                const unsigned long long t = ( unsigned long long )lw.e0 + j;
+                const unsigned int i = ( unsigned int )( idx - ( j ? prev : lw.excl0 ) );
+                const I4 m = in.meta[ t ];
+                sample = m.x;
+                const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+                const V3<R> nrm = xyz( nc );
+                const Basis<R> bs = basis_con_z( nrm );
+                u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )L * ( unsigned int )m.z + i );
+                Ray<R> out; out.p = xyz( pi );
+                out.d = from_basis( bs, sphere_cap<R>( &rv, R( 1 ) ) );
+                R wgt = dot( out.d, nrm );
+                tpm = xyz( tb ) * ( R( 2 ) / ( R )( unsigned int )m.w );                     // scene.c:620
+                if( wgt > R( 0 ) )                                                           // scene.c:600
+                {
+                    if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, xyz( pa ) );
+                    n_path++;
+                    const R ci = wgt * pi.w;
+                    const bool probe = ( m.y - 10 ) == 0 || ci < prm.min_intensity;
+                    if( trace_ray( w, out, ci, m.y - 10, tpm, RC_PATH, probe, m.x, mix64( in.key[ t ], KEY_PATH0 + i ) ) ) miss = ci;
+                }
+            }
+            __syncwarp();
+            // children that left the scene: background * throughput * sum of their intensities, one
+            // atomic triple per task segment
+            const int key = live ? j : -1;
+            miss = seg_sum( miss, key, lane );
+            const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
+            if( live && ( lane == 0 || kprev != key ) && miss != R( 0 ) ) add_sample( w, sample, mul( prm.background, tpm ) * miss );
+        }
+    }
+    warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
 }
 
-// finds the first task of the top slice of the stack whose path children fit the budget
-__global__ void k_plan( const u64* cum, unsigned long long n_tasks, unsigned long long budget, Counters* ctr )
+// New tasks of the iteration -> (a) the direct list: one entry per task with >= 1 shadow child,
+// (b) the task stack: tasks that still have path children.  A warp allocates its entries and their
+// child ranges with ONE packed atomic (entries << 38 | children), so entry order and child order agree.
+template <typename R> __global__ void __launch_bounds__( 256 )
+k_index( Sched* s, TaskBuf<R> in, unsigned long long in_cap, int n_lights,
+         u64* __restrict__ dl_cum, unsigned int* __restrict__ dl_slot, unsigned int* __restrict__ dl_dir,
+         unsigned long long dl_cap, unsigned long long dl_dir_cap,
+         TaskBuf<R> stack, unsigned int* __restrict__ pdir, unsigned long long stack_cap, unsigned long long pdir_cap )
 {
-    if( threadIdx.x != 0 || blockIdx.x != 0 ) return;
-    const unsigned long long top = cum[ n_tasks - 1 ];
-    // smallest s such that top - cum[s-1] <= budget  (cum[-1] := base of the stack, 0)
-    unsigned long long lo = 0, hi = n_tasks - 1;     // always take at least the top task
-    while( lo < hi )
+    if( blockIdx.x == 0 && threadIdx.x == 0 && s->fix_slot != ACN_NONE64 ) { stack.cum[ s->fix_slot ] = s->fix_cum; s->fix_slot = ACN_NONE64; }
+    unsigned long long count = s->tasks_new;
+    if( count > in_cap ) count = in_cap;
+    if( count == 0 || s->overflow ) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = ( 1u << lane ) - 1u;
+    const unsigned long long warps = ( ( unsigned long long )gridDim.x * blockDim.x ) >> 5;
+    for( unsigned long long g = ( ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x ) >> 5; ( g << 5 ) < count; g += warps )
     {
-        unsigned long long mid = ( lo + hi ) >> 1;
-        unsigned long long before = mid ? cum[ mid - 1 ] : 0;
-        if( top - before <= budget ) hi = mid; else lo = mid + 1;
+        const unsigned long long i = ( g << 5 ) + lane;
+        I4 m; m.x = m.y = m.z = m.w = 0;
+        if( i < count ) m = in.meta[ i ];
+        // ---- direct list
+        {
+            const unsigned int cd = ( unsigned int )m.z * ( unsigned int )n_lights;
+            const unsigned int mask = __ballot_sync( ACN_FULL, cd > 0 );
+            if( mask )
+            {
+                unsigned int inc = cd;
+                #pragma unroll
+                for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( ACN_FULL, inc, o ); if( lane >= o ) inc += v; }
+                const unsigned int total = __shfl_sync( ACN_FULL, inc, 31 );
+                unsigned long long base = 0;
+                if( lane == 0 ) base = atomicAdd( &s->dl_packed, ( ( unsigned long long )__popc( mask ) << ACN_TASK_SHIFT ) | total );
+                base = __shfl_sync( ACN_FULL, base, 0 );
+                if( cd > 0 )
+                {
+                    const unsigned long long e = ( base >> ACN_TASK_SHIFT ) + __popc( mask & lt );
+                    const unsigned long long incl = ( base & ACN_TASK_MASK ) + inc, excl = incl - cd;
+                    if( e < dl_cap && ( ( incl + 31 ) >> 5 ) <= dl_dir_cap )
+                    {
+                        dl_cum[ e ] = incl; dl_slot[ e ] = ( unsigned int )i;
+                        for( unsigned long long b = ( excl + 31 ) >> 5; ( b << 5 ) < incl; b++ ) dl_dir[ b ] = ( unsigned int )e;
+                    }
+                    else s->overflow = 4;
+                }
+            }
+        }
+        // ---- task stack
+        {
+            const unsigned int np = ( unsigned int )m.w;
+            const unsigned int mask = __ballot_sync( ACN_FULL, np > 0 );
+            if( mask )
+            {
+                unsigned int inc = np;
+                #pragma unroll
+                for( int o = 1; o < 32; o <<= 1 ) { unsigned int v = __shfl_up_sync( ACN_FULL, inc, o ); if( lane >= o ) inc += v; }
+                const unsigned int total = __shfl_sync( ACN_FULL, inc, 31 );
+                unsigned long long base = 0;
+                if( lane == 0 ) base = atomicAdd( &s->task_stack, ( ( unsigned long long )__popc( mask ) << ACN_TASK_SHIFT ) | total );
+                base = __shfl_sync( ACN_FULL, base, 0 );
+                if( np > 0 )
+                {
+                    const unsigned long long e = ( base >> ACN_TASK_SHIFT ) + __popc( mask & lt );
+                    const unsigned long long incl = ( base & ACN_TASK_MASK ) + inc, excl = incl - np;
+                    if( e < stack_cap && ( ( incl + 31 ) >> 5 ) <= pdir_cap )
+                    {
+                        stack.pos_id[ e ] = in.pos_id[ i ]; stack.nrm_ci[ e ] = in.nrm_ci[ i ];
+                        stack.prj_a[ e ]  = in.prj_a[ i ];  stack.tpc_b[ e ]  = in.tpc_b[ i ];
+                        stack.meta[ e ] = m; stack.rv0[ e ] = in.rv0[ i ]; stack.key[ e ] = in.key[ i ];
+                        stack.cum[ e ] = incl;
+                        for( unsigned long long b = ( excl + 31 ) >> 5; ( b << 5 ) < incl; b++ ) pdir[ b ] = ( unsigned int )e;
+                    }
+                    else s->overflow = 3;
+                }
+            }
+        }
     }
-    ctr->plan_start = lo;
-    ctr->plan_cum = lo ? cum[ lo - 1 ] : 0;
 }
 
 // cl_s_sat (vectors.h:372-384, scene.c:1010): pow(c, gamma) then clamp, per sample
@@ -709,13 +910,16 @@ template <typename R> struct Tracer : TracerBase
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
     // queues
     RayBuf<R>  ray_stack, ray_cur;
-    TaskBuf<R> task_stack, task_cur, task_new;
-    uint64_t   ray_cap = 0, task_stack_cap = 0, budget = 0;
-    Counters*  d_ctr = nullptr;
-    Counters*  h_ctr = nullptr;       // pinned
+    TaskBuf<R> task_stack, task_new;
+    u64* d_dl_cum = nullptr; unsigned int* d_dl_slot = nullptr; unsigned int* d_dl_dir = nullptr; unsigned int* d_pdir = nullptr;
+    uint64_t   budget = 0, ray_min = 0, ray_cap = 0, task_stack_cap = 0, task_new_cap = 0, dl_dir_cap = 0, pdir_cap = 0, prim_chunk = 0;
+    Sched*     d_sc = nullptr;
+    Sched*     h_sc = nullptr;        // pinned
     R*         d_accum = nullptr; uint64_t accum_cap = 0;
     int        smem_bytes = 0;
     int        max_csg_depth = 0;
+    int        grid_trace[ 4 ] = { 0, 0, 0, 0 };   // persistent grids: primary, rays, path, direct
+    int        grid_util = 0;
 
     ~Tracer() override
     {
@@ -724,8 +928,9 @@ template <typename R> struct Tracer : TracerBase
         cudaFree( d_prog ); cudaFree( d_prog_ref ); cudaFree( d_parent );
         cudaFree( d_mats ); cudaFree( d_lights ); cudaFree( d_skipA ); cudaFree( d_skipC );
         free_rays( ray_stack ); free_rays( ray_cur );
-        free_tasks( task_stack ); free_tasks( task_cur ); free_tasks( task_new );
-        cudaFree( d_ctr ); if( h_ctr ) cudaFreeHost( h_ctr );
+        free_tasks( task_stack ); free_tasks( task_new );
+        cudaFree( d_dl_cum ); cudaFree( d_dl_slot ); cudaFree( d_dl_dir ); cudaFree( d_pdir );
+        cudaFree( d_sc ); if( h_sc ) cudaFreeHost( h_sc );
         cudaFree( d_accum ); cudaFree( d_xy_stage ); cudaFree( d_rgb_stage );
         if( own_stream ) cudaStreamDestroy( own_stream );
     }
@@ -734,12 +939,11 @@ template <typename R> struct Tracer : TracerBase
     int render( const double* d_xy, uint64_t n, uint64_t index_base, float* d_rgb, cudaStream_t st,
                 const volatile int* cancel, acn_stats* stats ) override;
 
-    Wave<R> make_wave( uint64_t rays_base, uint64_t index_base )
+    Wave<R> make_wave( uint64_t index_base )
     {
         Wave<R> w;
-        w.prm = prm; w.rays_out = ray_stack; w.tasks_out = task_new; w.ctr = d_ctr; w.accum = d_accum;
-        w.rays_out_base = rays_base; w.rays_cap = ray_cap; w.tasks_cap = budget;
-        w.sample_base = 0; w.index_base = index_base;
+        w.prm = prm; w.rays_out = ray_stack; w.tasks_out = task_new; w.sc = d_sc; w.accum = d_accum;
+        w.rays_cap = ray_cap; w.tasks_cap = task_new_cap; w.index_base = index_base;
         return w;
     }
 };
@@ -1069,17 +1273,46 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         if( cur < want ) ACN_CUDA( cudaDeviceSetLimit( cudaLimitStackSize, want ) );
     }
 
-    // ---- queues
-    budget = opt->wave_budget > 0 ? ( uint64_t )opt->wave_budget : ( 1ull << 21 );
+
+    // ---- queues.  budget = path children (and explicit rays) traced per wavefront iteration
+    budget = opt->wave_budget > 0 ? ( uint64_t )opt->wave_budget : ( 1ull << 22 );
+    if( budget < 64 ) budget = 64;
+    ray_min = budget / 4 < 65536 ? budget / 4 : 65536;      // smaller ray waves wait for company while path work is pending
     ray_cap = budget * 24;
     task_stack_cap = budget * 6;
+    task_new_cap = budget * 2 + 64;
+    dl_dir_cap = task_new_cap * 16 > ( 1ull << 20 ) ? task_new_cap * 16 : ( 1ull << 20 );
+    pdir_cap = budget * 32 > ( 1ull << 20 ) ? budget * 32 : ( 1ull << 20 );
+    if( pdir_cap > ( 1ull << 27 ) ) pdir_cap = 1ull << 27;
+    prim_chunk = budget;
+    {   // first-generation tasks must fit the task-stack directory: chunk * path_samples children
+        const uint64_t ps = prm.path_samples > 0 ? ( uint64_t )prm.path_samples : 1;
+        const uint64_t lim = pdir_cap * 32 / ps / 2;
+        if( prim_chunk > lim ) prim_chunk = lim > 32 ? lim : 32;
+    }
     if( ( rc = alloc_rays( ray_stack, ray_cap ) ) ) return rc;
     if( ( rc = alloc_rays( ray_cur, budget ) ) ) return rc;
     if( ( rc = alloc_tasks( task_stack, task_stack_cap ) ) ) return rc;
-    if( ( rc = alloc_tasks( task_cur, task_stack_cap ) ) ) return rc;
-    if( ( rc = alloc_tasks( task_new, budget ) ) ) return rc;
-    if( ( rc = dev_alloc( &d_ctr, 1 ) ) ) return rc;
-    ACN_CUDA( cudaMallocHost( ( void** )&h_ctr, sizeof( Counters ) ) );
+    if( ( rc = alloc_tasks( task_new, task_new_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_dl_cum, task_new_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_dl_slot, task_new_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_dl_dir, dl_dir_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_pdir, pdir_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_sc, 1 ) ) ) return rc;
+    ACN_CUDA( cudaMallocHost( ( void** )&h_sc, sizeof( Sched ) ) );
+
+    // ---- persistent grids: as many blocks as are resident at once
+    {
+        cudaDeviceProp pr;
+        ACN_CUDA( cudaGetDeviceProperties( &pr, device ) );
+        const int sms = pr.multiProcessorCount;
+        int b = 0;
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_primary<R>, ACN_BLOCK, smem_bytes ) ); grid_trace[ 0 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_rays<R>, ACN_BLOCK, smem_bytes ) );    grid_trace[ 1 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_path<R>, ACN_BLOCK, smem_bytes ) );    grid_trace[ 2 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_direct<R>, ACN_BLOCK, smem_bytes ) );  grid_trace[ 3 ] = sms * ( b > 0 ? b : 1 );
+        grid_util = sms * 4;
+    }
     return ACN_OK;
 }
 
@@ -1103,119 +1336,66 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     ACN_CUDA( cudaEventCreate( &ev0 ) ); ACN_CUDA( cudaEventCreate( &ev1 ) );
     ACN_CUDA( cudaEventRecord( ev0, st ) );
     ACN_CUDA( cudaMemsetAsync( d_accum, 0, ( size_t )n * 3 * sizeof( R ), st ) );
-    ACN_CUDA( cudaMemsetAsync( d_ctr, 0, sizeof( Counters ), st ) );
+    ACN_CUDA( cudaMemsetAsync( d_sc, 0, sizeof( Sched ), st ) );
 
-    uint64_t launches = 0, waves = 0;
-    // optional per-kernel timing (ACN_PROFILE_KERNELS=1): events around the launches of each kernel class
-    struct KProf { bool on = false; cudaEvent_t a[ 4 ], b[ 4 ]; bool used[ 4 ] = { false, false, false, false }; double ms[ 4 ] = { 0, 0, 0, 0 }; unsigned long long cnt[ 4 ] = { 0, 0, 0, 0 }; } kp;
+    uint64_t launches = 0;
+    // optional per-kernel timing (ACN_PROFILE_KERNELS=1): an event pair around every launch of the four tracing kernels
+    struct KProf { bool on = false; std::vector<cudaEvent_t> a[ 4 ], b[ 4 ]; } kp;
     { const char* e = getenv( "ACN_PROFILE_KERNELS" ); kp.on = e && e[ 0 ] == '1'; }
-    if( kp.on ) for( int c = 0; c < 4; c++ ) { cudaEventCreate( &kp.a[ c ] ); cudaEventCreate( &kp.b[ c ] ); }
-    auto kp_begin = [ & ]( int c ) { if( kp.on ) cudaEventRecord( kp.a[ c ], st ); };
-    auto kp_end = [ & ]( int c ) { if( kp.on ) { cudaEventRecord( kp.b[ c ], st ); kp.used[ c ] = true; } };
-    auto kp_collect = [ & ]() { if( kp.on ) for( int c = 0; c < 4; c++ ) if( kp.used[ c ] ) { float m = 0; cudaEventElapsedTime( &m, kp.a[ c ], kp.b[ c ] ); kp.ms[ c ] += m; kp.cnt[ c ]++; kp.used[ c ] = false; } };
-    uint64_t nr = 0;                 // rays on the stack
-    uint64_t nt = 0, nt_cum = 0;     // tasks on the stack, their total path children
-    unsigned long long stat_sum[ ST_COUNT ] = { 0 };
+    auto kp_begin = [ & ]( int c ) { if( kp.on ) { cudaEvent_t e; cudaEventCreate( &e ); cudaEventRecord( e, st ); kp.a[ c ].push_back( e ); } };
+    auto kp_end = [ & ]( int c ) { if( kp.on ) { cudaEvent_t e; cudaEventCreate( &e ); cudaEventRecord( e, st ); kp.b[ c ].push_back( e ); } };
+
+    const Wave<R> w = make_wave( index_base );
     int result = ACN_OK;
 
-    // after every wave: direct lighting of the new tasks, keep those with path work, read the counters
-    auto post_wave = [ & ]( uint64_t rays_base ) -> int
+    // one k_sched + the kernels it planned; nothing here depends on device-side counts
+    auto enqueue = [ & ]( int mode, uint64_t first, uint64_t cnt )
     {
-        ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
-        ACN_CUDA( cudaStreamSynchronize( st ) );
-        kp_collect();
-        if( h_ctr->overflow ) { set_error( "wavefront queue overflow (code %d): raise acn_options.wave_budget", h_ctr->overflow ); return ACN_ERR_OUT_OF_MEMORY; }
-        const uint64_t new_tasks = h_ctr->tasks_new, new_path = h_ctr->tasks_new_path;
-        stat_sum[ ST_DIFFUSE ] += new_tasks;
-        nr = rays_base + h_ctr->rays_out;
-        if( new_tasks )
+        k_sched<<< 1, 32, 0, st >>>( d_sc, task_stack.cum, d_pdir, budget, ray_min, mode, first, cnt );
+        launches++;
+        if( mode == SCHED_PRIMARY )
         {
-            Wave<R> w = make_wave( nr, index_base );
-            const unsigned warps = ( unsigned )( ( new_tasks + 31 ) / 32 );
-            kp_begin( 3 );
-            k_direct<R><<< grid_for( warps, ACN_BLOCK / 32 ), ACN_BLOCK, smem_bytes, st >>>( w, task_new, new_tasks );
-            kp_end( 3 );
-            launches++;
-            if( new_path )
-            {
-                k_keep<R><<< grid_for( new_tasks, 256 ), 256, 0, st >>>( task_new, new_tasks, task_stack, task_stack_cap, d_ctr );
-                launches++;
-            }
-            ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
-            ACN_CUDA( cudaStreamSynchronize( st ) );
-            kp_collect();
-            if( h_ctr->overflow ) { set_error( "wavefront queue overflow (code %d): raise acn_options.wave_budget", h_ctr->overflow ); return ACN_ERR_OUT_OF_MEMORY; }
-            nt = h_ctr->task_stack >> ACN_TASK_SHIFT;
-            nt_cum = h_ctr->task_stack & ACN_TASK_MASK;
-        }
-        // reset the per-wave counters (stats keep accumulating on the device)
-        ACN_CUDA( cudaMemsetAsync( d_ctr, 0, offsetof( Counters, task_stack ), st ) );
-        waves++;
-        return ACN_OK;
-    };
-
-    for( uint64_t first = 0; first < n && result == ACN_OK; first += budget )
-    {
-        const uint64_t cnt = ( n - first < budget ) ? n - first : budget;
-        {
-            Wave<R> w = make_wave( 0, index_base );
             kp_begin( 0 );
-            k_primary<R><<< grid_for( cnt, ACN_BLOCK ), ACN_BLOCK, smem_bytes, st >>>( w, d_xy, first, cnt );
+            k_primary<R><<< grid_trace[ 0 ], ACN_BLOCK, smem_bytes, st >>>( w, d_xy );
             kp_end( 0 );
             launches++;
-            if( ( result = post_wave( 0 ) ) ) break;
         }
-        while( nr > 0 || nt > 0 )
+        else
         {
+            k_pop<R><<< grid_util, 256, 0, st >>>( d_sc, ray_stack, ray_cur );
+            kp_begin( 1 );
+            k_rays<R><<< grid_trace[ 1 ], ACN_BLOCK, smem_bytes, st >>>( w, ray_cur );
+            kp_end( 1 );
+            kp_begin( 2 );
+            k_path<R><<< grid_trace[ 2 ], ACN_BLOCK, smem_bytes, st >>>( w, task_stack, d_pdir );
+            kp_end( 2 );
+            launches += 3;
+        }
+        k_index<R><<< grid_util, 256, 0, st >>>( d_sc, task_new, task_new_cap, prm.n_lights, d_dl_cum, d_dl_slot, d_dl_dir, task_new_cap, dl_dir_cap,
+                                                 task_stack, d_pdir, task_stack_cap, pdir_cap );
+        kp_begin( 3 );
+        k_direct<R><<< grid_trace[ 3 ], ACN_BLOCK, smem_bytes, st >>>( w, task_new, d_dl_cum, d_dl_slot, d_dl_dir );
+        kp_end( 3 );
+        launches += 2;
+    };
+
+    const int iters_per_poll = 4;
+    for( uint64_t first = 0; first < n && result == ACN_OK; first += prim_chunk )
+    {
+        const uint64_t cnt = ( n - first < prim_chunk ) ? n - first : prim_chunk;
+        enqueue( SCHED_PRIMARY, first, cnt );
+        for( ;; )
+        {
+            for( int k = 0; k < iters_per_poll; k++ ) enqueue( SCHED_WAVE, 0, 0 );
+            ACN_CUDA( cudaMemcpyAsync( h_sc, d_sc, sizeof( Sched ), cudaMemcpyDeviceToHost, st ) );
+            ACN_CUDA( cudaStreamSynchronize( st ) );
+            if( h_sc->overflow )
+            {
+                set_error( "wavefront queue overflow (code %d): change acn_options.wave_budget", h_sc->overflow );
+                result = ACN_ERR_OUT_OF_MEMORY; break;
+            }
+            if( h_sc->done ) break;
             if( cancel && *cancel ) { result = ACN_ERR_CANCELLED; break; }
-            if( nr > 0 )
-            {
-                // pop the top `take` rays into ray_cur
-                const uint64_t take = nr < budget ? nr : budget;
-                const uint64_t base = nr - take;
-                ACN_CUDA( cudaMemcpyAsync( ray_cur.o_i, ray_stack.o_i + base, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( ray_cur.d_, ray_stack.d_ + base, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( ray_cur.tp, ray_stack.tp + base, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( ray_cur.meta, ray_stack.meta + base, take * sizeof( I4 ), cudaMemcpyDeviceToDevice, st ) );
-                Wave<R> w = make_wave( base, index_base );
-                kp_begin( 1 );
-                k_rays<R><<< grid_for( take, ACN_BLOCK ), ACN_BLOCK, smem_bytes, st >>>( w, ray_cur, take );
-                kp_end( 1 );
-                launches++;
-                if( ( result = post_wave( base ) ) ) break;
-            }
-            else
-            {
-                // cut the top of the task stack at an exact budget of path children
-                uint64_t start = 0, cum_before = 0;
-                if( nt_cum > budget )
-                {
-                    k_plan<<< 1, 32, 0, st >>>( task_stack.cum, nt, budget, d_ctr );
-                    launches++;
-                    ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
-                    ACN_CUDA( cudaStreamSynchronize( st ) );
-                    start = h_ctr->plan_start; cum_before = h_ctr->plan_cum;
-                }
-                const uint64_t take = nt - start;
-                // the popped slice moves to task_cur; the stack counter is rewound to the cut
-                ACN_CUDA( cudaMemcpyAsync( task_cur.pos_id, task_stack.pos_id + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( task_cur.nrm_ci, task_stack.nrm_ci + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( task_cur.prj_a, task_stack.prj_a + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( task_cur.tpc_b, task_stack.tpc_b + start, take * sizeof( R4<R> ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( task_cur.meta, task_stack.meta + start, take * sizeof( I4 ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( task_cur.rv0, task_stack.rv0 + start, take * sizeof( u64 ), cudaMemcpyDeviceToDevice, st ) );
-                ACN_CUDA( cudaMemcpyAsync( task_cur.key, task_stack.key + start, take * sizeof( u64 ), cudaMemcpyDeviceToDevice, st ) );
-                nt = start; nt_cum = cum_before;
-                h_ctr->task_stack = ( ( unsigned long long )nt << ACN_TASK_SHIFT ) | nt_cum;
-                ACN_CUDA( cudaMemcpyAsync( &d_ctr->task_stack, &h_ctr->task_stack, sizeof( unsigned long long ), cudaMemcpyHostToDevice, st ) );
-                Wave<R> w = make_wave( 0, index_base );
-                const unsigned warps = ( unsigned )( ( take + 31 ) / 32 );
-                kp_begin( 2 );
-                k_path<R><<< grid_for( warps, ACN_BLOCK / 32 ), ACN_BLOCK, smem_bytes, st >>>( w, task_cur, take );
-                kp_end( 2 );
-                launches++;
-                if( ( result = post_wave( 0 ) ) ) break;
-            }
         }
     }
 
@@ -1224,25 +1404,38 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         k_finish<R><<< grid_for( n * 3, 256 ), 256, 0, st >>>( d_accum, n, prm.gamma, d_rgb );
         launches++;
     }
-    ACN_CUDA( cudaMemcpyAsync( h_ctr, d_ctr, sizeof( Counters ), cudaMemcpyDeviceToHost, st ) );
+    ACN_CUDA( cudaMemcpyAsync( h_sc, d_sc, sizeof( Sched ), cudaMemcpyDeviceToHost, st ) );
     ACN_CUDA( cudaEventRecord( ev1, st ) );
     ACN_CUDA( cudaStreamSynchronize( st ) );
     cudaError_t le = cudaGetLastError();
     if( le != cudaSuccess ) { set_error( "kernel failure: %s", cudaGetErrorString( le ) ); result = ACN_ERR_CUDA; }
     float ms = 0; cudaEventElapsedTime( &ms, ev0, ev1 );
     cudaEventDestroy( ev0 ); cudaEventDestroy( ev1 );
-    for( int i = 0; i < ST_COUNT; i++ ) if( i != ST_DIFFUSE ) stat_sum[ i ] = h_ctr->stats[ i ];
     if( stats )
     {
+        const unsigned long long* ss = h_sc->stats;
         stats->samples = n;
-        stats->rays_primary = stat_sum[ ST_PRIMARY ]; stats->rays_reflection = stat_sum[ ST_REFLECT ];
-        stats->rays_chromatic = stat_sum[ ST_CHROMATIC ]; stats->rays_refraction = stat_sum[ ST_REFRACT ];
-        stats->rays_path = stat_sum[ ST_PATH ]; stats->rays_shadow = stat_sum[ ST_SHADOW ];
-        stats->rays_light = stat_sum[ ST_LIGHT ]; stats->diffuse_hits = stat_sum[ ST_DIFFUSE ];
-        stats->kernel_launches = launches; stats->waves = waves; stats->device_ms = ms;
-        for( int c = 0; c < 4; c++ ) { stats->kernel_ms[ c ] = kp.ms[ c ]; stats->kernel_launches_by_class[ c ] = kp.cnt[ c ]; }
+        stats->rays_primary = ss[ ST_PRIMARY ]; stats->rays_reflection = ss[ ST_REFLECT ];
+        stats->rays_chromatic = ss[ ST_CHROMATIC ]; stats->rays_refraction = ss[ ST_REFRACT ];
+        stats->rays_path = ss[ ST_PATH ]; stats->rays_shadow = ss[ ST_SHADOW ];
+        stats->rays_light = ss[ ST_LIGHT ]; stats->diffuse_hits = ss[ ST_DIFFUSE ];
+        stats->kernel_launches = launches; stats->waves = h_sc->waves; stats->device_ms = ms;
     }
-    if( kp.on ) for( int c = 0; c < 4; c++ ) { cudaEventDestroy( kp.a[ c ] ); cudaEventDestroy( kp.b[ c ] ); }
+    if( kp.on )
+    {
+        for( int c = 0; c < 4; c++ )
+        {
+            double tot = 0;
+            for( size_t i = 0; i < kp.a[ c ].size() && i < kp.b[ c ].size(); i++ )
+            {
+                float m = 0;
+                if( cudaEventElapsedTime( &m, kp.a[ c ][ i ], kp.b[ c ][ i ] ) == cudaSuccess ) tot += m;
+                cudaEventDestroy( kp.a[ c ][ i ] ); cudaEventDestroy( kp.b[ c ][ i ] );
+            }
+            if( stats ) { stats->kernel_ms[ c ] = tot; stats->kernel_launches_by_class[ c ] = kp.a[ c ].size(); }
+        }
+        cudaGetLastError();
+    }
     return result;
 }
 

@@ -243,7 +243,7 @@ def main():
     d_acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-    os.environ["ACN_PROFILE_KERNELS"] = "1"  # per-kernel-class CUDA events inside the library (events only)
+    os.environ.pop("ACN_PROFILE_KERNELS", None)
 
     def barrier():
         if world > 1:
@@ -282,8 +282,6 @@ def main():
         e1.record(stream)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
-        kernel_ms += np.array(list(st.kernel_ms))
-        kernel_cnt += np.array(list(st.kernel_launches_by_class))
         launches += st.kernel_launches + 1 + (1 if world > 1 else 0)
         rays += st.rays
         for k in ("rays_primary", "rays_reflection", "rays_chromatic", "rays_refraction", "rays_path", "rays_shadow", "diffuse_hits"):
@@ -292,6 +290,15 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
     total_ms = float(sum(step_ms))
+
+    # ---- one extra, untimed step with an event pair around every tracing-kernel launch (kernel shares for the roofline)
+    os.environ["ACN_PROFILE_KERNELS"] = "1"
+    st = device_step()
+    torch.cuda.synchronize(dev)
+    os.environ.pop("ACN_PROFILE_KERNELS", None)
+    kernel_ms = np.array(list(st.kernel_ms)) * args.steps            # scaled so that the per-step figures below hold
+    kernel_cnt = np.array(list(st.kernel_launches_by_class)) * args.steps
+    prof_step_ms = st.device_ms
 
     # ---- end to end through the reference-facing call with host buffers (pinned), same K steps
     h_xy = torch.from_numpy(xy_np).pin_memory()
@@ -342,7 +349,8 @@ def main():
             "traffic": None, "peak_source": "measured live: dependent-free FFMA chains on every SM (acn_measure_fp32_peak_tflops)",
             "kernel_ms_per_step": {class_names[i]: kernel_ms[i] / args.steps for i in range(4)},
             "kernel_launches_per_step": {class_names[i]: kernel_cnt[i] / args.steps for i in range(4)},
-            "kernel_share_of_step": {class_names[i]: kernel_ms[i] / total_ms for i in range(4)} if world == 1 else None}
+            "kernel_share_of_step": {class_names[i]: kernel_ms[i] / args.steps / prof_step_ms for i in range(4)},
+            "kernel_timing": "CUDA-event pairs around every launch of the four tracing kernels in one extra untimed step"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from tests.oracle_lib import Oracle
