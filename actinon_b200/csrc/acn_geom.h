@@ -32,7 +32,7 @@ enum { GEO_STRIDE = 5 };
 enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
 enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
 enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5 };   // instr = op | node << 4; CSG_ENV is followed by a skip count
-enum { CSG_K = 8, CSG_S = 8 };   // events per interval list, lists on the evaluation stack
+enum { CSG_K = 8, CSG_S = 4, CSG_SLOTS = CSG_S + 1, CSG_VIRTUAL = 255 };   // events per interval list, lists on the evaluation stack (+1 scratch)
 
 template <typename R> struct SceneView
 {
@@ -40,7 +40,7 @@ template <typename R> struct SceneView
     const I4*    link;
     const R4<R>* geo;
     const int*   children;
-    const int*   prog;      // postfix CSG programs (interval evaluator), see csg_fast_hit
+    const int*   prog;      // postfix CSG programs (interval evaluator), see acn_isect.cuh: csg_eval
     const int*   prog_ref;  // per node: [2n] start into prog, [2n+1] length (0: no program -> reference march)
     const int*   parent;    // per node: CSG parent (-1 at the top of an object)
     R   eps;            // shell thickness (f3_eps, vectors.h:33)
@@ -114,6 +114,88 @@ template <typename R> ACN_HD M3<R> node_rax( const SceneView<R>& sv, int n )
     return m;
 }
 
+// distance-field objects (objects.c:903-959): sphere tracing in the scaled object frame.  Kept out of line:
+// it is the heaviest and most divergent primitive and must not bloat every intersection site.
+template <typename R> ACN_NOINLINE R dist_hit( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, V3<R>* nor )
+{
+    const R inf = Num<R>::inf();
+    const R eps = sv.eps;
+    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
+    const V3<R> pos = xyz( g0 );
+    const M3<R> rax = node_rax( sv, n );
+
+    const R inv_scale = g0.w;
+    const R ex_radius = sv.geo[ n * GEO_STRIDE + 1 ].w;
+    const int cycles  = ( int )sv.geo[ n * GEO_STRIDE + 2 ].w;
+    const I4 lk = sv.link[ n ];
+    Ray<R> rl = ray;
+    R offs0 = R( 0 );
+    if( node_flags( lk ) & F_ENV )
+    {
+        const R4<R> e = sv.env[ n ];
+        if( sphere_side( xyz( e ), e.w, ray.p ) == 1 )
+        {
+            offs0 = sphere_hit<R>( xyz( e ), e.w, ray, eps, nullptr );
+            if( !( offs0 < inf ) ) return inf;
+            rl.p = madd( ray.p, ray.d, offs0 );
+        }
+    }
+    V3<R> lp = mlv( rax, rl.p - pos ) * inv_scale;
+    V3<R> ld = mlv( rax, rl.d );
+    R offs1 = R( 0 );
+    R dist = dist_fn( kind, ex_radius, lp );
+    if( dist > R( 0 ) )
+    {
+        for( int i = 0; i < cycles; i++ )
+        {
+            offs1 += dist + eps;
+            dist = dist_fn( kind, ex_radius, madd( lp, ld, offs1 ) );
+            if( dist < R( 0 ) || dist > Num<R>::mag() ) break;
+        }
+    }
+    else
+    {
+        for( int i = 0; i < cycles; i++ )
+        {
+            offs1 -= dist - eps;
+            dist = dist_fn( kind, ex_radius, madd( lp, ld, offs1 ) );
+            if( dist > R( 0 ) || dist < -Num<R>::mag() ) break;
+        }
+    }
+    if( r_abs( dist ) <= eps )
+    {
+        if( nor )
+        {
+            V3<R> p = madd( lp, ld, offs1 );
+            V3<R> g;
+            if( sizeof( R ) == 8 )
+            {
+                // the reference's forward differences with step eps (objects.c:947-953)
+                R d0 = dist_fn( kind, ex_radius, p );
+                g.x = ( dist_fn( kind, ex_radius, v3<R>( p.x + eps, p.y, p.z ) ) - d0 ) / eps;
+                g.y = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y + eps, p.z ) ) - d0 ) / eps;
+                g.z = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y, p.z + eps ) ) - d0 ) / eps;
+            }
+            else
+            {
+                // FP32: a difference quotient over eps would carry ~1e-3 rounding noise; both
+                // distance functions have a closed-form gradient, which the quotient approximates
+                // to O(eps) — use it.  torus: unit vector from the nearest point of the core circle.
+                g = p;
+                if( kind == K_DIST_TORUS )
+                {
+                    R f = r_sqrt( p.x * p.x + p.y * p.y );
+                    R fi = f > R( 0 ) ? R( 1 ) / f : R( 1 );
+                    g = v3<R>( p.x - p.x * fi, p.y - p.y * fi, p.z );
+                }
+            }
+            *nor = unit( tmlv( rax, g ) );
+        }
+        return offs0 + offs1 / inv_scale - eps;
+    }
+    return inf;
+}
+
 // ---------------------------------------------------------------------------------------------
 // primitives: fp_ray_hit of plane / sphere / squaroid / distance objects
 // (gmath.h:38-45, objects.c:529-537,649-657,778-821,903-959).  No envelope test, no roughness.
@@ -183,79 +265,7 @@ template <typename R> ACN_HD R prim_hit( const SceneView<R>& sv, int kind, int n
         return a - eps;
     }
 
-    // distance-field objects: sphere tracing in the scaled object frame
-    {
-        const R inv_scale = g0.w;
-        const R ex_radius = sv.geo[ n * GEO_STRIDE + 1 ].w;
-        const int cycles  = ( int )sv.geo[ n * GEO_STRIDE + 2 ].w;
-        const I4 lk = sv.link[ n ];
-        Ray<R> rl = ray;
-        R offs0 = R( 0 );
-        if( node_flags( lk ) & F_ENV )
-        {
-            const R4<R> e = sv.env[ n ];
-            if( sphere_side( xyz( e ), e.w, ray.p ) == 1 )
-            {
-                offs0 = sphere_hit<R>( xyz( e ), e.w, ray, eps, nullptr );
-                if( !( offs0 < inf ) ) return inf;
-                rl.p = madd( ray.p, ray.d, offs0 );
-            }
-        }
-        V3<R> lp = mlv( rax, rl.p - pos ) * inv_scale;
-        V3<R> ld = mlv( rax, rl.d );
-        R offs1 = R( 0 );
-        R dist = dist_fn( kind, ex_radius, lp );
-        if( dist > R( 0 ) )
-        {
-            for( int i = 0; i < cycles; i++ )
-            {
-                offs1 += dist + eps;
-                dist = dist_fn( kind, ex_radius, madd( lp, ld, offs1 ) );
-                if( dist < R( 0 ) || dist > Num<R>::mag() ) break;
-            }
-        }
-        else
-        {
-            for( int i = 0; i < cycles; i++ )
-            {
-                offs1 -= dist - eps;
-                dist = dist_fn( kind, ex_radius, madd( lp, ld, offs1 ) );
-                if( dist > R( 0 ) || dist < -Num<R>::mag() ) break;
-            }
-        }
-        if( r_abs( dist ) <= eps )
-        {
-            if( nor )
-            {
-                V3<R> p = madd( lp, ld, offs1 );
-                V3<R> g;
-                if( sizeof( R ) == 8 )
-                {
-                    // the reference's forward differences with step eps (objects.c:947-953)
-                    R d0 = dist_fn( kind, ex_radius, p );
-                    g.x = ( dist_fn( kind, ex_radius, v3<R>( p.x + eps, p.y, p.z ) ) - d0 ) / eps;
-                    g.y = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y + eps, p.z ) ) - d0 ) / eps;
-                    g.z = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y, p.z + eps ) ) - d0 ) / eps;
-                }
-                else
-                {
-                    // FP32: a difference quotient over eps would carry ~1e-3 rounding noise; both
-                    // distance functions have a closed-form gradient, which the quotient approximates
-                    // to O(eps) — use it.  torus: unit vector from the nearest point of the core circle.
-                    g = p;
-                    if( kind == K_DIST_TORUS )
-                    {
-                        R f = r_sqrt( p.x * p.x + p.y * p.y );
-                        R fi = f > R( 0 ) ? R( 1 ) / f : R( 1 );
-                        g = v3<R>( p.x - p.x * fi, p.y - p.y * fi, p.z );
-                    }
-                }
-                *nor = unit( tmlv( rax, g ) );
-            }
-            return offs0 + offs1 / inv_scale - eps;
-        }
-        return inf;
-    }
+    return dist_hit( sv, kind, n, ray, nor );
 }
 
 // fp_side of the primitives (gmath.h:52-55,93-97, objects.c:823-827,961-966)
@@ -284,7 +294,7 @@ template <typename R> ACN_HDN int obj_side( const SceneView<R>& sv, int n, V3<R>
 template <typename R> ACN_HDN R   obj_ray_hit( const SceneView<R>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx );
 
 // roughness perturbation of the normal (objects.c:266-282)
-template <typename R> ACN_HD void roughen( const SceneView<R>& sv, int n, const Ray<R>& ray, R a, V3<R>* nor, HitCtx ctx )
+template <typename R> ACN_NOINLINE void roughen( const SceneView<R>& sv, int n, const Ray<R>& ray, R a, V3<R>* nor, HitCtx ctx )
 {
     R rough = sv.geo[ n * GEO_STRIDE + 4 ].x;
     u64 rv = sv.seed_mode == SEED_POSITION_HASH ? random_seed( madd( ray.p, ray.d, a ), ( u64 )1246 )
@@ -336,204 +346,11 @@ template <typename R> ACN_HDN R pair_hit( const SceneView<R>& sv, int o1, int o2
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// CSG by interval lists.  The reference finds the first boundary of A&B / A|B by an alternating
-// march over the children (objects.c:1052-1094,1209-1251), re-tracing whole subtrees for every
-// rejected candidate: O(n^2) ray tests for an n-leaf solid and hopelessly divergent on a GPU.
-// The same first boundary comes out of classifying the ray against every leaf ONCE:
-//   * a leaf yields its state at the origin and its (<= 2) crossings for t > 0;
-//   * '!' complements, '&' intersects, '|' unites the in/out state sequences (merge of two short
-//     sorted lists, keeping only the crossings where the combined state flips);
-//   * a node's envelope clips its inside-set (obj_side reports "outside" beyond the own envelope,
-//     objects.c:365-370, also for negations) with VIRTUAL crossings that are never reported as hits
-//     (obj_ray_hit only returns shape crossings), and gates the whole subtree (objects.c:264).
-// A crossing of leaf X survives to the root exactly when every sibling on the way up is in the state
-// the pair demands — the reference's acceptance test.  Programs are postfix, ordered so that the
-// deeper operand is evaluated first (stack depth = Strahler number of the tree).
-// Supported leaves: plane, sphere, squaroid.  Objects with distance-field or scale nodes keep the
-// reference march.
-// ---------------------------------------------------------------------------------------------
-template <typename R> struct IvStack
-{
-    R   t[ CSG_S ][ CSG_K ];
-    int id[ CSG_S ][ CSG_K ];
-    int n[ CSG_S ];
-    int s0[ CSG_S ];     // 1: inside at the ray origin
-    R   t_valid;         // crossings beyond this parameter are unreliable (a list overflowed CSG_K)
-};
-
-// crossings of a sphere for t > 0 and the state at the origin
-template <typename R> ACN_HD int sphere_events( V3<R> c, R r, const Ray<R>& ray, int* s0, R* t )
-{
-    V3<R> p = ray.p - c;
-    R s = dot( p, ray.d );
-    R q = sqr( p ) - r * r;
-    V3<R> l = p - ray.d * s;
-    R disc = r * r - sqr( l );
-    *s0 = q > R( 0 ) ? 0 : 1;
-    if( disc < R( 0 ) ) return 0;
-    R sq = r_sqrt( disc );
-    if( q > R( 0 ) )
-    {
-        if( !( s < R( 0 ) ) ) return 0;
-        t[ 0 ] = -s - sq; t[ 1 ] = -s + sq;
-        return 2;
-    }
-    if( s < R( 0 ) || q < R( 0 ) ) { t[ 0 ] = -s + sq; return 1; }
-    return 0;
-}
-
-template <typename R> ACN_HD int leaf_events( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, int* s0, R* t )
-{
-    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
-    const V3<R> pos = xyz( g0 );
-    if( kind == K_SPHERE ) return sphere_events( pos, g0.w, ray, s0, t );
-    if( kind == K_PLANE )
-    {
-        V3<R> nz = xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
-        R g = dot( ray.p - pos, nz );
-        R dn = dot( nz, ray.d );
-        *s0 = g > R( 0 ) ? 0 : 1;
-        if( dn == R( 0 ) ) return 0;
-        R t0 = -g / dn;
-        if( t0 > R( 0 ) ) { t[ 0 ] = t0; return 1; }
-        return 0;
-    }
-    // squaroid
-    const M3<R> rax = node_rax( sv, n );
-    const R qa = g0.w, qb = sv.geo[ n * GEO_STRIDE + 1 ].w, qc = sv.geo[ n * GEO_STRIDE + 2 ].w, qr = sv.geo[ n * GEO_STRIDE + 3 ].w;
-    V3<R> p = mlv( rax, ray.p - pos );
-    V3<R> d = mlv( rax, ray.d );
-    V3<R> ad = v3<R>( qa * d.x, qb * d.y, qc * d.z );
-    R f = dot( ad, d ), fs = dot( ad, p );
-    R fq = qa * p.x * p.x + qb * p.y * p.y + qc * p.z * p.z + qr;
-    *s0 = fq > R( 0 ) ? 0 : 1;
-    if( f == R( 0 ) ) return 0;
-    R fi = R( 1 ) / f;
-    R t0 = -fs * fi;
-    V3<R> pm = madd( p, d, t0 );
-    R s = dot( ad, pm ) * fi;
-    R q = ( qa * pm.x * pm.x + qb * pm.y * pm.y + qc * pm.z * pm.z + qr ) * fi;
-    R r = s * s - q;
-    if( r < R( 0 ) ) return 0;
-    r = r_sqrt( r );
-    R ta = t0 - s - r, tb = t0 - s + r;
-    int c = 0;
-    if( ta >= R( 0 ) ) t[ c++ ] = ta;
-    if( tb >= R( 0 ) ) t[ c++ ] = tb;
-    return c;
-}
-
-// outward normal of a leaf at ray parameter t (the unshortened crossing), as its fp_ray_hit reports it
-template <typename R> ACN_HD V3<R> leaf_normal( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, R t )
-{
-    const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
-    const V3<R> pos = xyz( g0 );
-    if( kind == K_PLANE ) return xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
-    if( kind == K_SPHERE ) return unit( madd( ray.p - pos, ray.d, t - sv.eps ) );
-    const M3<R> rax = node_rax( sv, n );
-    V3<R> p = mlv( rax, ray.p - pos );
-    V3<R> d = mlv( rax, ray.d );
-    V3<R> x = madd( p, d, t );
-    return unit( tmlv( rax, v3<R>( x.x * g0.w, x.y * sv.geo[ n * GEO_STRIDE + 1 ].w, x.z * sv.geo[ n * GEO_STRIDE + 2 ].w ) ) );
-}
-
-// combine the two topmost lists: op_and ? intersection : union
-template <typename R> ACN_HD void iv_merge( IvStack<R>& st, int a, int b, bool op_and )
-{
-    R   ot[ CSG_K ];
-    int oi[ CSG_K ];
-    int sa = st.s0[ a ], sb = st.s0[ b ];
-    int s = op_and ? ( sa & sb ) : ( sa | sb );
-    const int s_init = s;
-    const int na = st.n[ a ], nb = st.n[ b ];
-    int i = 0, j = 0, o = 0;
-    while( i < na || j < nb )
-    {
-        bool take_a = j >= nb || ( i < na && st.t[ a ][ i ] <= st.t[ b ][ j ] );
-        R t; int id;
-        if( take_a ) { t = st.t[ a ][ i ]; id = st.id[ a ][ i ]; i++; sa ^= 1; }
-        else         { t = st.t[ b ][ j ]; id = st.id[ b ][ j ]; j++; sb ^= 1; }
-        int s2 = op_and ? ( sa & sb ) : ( sa | sb );
-        if( s2 != s ) { if( o < CSG_K ) { ot[ o ] = t; oi[ o ] = id; } o++; s = s2; }
-    }
-    if( o > CSG_K ) { o = CSG_K; st.t_valid = r_min( st.t_valid, ot[ CSG_K - 1 ] ); }   // exact up to the last kept crossing
-    st.s0[ a ] = s_init; st.n[ a ] = o;
-    for( int k = 0; k < o; k++ ) { st.t[ a ][ k ] = ot[ k ]; st.id[ a ][ k ] = oi[ k ]; }
-}
-
-template <typename R> ACN_NOINLINE R csg_fast_hit( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
-{
-    IvStack<R> st;
-    st.t_valid = Num<R>::inf();
-    int sp = 0;
-    const int start = sv.prog_ref[ 2 * root ], len = sv.prog_ref[ 2 * root + 1 ];
-    for( int pc = start; pc < start + len; pc++ )
-    {
-        const int ins = sv.prog[ pc ];
-        const int op = ins & 15, n = ins >> 4;
-        if( op == CSG_LEAF )
-        {
-            R t[ 2 ]; int s0;
-            const int c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, t );
-            st.s0[ sp ] = s0; st.n[ sp ] = c;
-            for( int k = 0; k < c; k++ ) { st.t[ sp ][ k ] = t[ k ]; st.id[ sp ][ k ] = n; }
-            sp++;
-        }
-        else if( op == CSG_NEG ) st.s0[ sp - 1 ] ^= 1;
-        else if( op == CSG_AND || op == CSG_OR ) { iv_merge( st, sp - 2, sp - 1, op == CSG_AND ); sp--; }
-        else if( op == CSG_ENV )
-        {
-            const int skip = sv.prog[ ++pc ];
-            if( !envelope_hits( sv.env[ n ], ray ) ) { st.s0[ sp ] = 0; st.n[ sp ] = 0; sp++; pc += skip; }
-        }
-        else    // CSG_CLIP: inside-set limited to the own envelope, with virtual crossings
-        {
-            const R4<R> e = sv.env[ n ];
-            R t[ 2 ]; int s0;
-            const int c = sphere_events( xyz( e ), e.w, ray, &s0, t );
-            st.s0[ sp ] = s0; st.n[ sp ] = c;
-            for( int k = 0; k < c; k++ ) { st.t[ sp ][ k ] = t[ k ]; st.id[ sp ][ k ] = -1; }
-            iv_merge( st, sp - 1, sp, true );
-        }
-    }
-    // first real crossing
-    for( int k = 0; k < st.n[ 0 ]; k++ )
-    {
-        const int leaf = st.id[ 0 ][ k ];
-        if( leaf < 0 ) continue;
-        const R t = st.t[ 0 ][ k ];
-        if( t > st.t_valid ) break;
-        const R a = t - sv.eps;
-        if( nor )
-        {
-            V3<R> nn = leaf_normal( sv, node_kind( sv.link[ leaf ] ), leaf, ray, t );
-            // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
-            for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
-            {
-                const I4 lk = sv.link[ m ];
-                if( node_kind( lk ) == K_NEG ) nn = -nn;
-                if( node_flags( lk ) & F_ROUGH ) roughen( sv, m, ray, a, &nn, ctx );
-            }
-            if( node_kind( sv.link[ root ] ) == K_NEG ) nn = -nn;
-            *nor = nn;
-        }
-        return a;
-    }
-    if( st.t_valid < Num<R>::inf() ) return R( -2 ) * Num<R>::mag();     // overflow: the caller falls back to the reference march
-    return Num<R>::inf();
-}
-
 // fp_ray_hit dispatch without the own-envelope test and without roughness
 template <typename R> ACN_HD R shape_hit( const SceneView<R>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     const int kind = node_kind( lk );
     if( kind <= K_DIST_TORUS ) return prim_hit( sv, kind, n, ray, nor );
-    if( sv.prog_ref && sv.prog_ref[ 2 * n + 1 ] > 0 )
-    {
-        R a = csg_fast_hit( sv, n, ray, nor, ctx );
-        if( a > -Num<R>::mag() ) return a;
-    }
     if( kind == K_PAIR_INSIDE )  return pair_hit( sv, lk.y, lk.z, -1, ray, nor, ctx );
     if( kind == K_PAIR_OUTSIDE ) return pair_hit( sv, lk.y, lk.z, +1, ray, nor, ctx );
     if( kind == K_NEG )                                                                  // objects.c:1329-1339
@@ -599,107 +416,6 @@ template <typename R> ACN_HDN int obj_side( const SceneView<R>& sv, int n, V3<R>
         const V3<R> inv = v3<R>( sv.geo[ n * GEO_STRIDE ].w, sv.geo[ n * GEO_STRIDE + 1 ].w, sv.geo[ n * GEO_STRIDE + 2 ].w );
         return obj_side( sv, lk.y, mul( mlv( rax, x - pos ), inv ) );
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// compound_s_ray_hit (compound.c:215-244): closest hit over a tree of compounds.  The recursion of
-// the reference becomes an explicit stack of child ranges; a single running minimum with strict
-// '<' selects the same element as the nested minima do (first in depth-first order wins ties).
-//   t_any: a hit with a <= t_any ends the search at once — exact for the shadow test, which only
-//          consumes (min > a) (scene.c:569); pass -inf for a full closest-hit search.
-// ---------------------------------------------------------------------------------------------
-template <typename R> ACN_HD R compound_ray_hit( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, int* hit_obj, HitCtx ctx, R t_any )
-{
-    const R inf = Num<R>::inf();
-    const I4 rl = sv.link[ root ];
-    if( ( node_flags( rl ) & F_ENV ) && !envelope_hits( sv.env[ root ], ray ) ) return inf;
-    int sb[ COMPOUND_STACK ], se[ COMPOUND_STACK ];
-    int sp = 0;
-    int beg = rl.y, end = rl.y + rl.z;
-    R min_a = inf;
-    V3<R> n;
-    for( ;; )
-    {
-        while( beg < end )
-        {
-            const int c = sv.children[ beg++ ];
-            const I4 lk = sv.link[ c ];
-            if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ c ], ray ) ) continue;
-            if( node_kind( lk ) == K_COMPOUND )
-            {
-                if( sp < COMPOUND_STACK ) { sb[ sp ] = beg; se[ sp ] = end; sp++; beg = lk.y; end = lk.y + lk.z; }
-                continue;
-            }
-            R a = obj_hit_noenv( sv, lk, c, ray, nor ? &n : nullptr, ctx );
-            if( a < min_a )
-            {
-                min_a = a;
-                if( nor ) *nor = n;
-                if( hit_obj ) *hit_obj = c;
-                if( a <= t_any ) return a;
-            }
-        }
-        if( sp == 0 ) break;
-        sp--; beg = sb[ sp ]; end = se[ sp ];
-    }
-    return min_a;
-}
-
-// compound_s_ray_trans_hit (compound.c:246-299): closest hit over the elements of a root compound
-// with the eps-merge of coincident surfaces into one (exit_obj, enter_obj) transition.
-template <typename R> ACN_HD R compound_trans_hit( const SceneView<R>& sv, int root, const Ray<R>& ray, Trans<R>* trans, HitCtx ctx )
-{
-    const R inf = Num<R>::inf();
-    const I4 rl = sv.link[ root ];
-    if( ( node_flags( rl ) & F_ENV ) && !envelope_hits( sv.env[ root ], ray ) ) return inf;
-    R min_a = inf;
-    for( int i = rl.y; i < rl.y + rl.z; i++ )
-    {
-        const int c = sv.children[ i ];
-        const I4 lk = sv.link[ c ];
-        V3<R> nor;
-        int hit_obj = c;
-        R a;
-        if( node_kind( lk ) == K_COMPOUND )
-        {
-            hit_obj = -1;
-            a = compound_ray_hit( sv, c, ray, &nor, &hit_obj, ctx, -inf );
-        }
-        else
-        {
-            if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ c ], ray ) ) continue;
-            a = obj_hit_noenv( sv, lk, c, ray, &nor, ctx );
-        }
-        if( a < inf )
-        {
-            if( a < min_a - sv.eps )
-            {
-                min_a = a;
-                if( dot( nor, ray.d ) > R( 0 ) ) { trans->exit_nor = nor;  trans->exit_obj = hit_obj; trans->enter_obj = -1; }
-                else                             { trans->exit_nor = -nor; trans->exit_obj = -1;      trans->enter_obj = hit_obj; }
-            }
-            else if( r_abs( a - min_a ) < sv.eps )
-            {
-                min_a = a < min_a ? a : min_a;
-                if( dot( nor, ray.d ) > R( 0 ) ) trans->exit_obj = hit_obj;
-                else                             trans->enter_obj = hit_obj;
-            }
-        }
-    }
-    return min_a;
-}
-
-// scene_s_trans_hit (scene.c:362-382): lights first, then matter, strictly smaller wins
-template <typename R> ACN_HD R scene_trans_hit( const SceneView<R>& sv, const Ray<R>& ray, Trans<R>* trans, HitCtx ctx )
-{
-    R min_a = Num<R>::inf();
-    Trans<R> tl;
-    tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( 0, 0, 0 );
-    R a = compound_trans_hit( sv, sv.light_root, ray, &tl, ctx );
-    if( a < min_a ) { min_a = a; *trans = tl; }
-    a = compound_trans_hit( sv, sv.matter_root, ray, &tl, ctx );
-    if( a < min_a ) { min_a = a; *trans = tl; }
-    return min_a;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@
 
 #if defined(__CUDACC__)
 #define ACN_HD  __host__ __device__ __forceinline__
-#define ACN_HDN __host__ __device__
+#define ACN_HDN __host__ __device__ __noinline__
 #define ACN_NOINLINE __host__ __device__ __noinline__
 #else
 #define ACN_HD  inline

@@ -27,8 +27,11 @@
 #include <string.h>
 #include <vector>
 #include <string>
+#include <algorithm>
+#include <functional>
 
 #include "acn_geom.h"
+#include "acn_isect.cuh"
 #include "../../include/actinon_b200.h"
 
 namespace acn {
@@ -405,42 +408,40 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
 //   cls != RC_PATH: scene_s_trans_hit (lights + matter)
 //   cls == RC_PATH: matter only; "leaves" = nothing closer than max_path_length        (scene.c:606-616)
 //   probe: the hit's shading would return 0 (depth 0 or I < Imin) — only "anything hit?" matters
-template <typename R> __device__ bool trace_ray( const Wave<R>& w, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
-                                                 bool probe, int sample, u64 key )
+template <typename R> __device__ __forceinline__ bool trace_ray( const Wave<R>& w, const CsgMem<R>& cm, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
+                                                                bool probe, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
     const R inf = Num<R>::inf();
     HitCtx ctx; ctx.key = key;
     const SceneView<R> sv = ray_view( prm, ray.p );
-    if( probe && cls != RC_PATH )
-    {
-        R a = compound_ray_hit<R>( sv, sv.light_root, ray, nullptr, nullptr, ctx, inf );
-        if( !( a < inf ) ) a = compound_ray_hit<R>( sv, sv.matter_root, ray, nullptr, nullptr, ctx, inf );
-        return !( a < inf );
-    }
-    if( probe )     // path child that cannot contribute on a hit: is anything closer than max_path_length?
-    {
-        R a = compound_ray_hit<R>( sv, sv.matter_root, ray, nullptr, nullptr, ctx, prm.max_path_length );
-        return !( a < prm.max_path_length );
-    }
+    const bool path = cls == RC_PATH;
+    // probe: "anything at all?" (path children: "anything closer than max_path_length?")
+    const int flags = ( path ? Q_MATTER : ( Q_LIGHT | Q_MATTER ) ) | ( probe ? 0 : Q_TRANS );
+    const R t_lim = path ? prm.max_path_length : inf;
     Trans<R> tr;
     tr.exit_obj = tr.enter_obj = -1; tr.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
-    R a;
-    if( cls == RC_PATH )
-    {
-        a = compound_trans_hit( sv, sv.matter_root, ray, &tr, ctx );
-        if( !( a < prm.max_path_length ) ) return true;
-    }
-    else
-    {
-        a = scene_trans_hit( sv, ray, &tr, ctx );
-        if( !( a < inf ) ) return true;
-    }
+    R a = scene_query( sv, ray, flags, t_lim, &tr, ctx, cm );
+    if( !( a < t_lim ) ) return true;
+    if( probe ) return false;
     // the hit distance itself is only good to a few ulp of its magnitude: keep the shading point that far in front
     const R hit_eps = r_max( sv.eps, prm.eps_rel * a );
     a -= hit_eps - sv.eps;
     shade_hit( w, ray, a, hit_eps, tr, depth, I, tp, sample, key );
     return false;
+}
+
+// obj_ray_hit of a light for a direct sample (scene.c:564): spheres in line, any other shape out of line
+template <typename R> __device__ __forceinline__ R light_hit( const SceneView<R>& sv, int node, const Ray<R>& ray, HitCtx ctx )
+{
+    const I4 lk = sv.link[ node ];
+    if( node_kind( lk ) == K_SPHERE )
+    {
+        if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ node ], ray ) ) return Num<R>::inf();
+        const R4<R> g0 = sv.geo[ node * GEO_STRIDE ];
+        return sphere_hit<R>( xyz( g0 ), g0.w, ray, sv.eps, nullptr );
+    }
+    return obj_ray_hit<R>( sv, node, ray, nullptr, ctx );
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -515,6 +516,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
     const unsigned long long first = w.sc->prim_first, count = w.sc->prim_count;
     if( count == 0 || w.sc->overflow ) return;
     stage_scene( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     unsigned long long n_rays = 0;
@@ -538,7 +540,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
             ray.d = prm.cam_rx * d.x + prm.cam_ry * d.y + prm.cam_rz * d.z;
             n_rays++;
             const V3<R> one = v3<R>( R( 1 ), R( 1 ), R( 1 ) );
-            if( trace_ray( w, ray, R( 1 ), prm.trace_depth, one, RC_PRIMARY, false, ( int )s, mix64( w.index_base + s, 0x5EEDull ) ) )
+            if( trace_ray( w, cm, ray, R( 1 ), prm.trace_depth, one, RC_PRIMARY, false, ( int )s, mix64( w.index_base + s, 0x5EEDull ) ) )
                 add_sample( w, ( int )s, prm.background );
         }
     }
@@ -553,6 +555,7 @@ k_rays( Wave<R> w, RayBuf<R> in )
     const unsigned long long count = w.sc->ray_take;
     if( count == 0 || w.sc->overflow ) return;
     stage_scene( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const int lane = threadIdx.x & 31;
     unsigned int n_refl = 0, n_chro = 0, n_refr = 0;
     for( ;; )
@@ -569,7 +572,7 @@ k_rays( Wave<R> w, RayBuf<R> in )
             const int depth = m.x & 0xFF, cls = ( m.x >> 8 ) & 0xFF;
             const u64 key = ( u64 )( unsigned )m.z | ( ( u64 )( unsigned )m.w << 32 );
             n_refl += cls == RC_REFLECT; n_chro += cls == RC_CHROMATIC; n_refr += cls == RC_REFRACT;
-            if( trace_ray( w, ray, a.w, depth, xyz( c ), cls, ( m.x & RAYF_PROBE ) != 0, m.y, key ) )
+            if( trace_ray( w, cm, ray, a.w, depth, xyz( c ), cls, ( m.x & RAYF_PROBE ) != 0, m.y, key ) )
                 add_sample( w, m.y, mul( w.prm.background, xyz( c ) ) * a.w );
         }
     }
@@ -606,6 +609,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
     if( total == 0 || w.sc->overflow ) return;
     stage_scene( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const unsigned long long n_blocks = ( total + 31 ) >> 5;
@@ -648,12 +652,12 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
                 {
                     HitCtx ctx; ctx.key = 0;
                     n_shadow++;
-                    R a = obj_ray_hit<R>( sv, lg.node, out, nullptr, ctx );              // scene.c:564
+                    R a = light_hit( sv, lg.node, out, ctx );                                // scene.c:564
                     if( a < Num<R>::inf() )
                     {
                         if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, prj );
                         n_shadow++;
-                        R sh = compound_ray_hit<R>( sv, sv.matter_root, out, nullptr, nullptr, ctx, a );   // scene.c:569
+                        R sh = scene_query<R>( sv, out, Q_MATTER, a, nullptr, ctx, cm );          // scene.c:569
                         if( sh > a )
                         {
                             V3<R> hp = madd( out.p, out.d, a );
@@ -686,6 +690,7 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     if( blk_hi <= blk_lo || w.sc->overflow ) return;
     const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
     stage_scene( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const int L = prm.n_lights;
@@ -726,7 +731,7 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
                     n_path++;
                     const R ci = wgt * pi.w;
                     const bool probe = ( m.y - 10 ) == 0 || ci < prm.min_intensity;
-                    if( trace_ray( w, out, ci, m.y - 10, tpm, RC_PATH, probe, m.x, mix64( in.key[ t ], KEY_PATH0 + i ) ) ) miss = ci;
+                    if( trace_ray( w, cm, out, ci, m.y - 10, tpm, RC_PATH, probe, m.x, mix64( in.key[ t ], KEY_PATH0 + i ) ) ) miss = ci;
                 }
             }
             __syncwarp();
@@ -1003,12 +1008,30 @@ struct CsgBuilder
         return false;
     }
 
-    // lists needed on the evaluation stack (Sethi-Ullman); a clipped node needs one more for its envelope
+    // operands of the maximal chain of one operator below n: children of the same pair kind are opened up
+    // unless they carry an envelope (which clips THEIR set, so they stay a unit).  A&(B&C) = (A&B)&C as point
+    // sets, so the chain may be evaluated left-deep with two lists however long it is.
+    void operands( int n, int kind, bool root, std::vector<int>& out ) const
+    {
+        const acn_flat_node& nd = fs->nodes[ n ];
+        if( nd.kind == kind && ( root || !nd.has_envelope ) ) { operands( nd.child0, kind, false, out ); operands( nd.child1, kind, false, out ); }
+        else out.push_back( n );
+    }
+
+    // lists needed on the evaluation stack; a clipped node needs one more for its envelope
     int need( int n, bool root ) const
     {
         const acn_flat_node& nd = fs->nodes[ n ];
         int v = 1;
-        if( is_pair( nd.kind ) ) { int a = need( nd.child0, false ), b = need( nd.child1, false ); v = a == b ? a + 1 : ( a > b ? a : b ); }
+        if( is_pair( nd.kind ) )
+        {
+            std::vector<int> ops; operands( n, nd.kind, true, ops );
+            std::vector<int> nd_( ops.size() );
+            for( size_t i = 0; i < ops.size(); i++ ) nd_[ i ] = need( ops[ i ], false );
+            std::sort( nd_.begin(), nd_.end(), std::greater<int>() );
+            v = nd_[ 0 ];
+            if( nd_.size() > 1 && nd_[ 1 ] + 1 > v ) v = nd_[ 1 ] + 1;
+        }
         else if( nd.kind == ACN_KIND_NEG ) v = need( nd.child0, false );
         if( nd.has_envelope && !root && v < 2 ) v = 2;
         return v;
@@ -1021,14 +1044,13 @@ struct CsgBuilder
         size_t skip_slot = 0;
         if( clip ) { prog.push_back( CSG_ENV | ( n << 4 ) ); skip_slot = prog.size(); prog.push_back( 0 ); }
         if( is_leaf( nd.kind ) ) prog.push_back( CSG_LEAF | ( n << 4 ) );
-        else if( nd.kind == ACN_KIND_NEG ) { parent[ nd.child0 ] = n; emit( nd.child0, false ); prog.push_back( CSG_NEG | ( n << 4 ) ); }
+        else if( nd.kind == ACN_KIND_NEG ) { emit( nd.child0, false ); prog.push_back( CSG_NEG | ( n << 4 ) ); }
         else
         {
-            parent[ nd.child0 ] = n; parent[ nd.child1 ] = n;
-            int a = nd.child0, b = nd.child1;
-            if( need( b, false ) > need( a, false ) ) { int t = a; a = b; b = t; }     // deeper operand first
-            emit( a, false ); emit( b, false );
-            prog.push_back( ( nd.kind == ACN_KIND_PAIR_INSIDE ? CSG_AND : CSG_OR ) | ( n << 4 ) );
+            std::vector<int> ops; operands( n, nd.kind, true, ops );
+            std::stable_sort( ops.begin(), ops.end(), [ & ]( int x, int y ) { return need( x, false ) > need( y, false ); } );   // deepest operand first
+            const int opc = ( nd.kind == ACN_KIND_PAIR_INSIDE ? CSG_AND : CSG_OR ) | ( n << 4 );
+            for( size_t i = 0; i < ops.size(); i++ ) { emit( ops[ i ], false ); if( i > 0 ) prog.push_back( opc ); }
         }
         if( clip ) { prog.push_back( CSG_CLIP | ( n << 4 ) ); prog[ skip_slot ] = ( int )( prog.size() - 1 - skip_slot ); }
     }
@@ -1053,9 +1075,14 @@ struct CsgBuilder
             set_parents( n, 0 );
             if( enable && ( is_pair( nd.kind ) || nd.kind == ACN_KIND_NEG ) && eligible( n, 0 ) && need( n, true ) <= CSG_S && prog_ref[ 2 * n + 1 ] == 0 )
             {
-                prog_ref[ 2 * n ] = ( int )prog.size();
+                const size_t mark = prog.size();
                 emit( n, true );
-                prog_ref[ 2 * n + 1 ] = ( int )prog.size() - prog_ref[ 2 * n ];
+                if( prog.size() - mark < ( size_t )CSG_VIRTUAL )       // crossing ids are one byte: program-relative leaf offsets
+                {
+                    prog_ref[ 2 * n ] = ( int )mark;
+                    prog_ref[ 2 * n + 1 ] = ( int )( prog.size() - mark );
+                }
+                else prog.resize( mark );
             }
         }
     }
@@ -1253,8 +1280,8 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
 
     // shared-memory staging of the node table
     size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + sizeof( I4 ) + 3 * sizeof( int ) ) + ( size_t )( fs->n_children + n_prog ) * sizeof( int );
-    smem_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
-    prm.stage_bytes = smem_bytes;
+    prm.stage_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
+    smem_bytes = prm.stage_bytes + ( int )csg_mem_bytes<R>( ACN_BLOCK );      // staged tables, then the CSG interval lists
     if( smem_bytes > 40 * 1024 )
     {
         ACN_CUDA( cudaFuncSetAttribute( k_primary<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
