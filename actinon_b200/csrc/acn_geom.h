@@ -31,8 +31,8 @@ enum { F_ENV = 1, F_ROUGH = 2 };
 enum { GEO_STRIDE = 5 };
 enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
 enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
-enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5 };   // instr = op | node << 4; CSG_ENV is followed by a skip count
-enum { CSG_K = 8, CSG_S = 4, CSG_SLOTS = CSG_S + 1, CSG_VIRTUAL = 255 };   // events per interval list, lists on the evaluation stack (+1 scratch)
+enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5, CSG_RUN = 6, CSG_MEMBER = 7, CSG_MEMBER_NEG = 8 };   // word = op | arg << 4, see acn_isect.cuh
+enum { CSG_E = 16, CSG_VIRTUAL = 255, CSG_MAX_VARS = 48, CSG_TABLE_VARS = 12 };   // crossings kept per ray, id of envelope crossings, variable limits
 
 template <typename R> struct SceneView
 {
@@ -41,7 +41,7 @@ template <typename R> struct SceneView
     const R4<R>* geo;
     const int*   children;
     const int*   prog;      // postfix CSG programs (interval evaluator), see acn_isect.cuh: csg_eval
-    const int*   prog_ref;  // per node: [2n] start into prog, [2n+1] length (0: no program -> reference march)
+    const I4*    prog_ref;  // per node: program start, length (0: none -> reference march), truth table offset (-1: none), variables
     const int*   parent;    // per node: CSG parent (-1 at the top of an object)
     R   eps;            // shell thickness (f3_eps, vectors.h:33)
     int light_root;

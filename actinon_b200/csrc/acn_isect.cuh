@@ -1,7 +1,7 @@
 // acn_isect.cuh — device-only scene queries of the wavefront tracer.
 //
 //   csg_eval      composite objects (obj_pair_inside_s / obj_pair_outside_s / obj_neg_s over plane, sphere
-//                 and squaroid leaves) by interval lists held in SHARED memory
+//                 and squaroid leaves) by an event sweep over a boolean function
 //   scene_query   ONE traversal routine for every kind of ray: scene_s_trans_hit (scene.c:362-382),
 //                 compound_s_ray_trans_hit / compound_s_ray_hit (compound.c:215-299) and the shadow /
 //                 probe "anything closer than t?" tests, selected by flags, so that each kernel holds a
@@ -14,38 +14,47 @@
 namespace acn {
 
 // ---------------------------------------------------------------------------------------------
-// CSG by interval lists.  The reference finds the first boundary of A&B / A|B by an alternating
+// CSG by event sweep.  The reference finds the first boundary of A&B / A|B by an alternating
 // march over the children (objects.c:1052-1094,1209-1251), re-tracing whole subtrees for every
 // rejected candidate: O(n^2) ray tests for an n-leaf solid and hopelessly divergent on a GPU.
 // The same first boundary comes out of classifying the ray against every leaf ONCE:
-//   * a leaf yields its state at the origin and its (<= 2) crossings for t > 0;
-//   * '!' complements, '&' intersects, '|' unites the in/out state sequences (merge of two short
-//     sorted lists, keeping only the crossings where the combined state flips);
+//   * a leaf is a boolean VARIABLE: its state at the ray origin plus its (<= 2) crossings for t > 0;
+//   * the solid is a boolean FUNCTION of the variables ('!' complement, '&' and, '|' or);
 //   * a node's envelope clips its inside-set (obj_side reports "outside" beyond the own envelope,
-//     objects.c:365-370, also for negations) with VIRTUAL crossings that are never reported as hits
-//     (obj_ray_hit only returns shape crossings), and gates the whole subtree (objects.c:264).
-// A crossing of leaf X survives to the root exactly when every sibling on the way up is in the state
-// the pair demands — the reference's acceptance test.  Programs are postfix; chains of the same
-// operator are re-associated to the left (the solid is the same point set), so the evaluation stack
-// stays at 2-3 lists however many facets an object has.
+//     objects.c:365-370, also for negations): one more variable whose crossings are VIRTUAL — they
+//     change the state but are never reported as hits (obj_ray_hit only returns shape crossings) —
+//     and a ray that misses the envelope skips the whole subtree (objects.c:264);
+//   * the hit is the first crossing, in order of t, at which the function of the toggled variables
+//     flips — the reference's acceptance test ("the boundary point of one child lies on the wanted
+//     side of the other") applied once per crossing instead of once per re-traced subtree.
+// Two reductions keep the variable count small: chains of one operator are opened up (A&(B&C) is the
+// same point set as (A&B)&C), and the CONVEX operands of an '&' chain (half-spaces, negated
+// half-spaces, balls, ellipsoids, elliptic cylinders) are fused into ONE variable, a RUN, whose
+// inside-set along the ray is the single interval [max entry, min exit] (slab clipping) — the
+// 58-facet brilliant of diamond.acn is one variable.  With <= CSG_TABLE_VARS variables the function
+// is a truth table of 2^n bits stored behind the program (64 bytes for the wine glass), so one state
+// evaluation is one shared-memory load; larger functions are interpreted with a bit stack.
 //
-// The lists live in shared memory, element (slot, k) of thread tid at [(slot*CSG_K + k)*nthreads + tid]:
-// conflict-free, and no local-memory frame (the previous register-array version cost 856 B of stack
-// per thread and thrashed L1).  Crossing ids are the program-relative offset of the leaf instruction
-// (one byte; CSG_VIRTUAL marks envelope crossings).
+// Per-thread storage: CSG_E events (t, leaf id, variable) in shared memory, element k of thread tid at
+// [k*nthreads + tid] — conflict-free, no local-memory frame.  If a ray produces more than CSG_E
+// crossings the smallest CSG_E are kept and the sweep is exact up to the first dropped one; a sweep
+// that gets that far without a hit falls back to the reference march.
+//
+// Program words (op | arg << 4):  LEAF node | RUN count, then count MEMBER/MEMBER_NEG node words |
+// NEG | AND | OR | ENV node, then (words to skip | variables skipped << 16) | CLIP node.
 // ---------------------------------------------------------------------------------------------
-template <typename R> struct CsgMem { R* t; unsigned char* id; int stride; };
+template <typename R> struct CsgMem { R* t; unsigned short* iv; int stride; };     // iv = leaf id | variable << 8
 
 template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthreads )
 {
-    return ( size_t )( sizeof( R ) + 1 ) * CSG_SLOTS * CSG_K * nthreads;
+    return ( size_t )( sizeof( R ) + 2 ) * CSG_E * nthreads;
 }
 
 template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned char* base, int nthreads, int tid )
 {
     CsgMem<R> m;
     m.t = reinterpret_cast<R*>( base ) + tid;
-    m.id = base + sizeof( R ) * CSG_SLOTS * CSG_K * nthreads + tid;
+    m.iv = reinterpret_cast<unsigned short*>( base + sizeof( R ) * CSG_E * nthreads ) + tid;
     m.stride = nthreads;
     return m;
 }
@@ -126,100 +135,126 @@ template <typename R> __device__ __forceinline__ V3<R> leaf_normal( const SceneV
     return unit( tmlv( rax, v3<R>( x.x * g0.w, x.y * sv.geo[ n * GEO_STRIDE + 1 ].w, x.z * sv.geo[ n * GEO_STRIDE + 2 ].w ) ) );
 }
 
-#define ACN_CSG_T( ph, k )  cm.t[ ( ( ph ) * CSG_K + ( k ) ) * cm.stride ]
-#define ACN_CSG_ID( ph, k ) cm.id[ ( ( ph ) * CSG_K + ( k ) ) * cm.stride ]
+// state of the solid for a variable assignment: truth table, or the postfix program on a bit stack
+template <typename R> __device__ __forceinline__ int csg_state( const SceneView<R>& sv, const I4& pr, unsigned long long vars )
+{
+    if( pr.z >= 0 ) return ( sv.prog[ pr.z + ( int )( vars >> 5 ) ] >> ( ( unsigned int )vars & 31u ) ) & 1;
+    unsigned int stk = 0;
+    int v = 0;
+    #pragma unroll 1
+    for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
+    {
+        const int ins = sv.prog[ pc ];
+        const int op = ins & 15;
+        if( op == CSG_LEAF )      { stk = ( stk << 1 ) | ( unsigned int )( ( vars >> v ) & 1ull ); v++; }
+        else if( op == CSG_RUN )  { stk = ( stk << 1 ) | ( unsigned int )( ( vars >> v ) & 1ull ); v++; pc += ins >> 4; }
+        else if( op == CSG_CLIP ) { stk &= ~1u | ( unsigned int )( ( vars >> v ) & 1ull ); v++; }
+        else if( op == CSG_NEG )  stk ^= 1u;
+        else if( op == CSG_AND )  { const unsigned int t = stk & 1u; stk >>= 1; stk &= t | ~1u; }
+        else if( op == CSG_OR )   { const unsigned int t = stk & 1u; stk >>= 1; stk |= t; }
+        else pc++;                                       // CSG_ENV: a skipped subtree is 0 through its CLIP variable
+    }
+    return ( int )( stk & 1u );
+}
 
-// returns the hit parameter, +inf for a miss, or a value below -mag when a list overflowed before the
-// first crossing was found (the caller then falls back to the reference march)
+// inside-set of one leaf for t > 0 as an interval ( lo, hi ): lo < 0 when the origin is inside
+template <typename R> __device__ __forceinline__ void member_interval( int s0, int c, R t0, R t1, R* lo, R* hi )
+{
+    const R inf = Num<R>::inf();
+    if( s0 ) { *lo = R( -1 ); *hi = c >= 1 ? t0 : inf; }
+    else     { *lo = c >= 1 ? t0 : inf; *hi = c == 2 ? t1 : inf; }
+}
+
+// returns the hit parameter, +inf for a miss, or a value below -mag when the sweep ran into dropped
+// crossings before it found the boundary (the caller then falls back to the reference march)
 template <typename R> __device__ __forceinline__ R csg_eval( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
                                                              const CsgMem<R>& cm )
 {
     const R inf = Num<R>::inf();
-    // registers: list headers (count 4 bits | origin state 1 bit, 6 bits per physical slot), the
-    // logical -> physical slot permutation (4 bits each; logical CSG_S is the scratch slot)
-    unsigned int hdr = 0, perm = 0x43210u;
-    int sp = 0;
+    const I4 pr = sv.prog_ref[ root ];          // start, length, truth table offset (-1: interpret), variables
+    unsigned long long vars = 0;
+    int nv = 0, ne = 0;
     R t_valid = inf;
-    const int start = sv.prog_ref[ 2 * root ], len = sv.prog_ref[ 2 * root + 1 ];
+    // ---- pass 1: classify the ray against every leaf
     #pragma unroll 1
-    for( int pc = start; pc < start + len; pc++ )
+    for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
     {
         const int ins = sv.prog[ pc ];
         const int op = ins & 15, n = ins >> 4;
-        bool merge = false, op_and = true;
-        if( op == CSG_LEAF || op == CSG_CLIP )
+        R t0 = R( 0 ), t1 = R( 0 ); int s0 = 0, c = 0, id0 = CSG_VIRTUAL, id1 = CSG_VIRTUAL;
+        if( op == CSG_LEAF ) { c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; }
+        else if( op == CSG_CLIP ) { const R4<R> e = sv.env[ n ]; c = sphere_events( xyz( e ), e.w, ray, &s0, &t0, &t1 ); }
+        else if( op == CSG_RUN )
         {
-            R t0 = R( 0 ), t1 = R( 0 ); int s0, c;
-            int id = CSG_VIRTUAL;
-            if( op == CSG_LEAF ) { c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id = pc - start; }
-            else { const R4<R> e = sv.env[ n ]; c = sphere_events( xyz( e ), e.w, ray, &s0, &t0, &t1 ); merge = true; }
-            const unsigned int ph = ( perm >> ( 4 * sp ) ) & 15u;
-            if( c > 0 ) { ACN_CSG_T( ph, 0 ) = t0; ACN_CSG_ID( ph, 0 ) = ( unsigned char )id; }
-            if( c > 1 ) { ACN_CSG_T( ph, 1 ) = t1; ACN_CSG_ID( ph, 1 ) = ( unsigned char )id; }
-            hdr = ( hdr & ~( 63u << ( 6 * ph ) ) ) | ( ( unsigned int )( c | ( s0 << 4 ) ) << ( 6 * ph ) );
-            sp++;
-        }
-        else if( op == CSG_NEG )
-        {
-            const unsigned int ph = ( perm >> ( 4 * ( sp - 1 ) ) ) & 15u;
-            hdr ^= 16u << ( 6 * ph );
-        }
-        else if( op == CSG_ENV )
-        {
-            const int skip = sv.prog[ ++pc ];
-            if( !envelope_hits( sv.env[ n ], ray ) )
+            R lo = R( -1 ), hi = inf;
+            #pragma unroll 1
+            for( int m = 1; m <= n; m++ )
             {
-                const unsigned int ph = ( perm >> ( 4 * sp ) ) & 15u;
-                hdr &= ~( 63u << ( 6 * ph ) );          // empty list, outside at the origin
-                sp++; pc += skip;
+                const int w = sv.prog[ pc + m ];
+                const int node = w >> 4;
+                R a0 = R( 0 ), a1 = R( 0 ); int ms0;
+                const int mc = leaf_events( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
+                if( ( w & 15 ) == CSG_MEMBER_NEG ) ms0 ^= 1;
+                R mlo, mhi;
+                member_interval( ms0, mc, a0, a1, &mlo, &mhi );
+                if( mlo > lo ) { lo = mlo; id0 = pc + m - pr.x; }
+                if( mhi < hi ) { hi = mhi; id1 = pc + m - pr.x; }
+            }
+            pc += n;
+            if( lo < R( 0 ) )   { s0 = 1; if( hi < inf ) { c = 1; t0 = hi; id0 = id1; } }
+            else if( lo < hi )  { s0 = 0; c = 1; t0 = lo; if( hi < inf ) { c = 2; t1 = hi; } }
+        }
+        else
+        {
+            if( op == CSG_ENV )
+            {
+                const int w2 = sv.prog[ ++pc ];
+                if( !envelope_hits( sv.env[ n ], ray ) ) { pc += w2 & 0xFFFF; nv += w2 >> 16; }
+            }
+            continue;
+        }
+        vars |= ( unsigned long long )s0 << nv;
+        #pragma unroll 1
+        for( int k = 0; k < c; k++ )
+        {
+            const R t = k ? t1 : t0;
+            const unsigned short iv = ( unsigned short )( ( k ? id1 : id0 ) | ( nv << 8 ) );
+            if( ne < CSG_E ) { cm.t[ ne * cm.stride ] = t; cm.iv[ ne * cm.stride ] = iv; ne++; }
+            else
+            {   // keep the CSG_E smallest crossings; the sweep is exact below the smallest dropped one
+                int kmax = 0; R tmax = cm.t[ 0 ];
+                for( int q = 1; q < CSG_E; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq > tmax ) { tmax = tq; kmax = q; } }
+                if( t < tmax ) { cm.t[ kmax * cm.stride ] = t; cm.iv[ kmax * cm.stride ] = iv; t_valid = r_min( t_valid, tmax ); }
+                else t_valid = r_min( t_valid, t );
             }
         }
-        else { merge = true; op_and = op == CSG_AND; }
-
-        if( merge )     // combine the two topmost lists into the scratch slot, which becomes the new top
-        {
-            const unsigned int pa = ( perm >> ( 4 * ( sp - 2 ) ) ) & 15u, pb = ( perm >> ( 4 * ( sp - 1 ) ) ) & 15u, po = ( perm >> ( 4 * CSG_S ) ) & 15u;
-            const int na = ( hdr >> ( 6 * pa ) ) & 15, nb = ( hdr >> ( 6 * pb ) ) & 15;
-            int sa = ( hdr >> ( 6 * pa + 4 ) ) & 1, sb = ( hdr >> ( 6 * pb + 4 ) ) & 1;
-            int s = op_and ? ( sa & sb ) : ( sa | sb );
-            const int s_init = s;
-            int i = 0, j = 0, o = 0;
-            R ta = na > 0 ? ACN_CSG_T( pa, 0 ) : inf, tb = nb > 0 ? ACN_CSG_T( pb, 0 ) : inf;
-            R t_last = R( 0 );
-            while( i < na || j < nb )
-            {
-                const bool take_a = j >= nb || ( i < na && ta <= tb );
-                R t; unsigned char id;
-                if( take_a ) { t = ta; id = ACN_CSG_ID( pa, i ); i++; sa ^= 1; ta = i < na ? ACN_CSG_T( pa, i ) : inf; }
-                else         { t = tb; id = ACN_CSG_ID( pb, j ); j++; sb ^= 1; tb = j < nb ? ACN_CSG_T( pb, j ) : inf; }
-                const int s2 = op_and ? ( sa & sb ) : ( sa | sb );
-                if( s2 != s )
-                {
-                    if( o < CSG_K ) { ACN_CSG_T( po, o ) = t; ACN_CSG_ID( po, o ) = id; t_last = t; }
-                    o++; s = s2;
-                }
-            }
-            if( o > CSG_K ) { o = CSG_K; t_valid = r_min( t_valid, t_last ); }   // exact up to the last kept crossing
-            hdr = ( hdr & ~( 63u << ( 6 * po ) ) ) | ( ( unsigned int )( o | ( s_init << 4 ) ) << ( 6 * po ) );
-            // logical sp-2 <- scratch; scratch <- old physical slot of A
-            perm = ( perm & ~( ( 15u << ( 4 * ( sp - 2 ) ) ) | ( 15u << ( 4 * CSG_S ) ) ) ) | ( po << ( 4 * ( sp - 2 ) ) ) | ( pa << ( 4 * CSG_S ) );
-            sp--;
-        }
+        nv++;
     }
-    // first real crossing of the root list
-    const unsigned int p0 = perm & 15u;
-    const int n0 = ( hdr >> ( 6 * p0 ) ) & 15;
-    for( int k = 0; k < n0; k++ )
+    // ---- sweep: crossings in order of t until the solid's state flips at a real one
+    int s = 0, id = CSG_VIRTUAL;
+    R tcur = R( 0 );
+    bool first = true, hit = false;
+    for( ;; )
     {
-        const int id = ACN_CSG_ID( p0, k );
-        if( id == CSG_VIRTUAL ) continue;
-        const R t = ACN_CSG_T( p0, k );
-        if( t > t_valid ) break;
-        const R a = t - sv.eps;
+        const int s2 = csg_state( sv, pr, vars );
+        if( !first && s2 != s && id != CSG_VIRTUAL ) { hit = true; break; }
+        s = s2; first = false;
+        int kmin = -1; R tmin = inf;
+        for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } }
+        if( kmin < 0 ) break;
+        if( tmin > t_valid ) return R( -2 ) * Num<R>::mag();
+        const unsigned int iv = cm.iv[ kmin * cm.stride ];
+        cm.t[ kmin * cm.stride ] = inf;
+        vars ^= 1ull << ( iv >> 8 );
+        tcur = tmin; id = ( int )( iv & 255u );
+    }
+    if( hit )
+    {
+        const R a = tcur - sv.eps;
         if( nor )
         {
-            const int leaf = sv.prog[ start + id ] >> 4;
-            V3<R> nn = leaf_normal( sv, node_kind( sv.link[ leaf ] ), leaf, ray, t );
+            const int leaf = sv.prog[ pr.x + id ] >> 4;
+            V3<R> nn = leaf_normal( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
             // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
             for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
             {
@@ -254,7 +289,7 @@ template <typename R> __device__ __forceinline__ R elem_hit( const SceneView<R>&
     else
     {
         a = R( -2 ) * Num<R>::mag();
-        if( kind >= K_PAIR_INSIDE && sv.prog_ref[ 2 * c + 1 ] > 0 ) a = csg_eval( sv, c, ray, nor, ctx, cm );
+        if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval( sv, c, ray, nor, ctx, cm );
         if( !( a > -Num<R>::mag() ) ) a = march_hit( sv, c, ray, nor, ctx );
     }
     if( nor && ( node_flags( lk ) & F_ROUGH ) && a < Num<R>::inf() ) roughen( sv, c, ray, a, nor, ctx );

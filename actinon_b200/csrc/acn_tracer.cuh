@@ -247,14 +247,14 @@ template <typename R> __device__ __forceinline__ void stage_scene( DParams<R>& p
     R4<R>* s_env  = reinterpret_cast<R4<R>*>( smem );
     R4<R>* s_geo  = s_env + n;
     I4*    s_link = reinterpret_cast<I4*>( s_geo + n * GEO_STRIDE );
-    int*   s_chl  = reinterpret_cast<int*>( s_link + n );
-    int*   s_pref = s_chl + prm.n_children;
-    int*   s_par  = s_pref + 2 * n;
+    I4*    s_pref = s_link + n;
+    int*   s_chl  = reinterpret_cast<int*>( s_pref + n );
+    int*   s_par  = s_chl + prm.n_children;
     int*   s_prog = s_par + n;
     for( int i = threadIdx.x; i < n; i += blockDim.x )
     {
         s_env[ i ] = prm.sv.env[ i ]; s_link[ i ] = prm.sv.link[ i ];
-        s_pref[ 2 * i ] = prm.sv.prog_ref[ 2 * i ]; s_pref[ 2 * i + 1 ] = prm.sv.prog_ref[ 2 * i + 1 ]; s_par[ i ] = prm.sv.parent[ i ];
+        s_pref[ i ] = prm.sv.prog_ref[ i ]; s_par[ i ] = prm.sv.parent[ i ];
     }
     for( int i = threadIdx.x; i < n * GEO_STRIDE; i += blockDim.x ) s_geo[ i ] = prm.sv.geo[ i ];
     for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_chl[ i ] = prm.sv.children[ i ];
@@ -910,7 +910,7 @@ template <typename R> struct Tracer : TracerBase
     DParams<R> prm;
     // device copies of the scene tables
     R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr;
-    int* d_prog = nullptr; int* d_prog_ref = nullptr; int* d_parent = nullptr; int n_prog = 0;
+    int* d_prog = nullptr; I4* d_prog_ref = nullptr; int* d_parent = nullptr; int n_prog = 0;
     DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
     // queues
@@ -993,7 +993,8 @@ static int compound_depth( const acn_flat_scene* fs, int n, int guard )
 struct CsgBuilder
 {
     const acn_flat_scene* fs;
-    std::vector<int> prog, prog_ref, parent;
+    std::vector<int> prog, parent;
+    std::vector<I4>  prog_ref;
 
     static bool is_leaf( int k ) { return k == ACN_KIND_PLANE || k == ACN_KIND_SPHERE || k == ACN_KIND_SQUAROID; }
     static bool is_pair( int k ) { return k == ACN_KIND_PAIR_INSIDE || k == ACN_KIND_PAIR_OUTSIDE; }
@@ -1009,8 +1010,7 @@ struct CsgBuilder
     }
 
     // operands of the maximal chain of one operator below n: children of the same pair kind are opened up
-    // unless they carry an envelope (which clips THEIR set, so they stay a unit).  A&(B&C) = (A&B)&C as point
-    // sets, so the chain may be evaluated left-deep with two lists however long it is.
+    // unless they carry an envelope (which clips THEIR set, so they stay a unit).  A&(B&C) = (A&B)&C as point sets.
     void operands( int n, int kind, bool root, std::vector<int>& out ) const
     {
         const acn_flat_node& nd = fs->nodes[ n ];
@@ -1018,41 +1018,93 @@ struct CsgBuilder
         else out.push_back( n );
     }
 
-    // lists needed on the evaluation stack; a clipped node needs one more for its envelope
-    int need( int n, bool root ) const
+    // convex along every ray, so that its inside-set is one interval: half-space, ball, and the squaroids
+    // a x^2 + b y^2 + c z^2 + r <= 0 with a,b,c >= 0 > r (ellipsoid, elliptic cylinder, slab)
+    bool convex_leaf( int n ) const
     {
         const acn_flat_node& nd = fs->nodes[ n ];
-        int v = 1;
-        if( is_pair( nd.kind ) )
-        {
-            std::vector<int> ops; operands( n, nd.kind, true, ops );
-            std::vector<int> nd_( ops.size() );
-            for( size_t i = 0; i < ops.size(); i++ ) nd_[ i ] = need( ops[ i ], false );
-            std::sort( nd_.begin(), nd_.end(), std::greater<int>() );
-            v = nd_[ 0 ];
-            if( nd_.size() > 1 && nd_[ 1 ] + 1 > v ) v = nd_[ 1 ] + 1;
-        }
-        else if( nd.kind == ACN_KIND_NEG ) v = need( nd.child0, false );
-        if( nd.has_envelope && !root && v < 2 ) v = 2;
-        return v;
+        if( nd.has_envelope ) return false;
+        if( nd.kind == ACN_KIND_PLANE || nd.kind == ACN_KIND_SPHERE ) return true;
+        if( nd.kind == ACN_KIND_SQUAROID ) return nd.tail[ 0 ] >= 0 && nd.tail[ 1 ] >= 0 && nd.tail[ 2 ] >= 0 && nd.tail[ 3 ] < 0;
+        return false;
     }
+    // member word of a RUN for operand n, or -1: a convex leaf, or the negation of a plane (the other half-space)
+    int run_member( int n ) const
+    {
+        const acn_flat_node& nd = fs->nodes[ n ];
+        if( convex_leaf( n ) ) return CSG_MEMBER | ( n << 4 );
+        if( nd.kind == ACN_KIND_NEG && !nd.has_envelope )
+        {
+            const acn_flat_node& c = fs->nodes[ nd.child0 ];
+            if( c.kind == ACN_KIND_PLANE && !c.has_envelope ) return CSG_MEMBER_NEG | ( nd.child0 << 4 );
+        }
+        return -1;
+    }
+
+    int n_vars = 0;
 
     void emit( int n, bool root )
     {
         const acn_flat_node& nd = fs->nodes[ n ];
         const bool clip = nd.has_envelope && !root;
         size_t skip_slot = 0;
+        const int vars_before = n_vars;
         if( clip ) { prog.push_back( CSG_ENV | ( n << 4 ) ); skip_slot = prog.size(); prog.push_back( 0 ); }
-        if( is_leaf( nd.kind ) ) prog.push_back( CSG_LEAF | ( n << 4 ) );
+        if( is_leaf( nd.kind ) ) { prog.push_back( CSG_LEAF | ( n << 4 ) ); n_vars++; }
         else if( nd.kind == ACN_KIND_NEG ) { emit( nd.child0, false ); prog.push_back( CSG_NEG | ( n << 4 ) ); }
         else
         {
             std::vector<int> ops; operands( n, nd.kind, true, ops );
-            std::stable_sort( ops.begin(), ops.end(), [ & ]( int x, int y ) { return need( x, false ) > need( y, false ); } );   // deepest operand first
             const int opc = ( nd.kind == ACN_KIND_PAIR_INSIDE ? CSG_AND : CSG_OR ) | ( n << 4 );
-            for( size_t i = 0; i < ops.size(); i++ ) { emit( ops[ i ], false ); if( i > 0 ) prog.push_back( opc ); }
+            std::vector<int> members, rest;
+            if( nd.kind == ACN_KIND_PAIR_INSIDE )
+            {
+                for( int o : ops ) { if( run_member( o ) >= 0 ) members.push_back( o ); else rest.push_back( o ); }
+                if( members.size() < 2 ) { rest = ops; members.clear(); }
+            }
+            else rest = ops;
+            int emitted = 0;
+            if( !members.empty() )
+            {
+                prog.push_back( CSG_RUN | ( ( int )members.size() << 4 ) );
+                for( int o : members ) prog.push_back( run_member( o ) );
+                n_vars++; emitted++;
+            }
+            for( int o : rest ) { emit( o, false ); if( emitted++ > 0 ) prog.push_back( opc ); }
         }
-        if( clip ) { prog.push_back( CSG_CLIP | ( n << 4 ) ); prog[ skip_slot ] = ( int )( prog.size() - 1 - skip_slot ); }
+        if( clip )
+        {
+            prog.push_back( CSG_CLIP | ( n << 4 ) ); n_vars++;
+            prog[ skip_slot ] = ( int )( prog.size() - 1 - skip_slot ) | ( ( n_vars - vars_before ) << 16 );
+        }
+    }
+
+    // the boolean function of a program for one variable assignment (host mirror of csg_state)
+    int eval( size_t start, size_t len, unsigned long long vars ) const
+    {
+        unsigned long long stk = 0;
+        int v = 0;
+        for( size_t pc = start; pc < start + len; pc++ )
+        {
+            const int ins = prog[ pc ], op = ins & 15;
+            if( op == CSG_LEAF )      { stk = ( stk << 1 ) | ( ( vars >> v ) & 1ull ); v++; }
+            else if( op == CSG_RUN )  { stk = ( stk << 1 ) | ( ( vars >> v ) & 1ull ); v++; pc += ( size_t )( ins >> 4 ); }
+            else if( op == CSG_CLIP ) { stk &= ~1ull | ( ( vars >> v ) & 1ull ); v++; }
+            else if( op == CSG_NEG )  stk ^= 1ull;
+            else if( op == CSG_AND )  { const unsigned long long t = stk & 1ull; stk >>= 1; stk &= t | ~1ull; }
+            else if( op == CSG_OR )   { const unsigned long long t = stk & 1ull; stk >>= 1; stk |= t; }
+            else pc++;
+        }
+        return ( int )( stk & 1ull );
+    }
+
+    int depth( int n, int guard ) const
+    {
+        if( guard > 64 ) return 64;
+        const acn_flat_node& nd = fs->nodes[ n ];
+        if( is_pair( nd.kind ) ) { int a = depth( nd.child0, guard + 1 ), b = depth( nd.child1, guard + 1 ); return 1 + ( a > b ? a : b ); }
+        if( nd.kind == ACN_KIND_NEG ) return 1 + depth( nd.child0, guard + 1 );
+        return 1;
     }
 
     void set_parents( int n, int guard )
@@ -1073,14 +1125,25 @@ struct CsgBuilder
             const acn_flat_node& nd = fs->nodes[ n ];
             if( nd.kind == ACN_KIND_COMPOUND ) { visit_compound( n, guard + 1, enable ); continue; }
             set_parents( n, 0 );
-            if( enable && ( is_pair( nd.kind ) || nd.kind == ACN_KIND_NEG ) && eligible( n, 0 ) && need( n, true ) <= CSG_S && prog_ref[ 2 * n + 1 ] == 0 )
+            // the bit stack of the interpreter holds 32 levels; a left-deep chain needs 2 however long it is
+            if( enable && ( is_pair( nd.kind ) || nd.kind == ACN_KIND_NEG ) && eligible( n, 0 ) && depth( n, 0 ) < 30 && prog_ref[ n ].y == 0 )
             {
                 const size_t mark = prog.size();
+                n_vars = 0;
                 emit( n, true );
-                if( prog.size() - mark < ( size_t )CSG_VIRTUAL )       // crossing ids are one byte: program-relative leaf offsets
+                const size_t len = prog.size() - mark;
+                if( len < ( size_t )CSG_VIRTUAL && n_vars <= CSG_MAX_VARS )     // crossing ids are one byte: program-relative leaf offsets
                 {
-                    prog_ref[ 2 * n ] = ( int )mark;
-                    prog_ref[ 2 * n + 1 ] = ( int )( prog.size() - mark );
+                    I4 r; r.x = ( int )mark; r.y = ( int )len; r.z = -1; r.w = n_vars;
+                    if( n_vars <= CSG_TABLE_VARS )
+                    {
+                        r.z = ( int )prog.size();
+                        const size_t rows = ( size_t )1 << n_vars;
+                        std::vector<int> tab( ( rows + 31 ) / 32, 0 );
+                        for( size_t a = 0; a < rows; a++ ) if( eval( mark, len, a ) ) tab[ a >> 5 ] |= ( int )( 1u << ( a & 31 ) );
+                        prog.insert( prog.end(), tab.begin(), tab.end() );
+                    }
+                    prog_ref[ n ] = r;
                 }
                 else prog.resize( mark );
             }
@@ -1091,7 +1154,8 @@ struct CsgBuilder
     {
         fs = scene;
         prog.clear();
-        prog_ref.assign( ( size_t )fs->n_nodes * 2, 0 );
+        I4 none; none.x = 0; none.y = 0; none.z = -1; none.w = 0;
+        prog_ref.assign( ( size_t )fs->n_nodes, none );
         parent.assign( fs->n_nodes, -1 );
         visit_compound( fs->light_root, 0, enable );
         visit_compound( fs->matter_root, 0, enable );
@@ -1168,7 +1232,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         if( ( rc = dev_alloc( &d_prog_ref, cb.prog_ref.size() ) ) ) return rc;
         if( ( rc = dev_alloc( &d_parent, cb.parent.size() ) ) ) return rc;
         ACN_CUDA( cudaMemcpy( d_prog, cb.prog.data(), cb.prog.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
-        ACN_CUDA( cudaMemcpy( d_prog_ref, cb.prog_ref.data(), cb.prog_ref.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
+        ACN_CUDA( cudaMemcpy( d_prog_ref, cb.prog_ref.data(), cb.prog_ref.size() * sizeof( I4 ), cudaMemcpyHostToDevice ) );
         ACN_CUDA( cudaMemcpy( d_parent, cb.parent.data(), cb.parent.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
     }
 
@@ -1279,7 +1343,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     prm.skipA = d_skipA; prm.skipC = d_skipC; prm.skip_n = skip_n;
 
     // shared-memory staging of the node table
-    size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + sizeof( I4 ) + 3 * sizeof( int ) ) + ( size_t )( fs->n_children + n_prog ) * sizeof( int );
+    size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )( fs->n_children + n_prog ) * sizeof( int );
     prm.stage_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
     smem_bytes = prm.stage_bytes + ( int )csg_mem_bytes<R>( ACN_BLOCK );      // staged tables, then the CSG interval lists
     if( smem_bytes > 40 * 1024 )
