@@ -136,7 +136,8 @@ EXPORTED_SYMBOLS = [
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # ACN_B200_LIBRARY: development hook for A/B-ing kernel build variants (tools/exp_build.sh); always a CUDA build
+    return os.environ.get("ACN_B200_LIBRARY") or os.path.join(_HERE, _LIB_NAME)
 
 
 def load_library():

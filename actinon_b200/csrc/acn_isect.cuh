@@ -43,6 +43,10 @@ namespace acn {
 // Program words (op | arg << 4):  LEAF node | RUN count, then count MEMBER/MEMBER_NEG node words |
 // NEG | AND | OR | ENV node, then (words to skip | variables skipped << 16) | CLIP node.
 // ---------------------------------------------------------------------------------------------
+#ifndef ACN_CSG_INLINE
+#define ACN_CSG_INLINE __forceinline__
+#endif
+
 template <typename R> struct CsgMem { R* t; unsigned short* iv; int stride; };     // iv = leaf id | variable << 8
 
 template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthreads )
@@ -165,114 +169,123 @@ template <typename R> __device__ __forceinline__ void member_interval( int s0, i
     else     { *lo = c >= 1 ? t0 : inf; *hi = c == 2 ? t1 : inf; }
 }
 
-// returns the hit parameter, +inf for a miss, or a value below -mag when the sweep ran into dropped
-// crossings before it found the boundary (the caller then falls back to the reference march)
-template <typename R> __device__ __forceinline__ R csg_eval( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
+// returns the hit parameter or +inf for a miss.  A ray with more than CSG_E crossings is swept in rounds:
+// each round keeps the CSG_E smallest crossings beyond t_floor; crossings at or before t_floor only
+// toggle their variable (they were swept in an earlier round).
+template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
                                                              const CsgMem<R>& cm )
 {
     const R inf = Num<R>::inf();
     const I4 pr = sv.prog_ref[ root ];          // start, length, truth table offset (-1: interpret), variables
-    unsigned long long vars = 0;
-    int nv = 0, ne = 0;
-    R t_valid = inf;
-    // ---- pass 1: classify the ray against every leaf
-    #pragma unroll 1
-    for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
+    R t_floor = R( 0 );
+    int s = -1;                                 // state of the solid before the next crossing (-1: not yet evaluated)
+    for( int round = 0; round < 16; round++ )
     {
-        const int ins = sv.prog[ pc ];
-        const int op = ins & 15, n = ins >> 4;
-        R t0 = R( 0 ), t1 = R( 0 ); int s0 = 0, c = 0, id0 = CSG_VIRTUAL, id1 = CSG_VIRTUAL;
-        if( op == CSG_LEAF ) { c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; }
-        else if( op == CSG_CLIP ) { const R4<R> e = sv.env[ n ]; c = sphere_events( xyz( e ), e.w, ray, &s0, &t0, &t1 ); }
-        else if( op == CSG_RUN )
-        {
-            R lo = R( -1 ), hi = inf;
-            #pragma unroll 1
-            for( int m = 1; m <= n; m++ )
-            {
-                const int w = sv.prog[ pc + m ];
-                const int node = w >> 4;
-                R a0 = R( 0 ), a1 = R( 0 ); int ms0;
-                const int mc = leaf_events( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
-                if( ( w & 15 ) == CSG_MEMBER_NEG ) ms0 ^= 1;
-                R mlo, mhi;
-                member_interval( ms0, mc, a0, a1, &mlo, &mhi );
-                if( mlo > lo ) { lo = mlo; id0 = pc + m - pr.x; }
-                if( mhi < hi ) { hi = mhi; id1 = pc + m - pr.x; }
-            }
-            pc += n;
-            if( lo < R( 0 ) )   { s0 = 1; if( hi < inf ) { c = 1; t0 = hi; id0 = id1; } }
-            else if( lo < hi )  { s0 = 0; c = 1; t0 = lo; if( hi < inf ) { c = 2; t1 = hi; } }
-        }
-        else
-        {
-            if( op == CSG_ENV )
-            {
-                const int w2 = sv.prog[ ++pc ];
-                if( !envelope_hits( sv.env[ n ], ray ) ) { pc += w2 & 0xFFFF; nv += w2 >> 16; }
-            }
-            continue;
-        }
-        vars |= ( unsigned long long )s0 << nv;
+        unsigned long long vars = 0;
+        int nv = 0, ne = 0;
+        bool dropped = false;
+        // ---- pass 1: classify the ray against every leaf
         #pragma unroll 1
-        for( int k = 0; k < c; k++ )
+        for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
         {
-            const R t = k ? t1 : t0;
-            const unsigned short iv = ( unsigned short )( ( k ? id1 : id0 ) | ( nv << 8 ) );
-            if( ne < CSG_E ) { cm.t[ ne * cm.stride ] = t; cm.iv[ ne * cm.stride ] = iv; ne++; }
-            else
-            {   // keep the CSG_E smallest crossings; the sweep is exact below the smallest dropped one
-                int kmax = 0; R tmax = cm.t[ 0 ];
-                for( int q = 1; q < CSG_E; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq > tmax ) { tmax = tq; kmax = q; } }
-                if( t < tmax ) { cm.t[ kmax * cm.stride ] = t; cm.iv[ kmax * cm.stride ] = iv; t_valid = r_min( t_valid, tmax ); }
-                else t_valid = r_min( t_valid, t );
-            }
-        }
-        nv++;
-    }
-    // ---- sweep: crossings in order of t until the solid's state flips at a real one
-    int s = 0, id = CSG_VIRTUAL;
-    R tcur = R( 0 );
-    bool first = true, hit = false;
-    for( ;; )
-    {
-        const int s2 = csg_state( sv, pr, vars );
-        if( !first && s2 != s && id != CSG_VIRTUAL ) { hit = true; break; }
-        s = s2; first = false;
-        int kmin = -1; R tmin = inf;
-        for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } }
-        if( kmin < 0 ) break;
-        if( tmin > t_valid ) return R( -2 ) * Num<R>::mag();
-        const unsigned int iv = cm.iv[ kmin * cm.stride ];
-        cm.t[ kmin * cm.stride ] = inf;
-        vars ^= 1ull << ( iv >> 8 );
-        tcur = tmin; id = ( int )( iv & 255u );
-    }
-    if( hit )
-    {
-        const R a = tcur - sv.eps;
-        if( nor )
-        {
-            const int leaf = sv.prog[ pr.x + id ] >> 4;
-            V3<R> nn = leaf_normal( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
-            // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
-            for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
+            const int ins = sv.prog[ pc ];
+            const int op = ins & 15, n = ins >> 4;
+            R t0 = R( 0 ), t1 = R( 0 ); int s0 = 0, c = 0, id0 = CSG_VIRTUAL, id1 = CSG_VIRTUAL;
+            if( op == CSG_LEAF ) { c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; }
+            else if( op == CSG_CLIP ) { const R4<R> e = sv.env[ n ]; c = sphere_events( xyz( e ), e.w, ray, &s0, &t0, &t1 ); }
+            else if( op == CSG_RUN )
             {
-                const I4 lk = sv.link[ m ];
-                if( node_kind( lk ) == K_NEG ) nn = -nn;
-                if( node_flags( lk ) & F_ROUGH ) roughen( sv, m, ray, a, &nn, ctx );
+                R lo = R( -1 ), hi = inf;
+                #pragma unroll 1
+                for( int m = 1; m <= n; m++ )
+                {
+                    const int w = sv.prog[ pc + m ];
+                    const int node = w >> 4;
+                    R a0 = R( 0 ), a1 = R( 0 ); int ms0;
+                    const int mc = leaf_events( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
+                    if( ( w & 15 ) == CSG_MEMBER_NEG ) ms0 ^= 1;
+                    R mlo, mhi;
+                    member_interval( ms0, mc, a0, a1, &mlo, &mhi );
+                    if( mlo > lo ) { lo = mlo; id0 = pc + m - pr.x; }
+                    if( mhi < hi ) { hi = mhi; id1 = pc + m - pr.x; }
+                }
+                pc += n;
+                if( lo < R( 0 ) )   { s0 = 1; if( hi < inf ) { c = 1; t0 = hi; id0 = id1; } }
+                else if( lo < hi )  { s0 = 0; c = 1; t0 = lo; if( hi < inf ) { c = 2; t1 = hi; } }
             }
-            if( node_kind( sv.link[ root ] ) == K_NEG ) nn = -nn;
-            *nor = nn;
+            else
+            {
+                if( op == CSG_ENV )
+                {
+                    const int w2 = sv.prog[ ++pc ];
+                    if( !envelope_hits( sv.env[ n ], ray ) ) { pc += w2 & 0xFFFF; nv += w2 >> 16; }
+                }
+                continue;
+            }
+            #pragma unroll 1
+            for( int k = 0; k < c; k++ )
+            {
+                const R t = k ? t1 : t0;
+                if( t <= t_floor ) { s0 ^= 1; continue; }                  // swept in an earlier round
+                const unsigned short iv = ( unsigned short )( ( k ? id1 : id0 ) | ( nv << 8 ) );
+                if( ne < CSG_E ) { cm.t[ ne * cm.stride ] = t; cm.iv[ ne * cm.stride ] = iv; ne++; }
+                else
+                {   // keep the CSG_E smallest
+                    dropped = true;
+                    int kmax = 0; R tmax = cm.t[ 0 ];
+                    for( int q = 1; q < CSG_E; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq > tmax ) { tmax = tq; kmax = q; } }
+                    if( t < tmax ) { cm.t[ kmax * cm.stride ] = t; cm.iv[ kmax * cm.stride ] = iv; }
+                }
+            }
+            vars |= ( unsigned long long )s0 << nv;
+            nv++;
         }
-        return a;
+        // ---- sweep: crossings in order of t until the solid's state flips at a real one
+        int id = CSG_VIRTUAL;
+        R tcur = t_floor;
+        bool hit = false;
+        for( ;; )
+        {
+            const int s2 = csg_state( sv, pr, vars );
+            if( s >= 0 && s2 != s && id != CSG_VIRTUAL ) { hit = true; break; }
+            s = s2;
+            int kmin = -1; R tmin = inf;
+            for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } }
+            if( kmin < 0 ) break;
+            const unsigned int iv = cm.iv[ kmin * cm.stride ];
+            cm.t[ kmin * cm.stride ] = inf;
+            vars ^= 1ull << ( iv >> 8 );
+            tcur = tmin; id = ( int )( iv & 255u );
+        }
+        if( hit )
+        {
+            const R a = tcur - sv.eps;
+            if( nor )
+            {
+                const int leaf = sv.prog[ pr.x + id ] >> 4;
+                V3<R> nn = leaf_normal( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
+                // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
+                for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
+                {
+                    const I4 lk = sv.link[ m ];
+                    if( node_kind( lk ) == K_NEG ) nn = -nn;
+                    if( node_flags( lk ) & F_ROUGH ) roughen( sv, m, ray, a, &nn, ctx );
+                }
+                if( node_kind( sv.link[ root ] ) == K_NEG ) nn = -nn;
+                *nor = nn;
+            }
+            return a;
+        }
+        if( !dropped ) break;
+        t_floor = tcur;                         // every kept crossing was swept: go on beyond the last one
     }
-    if( t_valid < inf ) return R( -2 ) * Num<R>::mag();
     return inf;
 }
 
-// objects the interval evaluator does not cover (distance fields, scale nodes, CSG over those, list
-// overflow): the reference's recursive march, out of line
+// objects the event sweep does not cover (scale nodes, CSG over distance fields): the reference's
+// recursive march, out of line.  Only the MARCH instantiation of the kernels contains it — the mutually
+// recursive obj_ray_hit / pair_hit / obj_side want ~250 registers, which would otherwise set the
+// register count (and the occupancy) of every tracing kernel.
 template <typename R> __device__ __noinline__ R march_hit( const SceneView<R>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     const I4 lk = sv.link[ n ];
@@ -280,18 +293,16 @@ template <typename R> __device__ __noinline__ R march_hit( const SceneView<R>& s
 }
 
 // obj_ray_hit after the envelope test (objects.c:261-284): fp_ray_hit + roughness
-template <typename R> __device__ __forceinline__ R elem_hit( const SceneView<R>& sv, const I4& lk, int c, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
-                                                             const CsgMem<R>& cm )
+template <typename R, bool MARCH> __device__ __forceinline__ R elem_hit( const SceneView<R>& sv, const I4& lk, int c, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
+                                                                         const CsgMem<R>& cm )
 {
     const int kind = node_kind( lk );
     R a;
     if( kind == K_PLANE || kind == K_SPHERE || kind == K_SQUAROID ) a = prim_hit( sv, kind, c, ray, nor );
-    else
-    {
-        a = R( -2 ) * Num<R>::mag();
-        if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval( sv, c, ray, nor, ctx, cm );
-        if( !( a > -Num<R>::mag() ) ) a = march_hit( sv, c, ray, nor, ctx );
-    }
+    else if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval( sv, c, ray, nor, ctx, cm );
+    else if( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) a = dist_hit( sv, kind, c, ray, nor );
+    else if( MARCH ) a = march_hit( sv, c, ray, nor, ctx );
+    else a = Num<R>::inf();                 // unreachable: such scenes run the MARCH instantiation
     if( nor && ( node_flags( lk ) & F_ROUGH ) && a < Num<R>::inf() ) roughen( sv, c, ray, a, nor, ctx );
     return a;
 }
@@ -327,7 +338,7 @@ template <typename R> __device__ __forceinline__ void trans_commit( const SceneV
     }
 }
 
-template <typename R> __device__ __forceinline__ R scene_query( const SceneView<R>& sv, const Ray<R>& ray, const int flags, const R t_any,
+template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( const SceneView<R>& sv, const Ray<R>& ray, const int flags, const R t_any,
                                                                 Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
 {
     const R inf = Num<R>::inf();
@@ -359,7 +370,7 @@ template <typename R> __device__ __forceinline__ R scene_query( const SceneView<
                     continue;
                 }
                 V3<R> n;
-                const R a = elem_hit( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm );
+                const R a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm );
                 if( !want_trans )
                 {
                     if( a < min_a ) { min_a = a; if( a <= t_any ) return a; }

@@ -82,6 +82,8 @@ template <typename R> struct DParams
     R     max_path_length;
     R     eps_rel;                            // per-ray shell thickness = max( sv.eps, eps_rel * |origin|_inf ); 0: constant
     int   stage_bytes;                        // node table bytes staged into shared memory (0: none)
+    int   n_heavy;                            // envelopes of the expensive top-level objects (CSG, distance fields); -1: no split
+    int   heavy[ 8 ];
     const u64* skipA;                         // LCG skip table: state after 2k steps = s*A[k] + C[k]
     const u64* skipC;
     int   skip_n;
@@ -99,6 +101,16 @@ template <typename R> struct RayBuf     // SoA
     R4<R>* d_;      // dir.xyz, -
     R4<R>* tp;      // throughput rgb, -
     I4*    meta;    // depth | class<<8 | flags, sample, key lo, key hi
+};
+
+template <typename R> struct HitBuf     // SoA: hits waiting for scene_s_lum (k_shade)
+{
+    R4<R>* o_a;       // ray origin, hit distance
+    R4<R>* d_i;       // ray direction, intensity
+    R4<R>* n_e;       // trans.exit_nor, hit_eps
+    R4<R>* tp;        // throughput rgb, -
+    I4*    meta;      // depth, sample, exit_obj, enter_obj
+    u64*   key;       // ray-tree key
 };
 
 template <typename R> struct TaskBuf    // SoA
@@ -140,9 +152,10 @@ struct Sched
     unsigned long long fix_slot, fix_cum;   // partially consumed task: cum[ fix_slot ] = fix_cum after k_path
     unsigned long long prim_first, prim_count;
     // work cursors of the persistent kernels (units: chunks)
-    unsigned long long cur_pop, cur_rays, cur_path, cur_index, cur_direct, cur_primary;
+    unsigned long long cur_pop, cur_rays, cur_path, cur_index, cur_direct, cur_primary, cur_shade;
     // per-iteration outputs
     unsigned long long rays_out;        // rays appended
+    unsigned long long hits;            // hits appended to the hit queue by the tracing kernels
     unsigned long long tasks_new;       // diffuse hits appended to the new-task scratch
     unsigned long long dl_packed;       // direct list: entries << 38 | shadow children
     unsigned long long task_stack;      // task stack: height << 38 | outstanding path children
@@ -158,10 +171,12 @@ template <typename R> struct Wave       // everything a kernel needs
     DParams<R>  prm;
     RayBuf<R>   rays_out;     // ray stack
     TaskBuf<R>  tasks_out;    // new-task scratch
+    HitBuf<R>   hits_out;     // hit queue
     Sched*      sc;
     R*          accum;        // per-sample RGB, 3 per sample
     unsigned long long rays_cap;
     unsigned long long tasks_cap;
+    unsigned long long hits_cap;
     u64         index_base;   // global index of sample 0 (index-keyed seeding)
 };
 
@@ -240,9 +255,10 @@ template <typename R> __device__ __forceinline__ void add_sample( const Wave<R>&
 }
 
 // stage the node table into shared memory when it fits (C1/C2/C4: a few KB); big scenes stay in L2
-template <typename R> __device__ __forceinline__ void stage_scene( DParams<R>& prm, unsigned char* smem )
+template <typename R> __device__ __forceinline__ SceneView<R> stage_scene( const DParams<R>& prm, unsigned char* smem )
 {
-    if( prm.stage_bytes <= 0 ) return;
+    SceneView<R> sv = prm.sv;
+    if( prm.stage_bytes <= 0 ) return sv;
     const int n = prm.n_nodes;
     R4<R>* s_env  = reinterpret_cast<R4<R>*>( smem );
     R4<R>* s_geo  = s_env + n;
@@ -260,18 +276,19 @@ template <typename R> __device__ __forceinline__ void stage_scene( DParams<R>& p
     for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_chl[ i ] = prm.sv.children[ i ];
     for( int i = threadIdx.x; i < prm.n_prog; i += blockDim.x ) s_prog[ i ] = prm.sv.prog[ i ];
     __syncthreads();
-    prm.sv.env = s_env; prm.sv.geo = s_geo; prm.sv.link = s_link; prm.sv.children = s_chl;
-    prm.sv.prog_ref = s_pref; prm.sv.parent = s_par; prm.sv.prog = s_prog;
+    sv.env = s_env; sv.geo = s_geo; sv.link = s_link; sv.children = s_chl;
+    sv.prog_ref = s_pref; sv.parent = s_par; sv.prog = s_prog;
+    return sv;
 }
 
 // obj_color (objects.c:411-422) with txm_plain / txm_chess (textures.c:99-102,142-148)
-template <typename R> __device__ __forceinline__ V3<R> obj_color( const DParams<R>& prm, int node, V3<R> pos )
+template <typename R> __device__ __forceinline__ V3<R> obj_color( const DParams<R>& prm, const SceneView<R>& sv0, int node, V3<R> pos )
 {
-    const DMat<R>& m = prm.mats[ prm.sv.link[ node ].w ];
+    const DMat<R>& m = prm.mats[ sv0.link[ node ].w ];
     if( m.tex_kind == ACN_TEX_NONE )  return v3<R>( m.color[ 0 ], m.color[ 1 ], m.color[ 2 ] );
     if( m.tex_kind == ACN_TEX_PLAIN ) return v3<R>( m.tex1[ 0 ], m.tex1[ 1 ], m.tex1[ 2 ] );
     R u, v;
-    obj_projection( prm.sv, node, pos, &u, &v );
+    obj_projection( sv0, node, pos, &u, &v );
     long long x = llrint( ( double )( u * m.tex_scale ) );
     long long y = llrint( ( double )( v * m.tex_scale ) );
     return ( ( x ^ y ) & 1 ) ? v3<R>( m.tex1[ 0 ], m.tex1[ 1 ], m.tex1[ 2 ] ) : v3<R>( m.tex2[ 0 ], m.tex2[ 1 ], m.tex2[ 2 ] );
@@ -280,9 +297,9 @@ template <typename R> __device__ __forceinline__ V3<R> obj_color( const DParams<
 // The reference's shell thickness is an absolute 1e-6 in FP64.  In FP32 a hit distance carries an error
 // of a few ulp of the ray origin's magnitude, so the product path scales the shell with the origin
 // (16 ulp) and never goes below the reference's 1e-6; see DESIGN.md "eps".
-template <typename R> __device__ __forceinline__ SceneView<R> ray_view( const DParams<R>& prm, V3<R> o )
+template <typename R> __device__ __forceinline__ SceneView<R> ray_view( const DParams<R>& prm, const SceneView<R>& sv0, V3<R> o )
 {
-    SceneView<R> sv = prm.sv;
+    SceneView<R> sv = sv0;
     if( prm.eps_rel > R( 0 ) ) sv.eps = r_max( sv.eps, prm.eps_rel * r_max( r_max( r_abs( o.x ), r_abs( o.y ) ), r_abs( o.z ) ) );
     return sv;
 }
@@ -310,19 +327,19 @@ template <typename R> __device__ __forceinline__ void emit_ray( const Wave<R>& w
 // ---------------------------------------------------------------------------------------------
 // scene_s_lum (scene.c:420-667) for one hit: emits child rays and at most one diffuse task.
 // ---------------------------------------------------------------------------------------------
-template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>& ray, R a, R hit_eps, const Trans<R>& tr,
+template <typename R> __device__ void shade_hit( const Wave<R>& w, const SceneView<R>& sv0, const Ray<R>& ray, R a, R hit_eps, const Trans<R>& tr,
                                                  int depth, R I, V3<R> tp, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
     if( depth == 0 || I < prm.min_intensity ) return;                                    // scene.c:428
     const V3<R> pos = madd( ray.p, ray.d, a );
 
-    const DMat<R>* me = tr.enter_obj >= 0 ? &prm.mats[ prm.sv.link[ tr.enter_obj ].w ] : nullptr;
+    const DMat<R>* me = tr.enter_obj >= 0 ? &prm.mats[ sv0.link[ tr.enter_obj ].w ] : nullptr;
     if( me && me->radiance > R( 0 ) )                                                    // scene.c:432-437
     {
-        R d2 = sqr( pos - xyz( prm.sv.geo[ tr.enter_obj * GEO_STRIDE ] ) );
+        R d2 = sqr( pos - xyz( sv0.geo[ tr.enter_obj * GEO_STRIDE ] ) );
         R li = d2 > R( 0 ) ? me->radiance / d2 : Num<R>::mag();
-        add_sample( w, sample, mul( obj_color( prm, tr.enter_obj, pos ), tp ) * ( li * I ) );
+        add_sample( w, sample, mul( obj_color( prm, sv0, tr.enter_obj, pos ), tp ) * ( li * I ) );
         agg_count( &w.sc->stats[ ST_LIGHT ] );
         return;
     }
@@ -336,7 +353,7 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
     }
     if( tr.exit_obj >= 0 )                                                               // scene.c:464-470, 656-664
     {
-        const DMat<R>& mx = prm.mats[ prm.sv.link[ tr.exit_obj ].w ];
+        const DMat<R>& mx = prm.mats[ sv0.link[ tr.exit_obj ].w ];
         nrel /= mx.refr; F = R( 1 ); C = R( 0 ); Dff = R( 0 ); T = true;
         if( a > R( 0 ) )
         {
@@ -355,7 +372,7 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
 
     if( C > R( 0 ) && I >= prm.min_intensity )                                           // scene.c:498-523
     {
-        V3<R> col = obj_color( prm, tr.enter_obj, pos );
+        V3<R> col = obj_color( prm, sv0, tr.enter_obj, pos );
         emit_ray( w, pos, reflect( ray.d, tr.exit_nor ), C * I, depth - 1, mul( tp, col ), RC_CHROMATIC, sample, mix64( key, KEY_CHROMATIC ) );
         I *= ( R( 1 ) - C );
     }
@@ -366,10 +383,10 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
         const V3<R> nrm = -tr.exit_nor;
         const R cos_i = dot( ray.d, tr.exit_nor );
         const V3<R> prj = unit( ray.d - nrm * dot( ray.d, nrm ) );
-        u64 rv0 = prm.sv.seed_mode == SEED_POSITION_HASH
+        u64 rv0 = sv0.seed_mode == SEED_POSITION_HASH
                       ? random_seed( pos, ( u64 )3294479285ull ) + random_seed( nrm, ( u64 )3247146734ull )
                       : mix64( key, KEY_DIFFUSE );
-        V3<R> col = obj_color( prm, tr.enter_obj, pos );
+        V3<R> col = obj_color( prm, sv0, tr.enter_obj, pos );
         unsigned long long nd = ( unsigned long long )( ( double )prm.direct_samples * ( double )Id );   // scene.c:553
         if( nd == 0 ) nd = 1;
         unsigned long long np = 0;
@@ -408,31 +425,70 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const Ray<R>&
 //   cls != RC_PATH: scene_s_trans_hit (lights + matter)
 //   cls == RC_PATH: matter only; "leaves" = nothing closer than max_path_length        (scene.c:606-616)
 //   probe: the hit's shading would return 0 (depth 0 or I < Imin) — only "anything hit?" matters
-template <typename R> __device__ __forceinline__ bool trace_ray( const Wave<R>& w, const CsgMem<R>& cm, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
+template <typename R, bool MARCH> __device__ __forceinline__ bool trace_ray( const Wave<R>& w, const SceneView<R>& sv0, const CsgMem<R>& cm, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
                                                                 bool probe, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
     const R inf = Num<R>::inf();
     HitCtx ctx; ctx.key = key;
-    const SceneView<R> sv = ray_view( prm, ray.p );
+    const SceneView<R> sv = ray_view( prm, sv0, ray.p );
     const bool path = cls == RC_PATH;
     // probe: "anything at all?" (path children: "anything closer than max_path_length?")
     const int flags = ( path ? Q_MATTER : ( Q_LIGHT | Q_MATTER ) ) | ( probe ? 0 : Q_TRANS );
     const R t_lim = path ? prm.max_path_length : inf;
     Trans<R> tr;
     tr.exit_obj = tr.enter_obj = -1; tr.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
-    R a = scene_query( sv, ray, flags, t_lim, &tr, ctx, cm );
+    R a = scene_query<R, MARCH>( sv, ray, flags, t_lim, &tr, ctx, cm );
     if( !( a < t_lim ) ) return true;
     if( probe ) return false;
     // the hit distance itself is only good to a few ulp of its magnitude: keep the shading point that far in front
     const R hit_eps = r_max( sv.eps, prm.eps_rel * a );
     a -= hit_eps - sv.eps;
-    shade_hit( w, ray, a, hit_eps, tr, depth, I, tp, sample, key );
+    // the surface response (scene_s_lum) runs in its own kernel over the compacted hits
+    const unsigned long long slot = agg_inc( &w.sc->hits );
+    if( slot >= w.hits_cap ) { w.sc->overflow = 5; return false; }
+    R4<R> q;
+    q.x = ray.p.x; q.y = ray.p.y; q.z = ray.p.z; q.w = a;                          w.hits_out.o_a[ slot ] = q;
+    q.x = ray.d.x; q.y = ray.d.y; q.z = ray.d.z; q.w = I;                          w.hits_out.d_i[ slot ] = q;
+    q.x = tr.exit_nor.x; q.y = tr.exit_nor.y; q.z = tr.exit_nor.z; q.w = hit_eps;  w.hits_out.n_e[ slot ] = q;
+    q.x = tp.x; q.y = tp.y; q.z = tp.z; q.w = R( 0 );                              w.hits_out.tp[ slot ] = q;
+    I4 m; m.x = depth; m.y = sample; m.z = tr.exit_obj; m.w = tr.enter_obj;        w.hits_out.meta[ slot ] = m;
+    w.hits_out.key[ slot ] = key;
     return false;
 }
 
+// Warp-level ray compaction.  Most rays of a wave touch only planes and spheres; a minority enters the
+// envelope of an expensive object (a CSG solid, a distance field) and then costs 10-50x more.  Traced
+// in the order they come, the expensive rays run a few lanes at a time while the rest of the warp
+// idles.  Each persistent warp therefore DEFERS the rays that pass the envelope of an expensive object
+// into a small ring in shared memory and traces them only when a full group of 32 has collected (or the
+// input is exhausted): cheap groups run without them, expensive groups run dense.
+#define ACN_PEND 64
+template <typename R> __device__ __forceinline__ bool ray_is_heavy( const DParams<R>& prm, const SceneView<R>& sv0, const Ray<R>& ray )
+{
+    bool h = false;
+    for( int k = 0; k < prm.n_heavy; k++ ) h = h || envelope_hits( sv0.env[ prm.heavy[ k ] ], ray );
+    return h;
+}
+
+// appends the items of the lanes with `take` to the warp's ring (order of lanes preserved)
+__device__ __forceinline__ void pend_push( unsigned long long* ring, int head, int& count, bool take, unsigned long long item, int lane )
+{
+    const unsigned int mask = __ballot_sync( ACN_FULL, take );
+    if( take ) ring[ ( head + count + __popc( mask & ( ( 1u << lane ) - 1u ) ) ) & ( ACN_PEND - 1 ) ] = item;
+    count += __popc( mask );
+    __syncwarp();
+}
+
 // obj_ray_hit of a light for a direct sample (scene.c:564): spheres in line, any other shape out of line
-template <typename R> __device__ __forceinline__ R light_hit( const SceneView<R>& sv, int node, const Ray<R>& ray, HitCtx ctx )
+template <typename R, bool MARCH> __device__ __noinline__ R light_hit_cold( const SceneView<R>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
+{
+    const I4 lk = sv.link[ node ];
+    if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ node ], ray ) ) return Num<R>::inf();
+    return elem_hit<R, MARCH>( sv, lk, node, ray, nullptr, ctx, cm );
+}
+
+template <typename R, bool MARCH> __device__ __forceinline__ R light_hit( const SceneView<R>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
 {
     const I4 lk = sv.link[ node ];
     if( node_kind( lk ) == K_SPHERE )
@@ -441,14 +497,26 @@ template <typename R> __device__ __forceinline__ R light_hit( const SceneView<R>
         const R4<R> g0 = sv.geo[ node * GEO_STRIDE ];
         return sphere_hit<R>( xyz( g0 ), g0.w, ray, sv.eps, nullptr );
     }
-    return obj_ray_hit<R>( sv, node, ray, nullptr, ctx );
+    return light_hit_cold<R, MARCH>( sv, node, ray, ctx, cm );
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernels — all persistent: fixed grid, warps fetch chunks of work through a cursor in Sched
 // ---------------------------------------------------------------------------------------------
 #define ACN_BLOCK 128
+#ifndef ACN_CHUNK
 #define ACN_CHUNK 4        // 32-item groups per cursor fetch
+#endif
+// minimum resident blocks per SM the compiler must fit the registers of each tracing kernel into
+#ifndef ACN_MINB_RAYS
+#define ACN_MINB_RAYS 5
+#endif
+#ifndef ACN_MINB_PATH
+#define ACN_MINB_PATH 5
+#endif
+#ifndef ACN_MINB_DIRECT
+#define ACN_MINB_DIRECT 5
+#endif
 
 enum { SCHED_PRIMARY = 0, SCHED_WAVE = 1 };
 
@@ -462,8 +530,8 @@ __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, uns
     unsigned long long nt = s->task_stack >> ACN_TASK_SHIFT, nt_cum = s->task_stack & ACN_TASK_MASK;
     s->stats[ ST_DIFFUSE ] += s->tasks_new;
     if( s->rays_out | s->tasks_new | s->ray_take | ( s->path_blk_hi - s->path_blk_lo ) | s->prim_count ) s->waves++;
-    s->rays_out = 0; s->tasks_new = 0; s->dl_packed = 0;
-    s->cur_pop = s->cur_rays = s->cur_path = s->cur_index = s->cur_direct = s->cur_primary = 0;
+    s->rays_out = 0; s->tasks_new = 0; s->dl_packed = 0; s->hits = 0;
+    s->cur_pop = s->cur_rays = s->cur_path = s->cur_index = s->cur_direct = s->cur_primary = s->cur_shade = 0;
     // ---- plan
     unsigned long long ray_take = 0, blk_lo = 0, blk_hi = 0, fix_slot = ACN_NONE64, fix_cum = 0;
     s->path_nt = nt; s->path_c_hi = nt_cum;
@@ -509,13 +577,13 @@ k_pop( const Sched* __restrict__ s, RayBuf<R> stack, RayBuf<R> cur )
 }
 
 // camera rays (scene.c:976-990) fused with their first trace + shade
-template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK )
 k_primary( Wave<R> w, const double* __restrict__ xy )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     const unsigned long long first = w.sc->prim_first, count = w.sc->prim_count;
     if( count == 0 || w.sc->overflow ) return;
-    stage_scene( w.prm, smem );
+    const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
@@ -540,7 +608,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
             ray.d = prm.cam_rx * d.x + prm.cam_ry * d.y + prm.cam_rz * d.z;
             n_rays++;
             const V3<R> one = v3<R>( R( 1 ), R( 1 ), R( 1 ) );
-            if( trace_ray( w, cm, ray, R( 1 ), prm.trace_depth, one, RC_PRIMARY, false, ( int )s, mix64( w.index_base + s, 0x5EEDull ) ) )
+            if( trace_ray<R, MARCH>( w, sv0, cm, ray, R( 1 ), prm.trace_depth, one, RC_PRIMARY, false, ( int )s, mix64( w.index_base + s, 0x5EEDull ) ) )
                 add_sample( w, ( int )s, prm.background );
         }
     }
@@ -548,37 +616,98 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
 }
 
 // explicit rays popped from the ray stack
-template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_RAYS )
 k_rays( Wave<R> w, RayBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
+    __shared__ unsigned long long ring_all[ ACN_BLOCK / 32 ][ ACN_PEND ];
     const unsigned long long count = w.sc->ray_take;
     if( count == 0 || w.sc->overflow ) return;
-    stage_scene( w.prm, smem );
+    const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const int lane = threadIdx.x & 31;
+    unsigned long long* ring = ring_all[ threadIdx.x >> 5 ];
+    int pend_head = 0, pend_n = 0;
+    bool input_done = false;
+    unsigned long long c_cur = 0, c_end = 0;
+    const bool split = w.prm.n_heavy > 0;
     unsigned int n_refl = 0, n_chro = 0, n_refr = 0;
     for( ;; )
     {
-        const unsigned long long c0 = warp_fetch( &w.sc->cur_rays, 32ull * ACN_CHUNK, lane );
-        if( c0 >= count ) break;
-        for( int g = 0; g < ACN_CHUNK; g++ )
+        unsigned long long i = ACN_NONE64;
+        if( pend_n >= 32 || ( input_done && pend_n > 0 ) )
         {
-            const unsigned long long i = c0 + 32ull * g + lane;
-            if( i >= count ) continue;
+            const int k = pend_n < 32 ? pend_n : 32;
+            if( lane < k ) i = ring[ ( pend_head + lane ) & ( ACN_PEND - 1 ) ];
+            pend_head += k; pend_n -= k;
+            __syncwarp();
+        }
+        else if( !input_done )
+        {
+            if( c_cur >= c_end )
+            {
+                c_cur = warp_fetch( &w.sc->cur_rays, 32ull * ACN_CHUNK, lane );
+                c_end = c_cur + 32ull * ACN_CHUNK;
+                if( c_cur >= count ) { input_done = true; continue; }
+            }
+            i = c_cur + lane; c_cur += 32;
+            if( i >= count ) i = ACN_NONE64;
+            if( split )
+            {
+                bool heavy = false;
+                if( i != ACN_NONE64 )
+                {
+                    Ray<R> ray; ray.p = xyz( in.o_i[ i ] ); ray.d = xyz( in.d_[ i ] );
+                    heavy = ray_is_heavy( w.prm, sv0, ray );
+                }
+                pend_push( ring, pend_head, pend_n, heavy, i, lane );
+                if( heavy ) i = ACN_NONE64;
+            }
+        }
+        else break;
+        if( i != ACN_NONE64 )
+        {
             const R4<R> a = in.o_i[ i ], b = in.d_[ i ], c = in.tp[ i ];
             const I4 m = in.meta[ i ];
             Ray<R> ray; ray.p = xyz( a ); ray.d = xyz( b );
             const int depth = m.x & 0xFF, cls = ( m.x >> 8 ) & 0xFF;
             const u64 key = ( u64 )( unsigned )m.z | ( ( u64 )( unsigned )m.w << 32 );
             n_refl += cls == RC_REFLECT; n_chro += cls == RC_CHROMATIC; n_refr += cls == RC_REFRACT;
-            if( trace_ray( w, cm, ray, a.w, depth, xyz( c ), cls, ( m.x & RAYF_PROBE ) != 0, m.y, key ) )
+            if( trace_ray<R, MARCH>( w, sv0, cm, ray, a.w, depth, xyz( c ), cls, ( m.x & RAYF_PROBE ) != 0, m.y, key ) )
                 add_sample( w, m.y, mul( w.prm.background, xyz( c ) ) * a.w );
         }
+        __syncwarp();
     }
     warp_count( &w.sc->stats[ ST_REFLECT ], n_refl, lane );
     warp_count( &w.sc->stats[ ST_CHROMATIC ], n_chro, lane );
     warp_count( &w.sc->stats[ ST_REFRACT ], n_refr, lane );
+}
+
+// scene_s_lum (scene.c:420-667) over the hits of the iteration: emits child rays and diffuse tasks
+template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+k_shade( Wave<R> w, HitBuf<R> in )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    unsigned long long count = w.sc->hits;
+    if( count > w.hits_cap ) count = w.hits_cap;
+    if( count == 0 || w.sc->overflow ) return;
+    const SceneView<R> sv0 = stage_scene( w.prm, smem );
+    const int lane = threadIdx.x & 31;
+    for( ;; )
+    {
+        const unsigned long long c0 = warp_fetch( &w.sc->cur_shade, 32ull * ACN_CHUNK, lane );
+        if( c0 >= count ) break;
+        for( int g = 0; g < ACN_CHUNK; g++ )
+        {
+            const unsigned long long i = c0 + 32ull * g + lane;
+            if( i >= count ) continue;
+            const R4<R> oa = in.o_a[ i ], di = in.d_i[ i ], ne = in.n_e[ i ], tp = in.tp[ i ];
+            const I4 m = in.meta[ i ];
+            Ray<R> ray; ray.p = xyz( oa ); ray.d = xyz( di );
+            Trans<R> tr; tr.exit_nor = xyz( ne ); tr.exit_obj = m.z; tr.enter_obj = m.w;
+            shade_hit( w, sv0, ray, oa.w, ne.w, tr, m.x, di.w, xyz( tp ), m.y, in.key[ i ] );
+        }
+    }
 }
 
 // Lists of work entries with implicit children.  An entry owns the children [ excl, incl ) of a global
@@ -601,14 +730,14 @@ __device__ __forceinline__ ListWindow list_window( const u64* __restrict__ cum, 
 
 // direct lighting (scene.c:542-581): one lane per (task, light, sample); the shadow rays exist only
 // as (entry, child index) and are regenerated from the task with an O(1) LCG skip-ahead
-template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_DIRECT )
 k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
           const unsigned int* __restrict__ dl_dir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
     if( total == 0 || w.sc->overflow ) return;
-    stage_scene( w.prm, smem );
+    const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
@@ -639,7 +768,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
                 const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
                 const DLight<R>& lg = prm.lights[ li ];
 
-                const SceneView<R> sv = ray_view( prm, pos );
+                const SceneView<R> sv = ray_view( prm, sv0, pos );
                 V3<R> axis; R cos_rs;
                 obj_fov( sv, lg.node, pos, &axis, &cos_rs );
                 const Basis<R> bs = basis_con_z( axis );
@@ -652,12 +781,12 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
                 {
                     HitCtx ctx; ctx.key = 0;
                     n_shadow++;
-                    R a = light_hit( sv, lg.node, out, ctx );                                // scene.c:564
+                    R a = light_hit<R, MARCH>( sv, lg.node, out, ctx, cm );                                // scene.c:564
                     if( a < Num<R>::inf() )
                     {
                         if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, prj );
                         n_shadow++;
-                        R sh = scene_query<R>( sv, out, Q_MATTER, a, nullptr, ctx, cm );          // scene.c:569
+                        R sh = scene_query<R, MARCH>( sv, out, Q_MATTER, a, nullptr, ctx, cm );          // scene.c:569
                         if( sh > a )
                         {
                             V3<R> hp = madd( out.p, out.d, a );
@@ -682,65 +811,100 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
 
 // indirect rays (scene.c:584-621): one lane per (task, path sample); the child ray is generated,
 // traced and shaded in place, never stored.
-template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_PATH )
 k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
+    __shared__ unsigned long long ring_all[ ACN_BLOCK / 32 ][ ACN_PEND ];
     const unsigned long long blk_lo = w.sc->path_blk_lo, blk_hi = w.sc->path_blk_hi;
     if( blk_hi <= blk_lo || w.sc->overflow ) return;
     const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
-    stage_scene( w.prm, smem );
+    const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const int L = prm.n_lights;
     const unsigned long long n_blocks = blk_hi - blk_lo;
+    unsigned long long* ring = ring_all[ threadIdx.x >> 5 ];
+    int pend_head = 0, pend_n = 0;
+    bool input_done = false;
+    unsigned long long b_cur = 0, b_end = 0;
+    const bool split = prm.n_heavy > 0;
     unsigned long long n_path = 0;
     for( ;; )
     {
-        const unsigned long long b0 = warp_fetch( &w.sc->cur_path, ACN_CHUNK, lane );
-        if( b0 >= n_blocks ) break;
-        for( unsigned long long bb = b0; bb < b0 + ACN_CHUNK && bb < n_blocks; bb++ )
+        // one item per lane: ( task entry t, child i ) packed as t << 32 | i
+        unsigned long long item = ACN_NONE64;
+        bool fresh = false;
+        if( pend_n >= 32 || ( input_done && pend_n > 0 ) )
         {
-            const unsigned long long blk = blk_lo + bb;
+            const int k = pend_n < 32 ? pend_n : 32;
+            if( lane < k ) item = ring[ ( pend_head + lane ) & ( ACN_PEND - 1 ) ];
+            pend_head += k; pend_n -= k;
+            __syncwarp();
+        }
+        else if( !input_done )
+        {
+            if( b_cur >= b_end )
+            {
+                b_cur = warp_fetch( &w.sc->cur_path, ACN_CHUNK, lane );
+                b_end = b_cur + ACN_CHUNK < n_blocks ? b_cur + ACN_CHUNK : n_blocks;
+                if( b_cur >= n_blocks ) { input_done = true; continue; }
+            }
+            const unsigned long long blk = blk_lo + b_cur; b_cur++;
             const ListWindow lw = list_window( in.cum, pdir, blk, n_entries, lane );
             const unsigned long long idx = ( blk << 5 ) + lane;
             const bool live = idx < c_hi;
             const int j = window_find( lw.incl, live ? idx : ( blk << 5 ) );
             const unsigned long long prev = __shfl_sync( ACN_FULL, lw.incl, ( j + 31 ) & 31 );
-            R miss = R( 0 );
-            V3<R> tpm = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
-            int sample = -1;
-            if( live )
+            if( live ) item = ( ( unsigned long long )( lw.e0 + j ) << 32 ) | ( unsigned int )( idx - ( j ? prev : lw.excl0 ) );
+            fresh = true;
+        }
+        else break;
+
+        R miss = R( 0 );
+        V3<R> tpm = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+        int sample = -1, key = -1;
+        bool defer = false;
+        if( item != ACN_NONE64 )
+        {
+            const unsigned long long t = item >> 32;
+            const unsigned int i = ( unsigned int )item;
+            const I4 m = in.meta[ t ];
+            const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+            const V3<R> nrm = xyz( nc );
+            const Basis<R> bs = basis_con_z( nrm );
+            u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )L * ( unsigned int )m.z + i );
+            Ray<R> out; out.p = xyz( pi );
+            out.d = from_basis( bs, sphere_cap<R>( &rv, R( 1 ) ) );
+            R wgt = dot( out.d, nrm );
+            // every lane of a task carries the task's key, sample and throughput: the lane that ends up
+            // adding the run's sum may itself be a deferred or back-facing child
+            sample = m.x; key = ( int )( t & 0x7FFFFFFFull );
+            tpm = xyz( tb ) * ( R( 2 ) / ( R )( unsigned int )m.w );                         // scene.c:620
+            if( wgt > R( 0 ) )                                                           // scene.c:600
             {
-                const unsigned long long t = ( unsigned long long )lw.e0 + j;
-                const unsigned int i = ( unsigned int )( idx - ( j ? prev : lw.excl0 ) );
-                const I4 m = in.meta[ t ];
-                sample = m.x;
-                const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
-                const V3<R> nrm = xyz( nc );
-                const Basis<R> bs = basis_con_z( nrm );
-                u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )L * ( unsigned int )m.z + i );
-                Ray<R> out; out.p = xyz( pi );
-                out.d = from_basis( bs, sphere_cap<R>( &rv, R( 1 ) ) );
-                R wgt = dot( out.d, nrm );
-                tpm = xyz( tb ) * ( R( 2 ) / ( R )( unsigned int )m.w );                     // scene.c:620
-                if( wgt > R( 0 ) )                                                           // scene.c:600
+                if( fresh && split && ray_is_heavy( prm, sv0, out ) ) defer = true;
+                else
                 {
                     if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, xyz( pa ) );
                     n_path++;
                     const R ci = wgt * pi.w;
                     const bool probe = ( m.y - 10 ) == 0 || ci < prm.min_intensity;
-                    if( trace_ray( w, cm, out, ci, m.y - 10, tpm, RC_PATH, probe, m.x, mix64( in.key[ t ], KEY_PATH0 + i ) ) ) miss = ci;
+                    if( trace_ray<R, MARCH>( w, sv0, cm, out, ci, m.y - 10, tpm, RC_PATH, probe, m.x, mix64( in.key[ t ], KEY_PATH0 + i ) ) ) miss = ci;
                 }
             }
-            __syncwarp();
-            // children that left the scene: background * throughput * sum of their intensities, one
-            // atomic triple per task segment
-            const int key = live ? j : -1;
+        }
+        __syncwarp();
+        if( fresh && split ) pend_push( ring, pend_head, pend_n, defer, item, lane );
+        // children that left the scene: background * throughput * sum of their intensities, one atomic
+        // triple per run of lanes of the same task (items are in non-decreasing task order in both kinds of group)
+        const unsigned int has = __ballot_sync( ACN_FULL, miss != R( 0 ) );
+        if( has )
+        {
             miss = seg_sum( miss, key, lane );
             const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
-            if( live && ( lane == 0 || kprev != key ) && miss != R( 0 ) ) add_sample( w, sample, mul( prm.background, tpm ) * miss );
+            if( key >= 0 && ( lane == 0 || kprev != key ) && miss != R( 0 ) ) add_sample( w, sample, mul( prm.background, tpm ) * miss );
         }
     }
     warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
@@ -886,6 +1050,22 @@ template <typename R> static int alloc_rays( RayBuf<R>& b, size_t n )
 }
 template <typename R> static void free_rays( RayBuf<R>& b ) { cudaFree( b.o_i ); cudaFree( b.d_ ); cudaFree( b.tp ); cudaFree( b.meta ); }
 
+template <typename R> static int alloc_hits( HitBuf<R>& b, size_t n )
+{
+    int rc;
+    if( ( rc = dev_alloc( &b.o_a, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.d_i, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.n_e, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.tp, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.meta, n ) ) ) return rc;
+    if( ( rc = dev_alloc( &b.key, n ) ) ) return rc;
+    return ACN_OK;
+}
+template <typename R> static void free_hits( HitBuf<R>& b )
+{
+    cudaFree( b.o_a ); cudaFree( b.d_i ); cudaFree( b.n_e ); cudaFree( b.tp ); cudaFree( b.meta ); cudaFree( b.key );
+}
+
 template <typename R> static int alloc_tasks( TaskBuf<R>& b, size_t n )
 {
     int rc;
@@ -916,6 +1096,7 @@ template <typename R> struct Tracer : TracerBase
     // queues
     RayBuf<R>  ray_stack, ray_cur;
     TaskBuf<R> task_stack, task_new;
+    HitBuf<R>  hit_q;
     u64* d_dl_cum = nullptr; unsigned int* d_dl_slot = nullptr; unsigned int* d_dl_dir = nullptr; unsigned int* d_pdir = nullptr;
     uint64_t   budget = 0, ray_min = 0, ray_cap = 0, task_stack_cap = 0, task_new_cap = 0, dl_dir_cap = 0, pdir_cap = 0, prim_chunk = 0;
     Sched*     d_sc = nullptr;
@@ -923,8 +1104,13 @@ template <typename R> struct Tracer : TracerBase
     R*         d_accum = nullptr; uint64_t accum_cap = 0;
     int        smem_bytes = 0;
     int        max_csg_depth = 0;
-    int        grid_trace[ 4 ] = { 0, 0, 0, 0 };   // persistent grids: primary, rays, path, direct
+    int        grid_trace[ 5 ] = { 0, 0, 0, 0, 0 };   // persistent grids: primary, rays, path, direct, shade
     int        grid_util = 0;
+    bool       march = false;     // kernels instantiated with the reference's recursive CSG march (scale nodes, CSG over distance fields, f64 validation)
+    void ( *kp_primary )( Wave<R>, const double* ) = nullptr;
+    void ( *kp_rays )( Wave<R>, RayBuf<R> ) = nullptr;
+    void ( *kp_path )( Wave<R>, TaskBuf<R>, const unsigned int* ) = nullptr;
+    void ( *kp_direct )( Wave<R>, TaskBuf<R>, const u64*, const unsigned int*, const unsigned int* ) = nullptr;
 
     ~Tracer() override
     {
@@ -933,7 +1119,7 @@ template <typename R> struct Tracer : TracerBase
         cudaFree( d_prog ); cudaFree( d_prog_ref ); cudaFree( d_parent );
         cudaFree( d_mats ); cudaFree( d_lights ); cudaFree( d_skipA ); cudaFree( d_skipC );
         free_rays( ray_stack ); free_rays( ray_cur );
-        free_tasks( task_stack ); free_tasks( task_new );
+        free_tasks( task_stack ); free_tasks( task_new ); free_hits( hit_q );
         cudaFree( d_dl_cum ); cudaFree( d_dl_slot ); cudaFree( d_dl_dir ); cudaFree( d_pdir );
         cudaFree( d_sc ); if( h_sc ) cudaFreeHost( h_sc );
         cudaFree( d_accum ); cudaFree( d_xy_stage ); cudaFree( d_rgb_stage );
@@ -947,8 +1133,8 @@ template <typename R> struct Tracer : TracerBase
     Wave<R> make_wave( uint64_t index_base )
     {
         Wave<R> w;
-        w.prm = prm; w.rays_out = ray_stack; w.tasks_out = task_new; w.sc = d_sc; w.accum = d_accum;
-        w.rays_cap = ray_cap; w.tasks_cap = task_new_cap; w.index_base = index_base;
+        w.prm = prm; w.rays_out = ray_stack; w.tasks_out = task_new; w.hits_out = hit_q; w.sc = d_sc; w.accum = d_accum;
+        w.rays_cap = ray_cap; w.tasks_cap = task_new_cap; w.hits_cap = task_new_cap; w.index_base = index_base;
         return w;
     }
 };
@@ -1234,6 +1420,28 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         ACN_CUDA( cudaMemcpy( d_prog, cb.prog.data(), cb.prog.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
         ACN_CUDA( cudaMemcpy( d_prog_ref, cb.prog_ref.data(), cb.prog_ref.size() * sizeof( I4 ), cudaMemcpyHostToDevice ) );
         ACN_CUDA( cudaMemcpy( d_parent, cb.parent.data(), cb.parent.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
+        // does any top-level object need the recursive march?
+        march = false;
+        std::function<void( int )> walk = [ & ]( int c )
+        {
+            const acn_flat_node& cn = fs->nodes[ c ];
+            for( int i = 0; i < cn.child1; i++ )
+            {
+                const int e = fs->children[ cn.child0 + i ];
+                const acn_flat_node& nd = fs->nodes[ e ];
+                if( nd.kind == ACN_KIND_COMPOUND ) { walk( e ); continue; }
+                if( nd.kind >= ACN_KIND_PAIR_INSIDE && cb.prog_ref[ e ].y == 0 ) march = true;
+            }
+        };
+        walk( fs->light_root ); walk( fs->matter_root );
+        if( march )
+        {
+            kp_primary = k_primary<R, true>; kp_rays = k_rays<R, true>; kp_path = k_path<R, true>; kp_direct = k_direct<R, true>;
+        }
+        else
+        {
+            kp_primary = k_primary<R, false>; kp_rays = k_rays<R, false>; kp_path = k_path<R, false>; kp_direct = k_direct<R, false>;
+        }
     }
 
     // ---- materials
@@ -1342,16 +1550,42 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     prm.eps_rel = ( R )eps_rel;
     prm.skipA = d_skipA; prm.skipC = d_skipC; prm.skip_n = skip_n;
 
+    // expensive top-level objects for the warp-level compaction: everything that is not a plane/sphere/squaroid
+    {
+        prm.n_heavy = 0;
+        std::vector<int> hv;
+        bool open = false;      // an expensive object without envelope: every ray is expensive, nothing to split
+        std::function<void( int )> walk = [ & ]( int c )
+        {
+            const acn_flat_node& cn = fs->nodes[ c ];
+            for( int i = 0; i < cn.child1; i++ )
+            {
+                const int e = fs->children[ cn.child0 + i ];
+                const acn_flat_node& nd = fs->nodes[ e ];
+                if( nd.kind == ACN_KIND_COMPOUND ) { walk( e ); continue; }
+                if( nd.kind == ACN_KIND_PLANE || nd.kind == ACN_KIND_SPHERE || nd.kind == ACN_KIND_SQUAROID ) continue;
+                if( nd.has_envelope ) hv.push_back( e ); else open = true;
+            }
+        };
+        walk( fs->light_root ); walk( fs->matter_root );
+        if( !open && !hv.empty() && hv.size() <= 8 && !getenv( "ACN_NO_COMPACTION" ) )
+        {
+            prm.n_heavy = ( int )hv.size();
+            for( size_t i = 0; i < hv.size(); i++ ) prm.heavy[ i ] = hv[ i ];
+        }
+    }
+
     // shared-memory staging of the node table
     size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )( fs->n_children + n_prog ) * sizeof( int );
     prm.stage_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
     smem_bytes = prm.stage_bytes + ( int )csg_mem_bytes<R>( ACN_BLOCK );      // staged tables, then the CSG interval lists
     if( smem_bytes > 40 * 1024 )
     {
-        ACN_CUDA( cudaFuncSetAttribute( k_primary<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
-        ACN_CUDA( cudaFuncSetAttribute( k_rays<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
-        ACN_CUDA( cudaFuncSetAttribute( k_direct<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
-        ACN_CUDA( cudaFuncSetAttribute( k_path<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_path, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( k_shade<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
     }
 
     // device stack for the CSG recursion (obj_ray_hit <-> pair_hit <-> obj_side)
@@ -1385,6 +1619,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     if( ( rc = alloc_rays( ray_cur, budget ) ) ) return rc;
     if( ( rc = alloc_tasks( task_stack, task_stack_cap ) ) ) return rc;
     if( ( rc = alloc_tasks( task_new, task_new_cap ) ) ) return rc;
+    if( ( rc = alloc_hits( hit_q, task_new_cap ) ) ) return rc;
     if( ( rc = dev_alloc( &d_dl_cum, task_new_cap ) ) ) return rc;
     if( ( rc = dev_alloc( &d_dl_slot, task_new_cap ) ) ) return rc;
     if( ( rc = dev_alloc( &d_dl_dir, dl_dir_cap ) ) ) return rc;
@@ -1398,10 +1633,11 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         ACN_CUDA( cudaGetDeviceProperties( &pr, device ) );
         const int sms = pr.multiProcessorCount;
         int b = 0;
-        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_primary<R>, ACN_BLOCK, smem_bytes ) ); grid_trace[ 0 ] = sms * ( b > 0 ? b : 1 );
-        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_rays<R>, ACN_BLOCK, smem_bytes ) );    grid_trace[ 1 ] = sms * ( b > 0 ? b : 1 );
-        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_path<R>, ACN_BLOCK, smem_bytes ) );    grid_trace[ 2 ] = sms * ( b > 0 ? b : 1 );
-        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_direct<R>, ACN_BLOCK, smem_bytes ) );  grid_trace[ 3 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_primary, ACN_BLOCK, smem_bytes ) ); grid_trace[ 0 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_rays, ACN_BLOCK, smem_bytes ) );    grid_trace[ 1 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_path, ACN_BLOCK, smem_bytes ) );    grid_trace[ 2 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_direct, ACN_BLOCK, smem_bytes ) );  grid_trace[ 3 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_shade<R>, ACN_BLOCK, smem_bytes ) );   grid_trace[ 4 ] = sms * ( b > 0 ? b : 1 );
         grid_util = sms * 4;
     }
     return ACN_OK;
@@ -1447,7 +1683,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         if( mode == SCHED_PRIMARY )
         {
             kp_begin( 0 );
-            k_primary<R><<< grid_trace[ 0 ], ACN_BLOCK, smem_bytes, st >>>( w, d_xy );
+            kp_primary<<< grid_trace[ 0 ], ACN_BLOCK, smem_bytes, st >>>( w, d_xy );
             kp_end( 0 );
             launches++;
         }
@@ -1455,19 +1691,20 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         {
             k_pop<R><<< grid_util, 256, 0, st >>>( d_sc, ray_stack, ray_cur );
             kp_begin( 1 );
-            k_rays<R><<< grid_trace[ 1 ], ACN_BLOCK, smem_bytes, st >>>( w, ray_cur );
+            kp_rays<<< grid_trace[ 1 ], ACN_BLOCK, smem_bytes, st >>>( w, ray_cur );
             kp_end( 1 );
             kp_begin( 2 );
-            k_path<R><<< grid_trace[ 2 ], ACN_BLOCK, smem_bytes, st >>>( w, task_stack, d_pdir );
+            kp_path<<< grid_trace[ 2 ], ACN_BLOCK, smem_bytes, st >>>( w, task_stack, d_pdir );
             kp_end( 2 );
             launches += 3;
         }
+        k_shade<R><<< grid_trace[ 4 ], ACN_BLOCK, smem_bytes, st >>>( w, hit_q );
         k_index<R><<< grid_util, 256, 0, st >>>( d_sc, task_new, task_new_cap, prm.n_lights, d_dl_cum, d_dl_slot, d_dl_dir, task_new_cap, dl_dir_cap,
                                                  task_stack, d_pdir, task_stack_cap, pdir_cap );
         kp_begin( 3 );
-        k_direct<R><<< grid_trace[ 3 ], ACN_BLOCK, smem_bytes, st >>>( w, task_new, d_dl_cum, d_dl_slot, d_dl_dir );
+        kp_direct<<< grid_trace[ 3 ], ACN_BLOCK, smem_bytes, st >>>( w, task_new, d_dl_cum, d_dl_slot, d_dl_dir );
         kp_end( 3 );
-        launches += 2;
+        launches += 3;
     };
 
     const int iters_per_poll = 4;
