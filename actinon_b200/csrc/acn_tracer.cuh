@@ -505,7 +505,7 @@ template <typename R, bool MARCH> __device__ __forceinline__ R light_hit( const 
 // ---------------------------------------------------------------------------------------------
 #define ACN_BLOCK 128
 #ifndef ACN_CHUNK
-#define ACN_CHUNK 4        // 32-item groups per cursor fetch
+#define ACN_CHUNK 2        // 32-item groups per cursor fetch
 #endif
 // minimum resident blocks per SM the compiler must fit the registers of each tracing kernel into
 #ifndef ACN_MINB_RAYS
@@ -1600,7 +1600,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
 
 
     // ---- queues.  budget = path children (and explicit rays) traced per wavefront iteration
-    budget = opt->wave_budget > 0 ? ( uint64_t )opt->wave_budget : ( 1ull << 22 );
+    budget = opt->wave_budget > 0 ? ( uint64_t )opt->wave_budget : ( 1ull << 23 );
     if( budget < 64 ) budget = 64;
     ray_min = budget / 4 < 65536 ? budget / 4 : 65536;      // smaller ray waves wait for company while path work is pending
     ray_cap = budget * 24;
