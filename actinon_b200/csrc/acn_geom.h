@@ -21,6 +21,9 @@ namespace acn {
 
 template <typename R> struct alignas( sizeof( R ) * 4 ) R4 { R x, y, z, w; };
 struct alignas( 16 ) I4 { int x, y, z, w; };
+// one child of a compound, packed for the traversal: its envelope and its link word with the node index in .w
+// (the material, which the traversal does not need, stays in link[n].w)
+template <typename R> struct CRec { R4<R> env; I4 link; };
 
 enum
 {
@@ -39,7 +42,8 @@ template <typename R> struct SceneView
     const R4<R>* env;
     const I4*    link;
     const R4<R>* geo;
-    const int*   children;
+    const int*   children;  // child node indices of all compounds (host / march)
+    const CRec<R>* crec;    // the same lists as packed records (device traversal)
     const int*   prog;      // postfix CSG programs (interval evaluator), see acn_isect.cuh: csg_eval
     const I4*    prog_ref;  // per node: program start, length (0: none -> reference march), truth table offset (-1: none), variables
     const int*   parent;    // per node: CSG parent (-1 at the top of an object)
@@ -73,6 +77,22 @@ template <typename R> ACN_HD bool envelope_hits( const R4<R>& e, const Ray<R>& r
     V3<R> l = p - ray.d * s;
     R disc = e.w * e.w - sqr( l );
     return disc >= R( 0 ) && ( s < R( 0 ) || q < R( 0 ) );
+}
+
+// envelope test with a horizon: false as well when the ray enters the envelope beyond t_far (nothing inside can be
+// hit before t_far then).  -s - sqrt(disc) > t_far  <=>  -s - t_far > 0 and ( -s - t_far )^2 > disc: no square root.
+template <typename R> ACN_HD bool envelope_hits_before( const R4<R>& e, const Ray<R>& ray, R t_far )
+{
+    V3<R> p = ray.p - xyz( e );
+    R s = dot( p, ray.d );
+    R q = sqr( p ) - e.w * e.w;
+    V3<R> l = p - ray.d * s;
+    R disc = e.w * e.w - sqr( l );
+    if( !( disc >= R( 0 ) ) ) return false;
+    if( q < R( 0 ) ) return true;               // origin inside
+    if( !( s < R( 0 ) ) ) return false;
+    R g = -s - t_far;
+    return !( g > R( 0 ) && g * g > disc );
 }
 
 template <typename R> ACN_HD R sphere_hit( V3<R> c, R r, const Ray<R>& ray, R eps, V3<R>* nor )

@@ -338,11 +338,16 @@ template <typename R> __device__ __forceinline__ void trans_commit( const SceneV
     }
 }
 
-template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( const SceneView<R>& sv, const Ray<R>& ray, const int flags, const R t_any,
-                                                                Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
+template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( const SceneView<R>& sv, const Ray<R>& ray, const int flags, const R t_far,
+                                                                            Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
 {
+    // t_far: hits at a >= t_far are of no interest to the caller (the shadow test's light distance, a path
+    // ray's max_path_length, +inf otherwise).  Without Q_TRANS a hit with a <= t_far ends the search at once.
+    // Envelopes are culled against the best candidate so far: nothing inside an envelope that the ray enters
+    // at t_env can be reported closer than t_env - eps, so skipping it when t_env > horizon + 2 eps changes nothing.
     const R inf = Num<R>::inf();
     const bool want_trans = ( flags & Q_TRANS ) != 0;
+    const R slack = R( 2 ) * sv.eps;
     R best = inf;
     #pragma unroll 1
     for( int pass = 0; pass < 2; pass++ )
@@ -350,7 +355,8 @@ template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( cons
         if( !( flags & ( pass == 0 ? Q_LIGHT : Q_MATTER ) ) ) continue;
         const int root = pass == 0 ? sv.light_root : sv.matter_root;
         const I4 rl = sv.link[ root ];
-        if( ( node_flags( rl ) & F_ENV ) && !envelope_hits( sv.env[ root ], ray ) ) continue;
+        const R far0 = r_min( t_far, best );                 // strict '<' between the roots: matter must beat the lights
+        if( ( node_flags( rl ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + slack ) ) continue;
         int sb[ COMPOUND_STACK ], se[ COMPOUND_STACK ];
         int sp = 0;
         int beg = rl.y, end = rl.y + rl.z;
@@ -361,9 +367,16 @@ template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( cons
         {
             while( beg < end )
             {
-                const int c = sv.children[ beg++ ];
-                const I4 lk = sv.link[ c ];
-                if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ c ], ray ) ) continue;
+                const CRec<R> rec = sv.crec[ beg++ ];
+                const I4 lk = rec.link;
+                const int c = lk.w;
+                if( node_flags( lk ) & F_ENV )
+                {
+                    // horizon: an element must come within eps of the root's minimum to matter (merge rule);
+                    // inside a nested element it must also beat that element's own minimum
+                    const R hor = want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 );
+                    if( !envelope_hits_before( rec.env, ray, hor + slack ) ) continue;
+                }
                 if( node_kind( lk ) == K_COMPOUND )
                 {
                     if( sp < COMPOUND_STACK ) { sb[ sp ] = beg; se[ sp ] = end; sp++; beg = lk.y; end = lk.y + lk.z; }
@@ -373,7 +386,7 @@ template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( cons
                 const R a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm );
                 if( !want_trans )
                 {
-                    if( a < min_a ) { min_a = a; if( a <= t_any ) return a; }
+                    if( a < min_a ) { min_a = a; if( a <= t_far ) return a; }
                 }
                 else if( sp > 0 )
                 {

@@ -264,8 +264,8 @@ template <typename R> __device__ __forceinline__ SceneView<R> stage_scene( const
     R4<R>* s_geo  = s_env + n;
     I4*    s_link = reinterpret_cast<I4*>( s_geo + n * GEO_STRIDE );
     I4*    s_pref = s_link + n;
-    int*   s_chl  = reinterpret_cast<int*>( s_pref + n );
-    int*   s_par  = s_chl + prm.n_children;
+    CRec<R>* s_crec = reinterpret_cast<CRec<R>*>( s_pref + n );
+    int*   s_par  = reinterpret_cast<int*>( s_crec + prm.n_children );
     int*   s_prog = s_par + n;
     for( int i = threadIdx.x; i < n; i += blockDim.x )
     {
@@ -273,10 +273,10 @@ template <typename R> __device__ __forceinline__ SceneView<R> stage_scene( const
         s_pref[ i ] = prm.sv.prog_ref[ i ]; s_par[ i ] = prm.sv.parent[ i ];
     }
     for( int i = threadIdx.x; i < n * GEO_STRIDE; i += blockDim.x ) s_geo[ i ] = prm.sv.geo[ i ];
-    for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_chl[ i ] = prm.sv.children[ i ];
+    for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_crec[ i ] = prm.sv.crec[ i ];
     for( int i = threadIdx.x; i < prm.n_prog; i += blockDim.x ) s_prog[ i ] = prm.sv.prog[ i ];
     __syncthreads();
-    sv.env = s_env; sv.geo = s_geo; sv.link = s_link; sv.children = s_chl;
+    sv.env = s_env; sv.geo = s_geo; sv.link = s_link; sv.crec = s_crec;
     sv.prog_ref = s_pref; sv.parent = s_par; sv.prog = s_prog;
     return sv;
 }
@@ -438,7 +438,7 @@ template <typename R, bool MARCH> __device__ __forceinline__ bool trace_ray( con
     const R t_lim = path ? prm.max_path_length : inf;
     Trans<R> tr;
     tr.exit_obj = tr.enter_obj = -1; tr.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
-    R a = scene_query<R, MARCH>( sv, ray, flags, t_lim, &tr, ctx, cm );
+    R a = scene_query<R, MARCH>( sv, ray, flags, t_lim, &tr, ctx, cm );     // nothing at or beyond t_lim matters
     if( !( a < t_lim ) ) return true;
     if( probe ) return false;
     // the hit distance itself is only good to a few ulp of its magnitude: keep the shading point that far in front
@@ -1089,7 +1089,7 @@ template <typename R> struct Tracer : TracerBase
 {
     DParams<R> prm;
     // device copies of the scene tables
-    R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr;
+    R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr; CRec<R>* d_crec = nullptr;
     int* d_prog = nullptr; I4* d_prog_ref = nullptr; int* d_parent = nullptr; int n_prog = 0;
     DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
@@ -1115,7 +1115,7 @@ template <typename R> struct Tracer : TracerBase
     ~Tracer() override
     {
         cudaSetDevice( device );
-        cudaFree( d_env ); cudaFree( d_link ); cudaFree( d_geo ); cudaFree( d_children );
+        cudaFree( d_env ); cudaFree( d_link ); cudaFree( d_geo ); cudaFree( d_children ); cudaFree( d_crec );
         cudaFree( d_prog ); cudaFree( d_prog_ref ); cudaFree( d_parent );
         cudaFree( d_mats ); cudaFree( d_lights ); cudaFree( d_skipA ); cudaFree( d_skipC );
         free_rays( ray_stack ); free_rays( ray_cur );
@@ -1407,6 +1407,16 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     ACN_CUDA( cudaMemcpy( d_link, link.data(), n * sizeof( I4 ), cudaMemcpyHostToDevice ) );
     ACN_CUDA( cudaMemcpy( d_geo, geo.data(), ( size_t )n * GEO_STRIDE * sizeof( R4<R> ), cudaMemcpyHostToDevice ) );
     if( fs->n_children > 0 ) ACN_CUDA( cudaMemcpy( d_children, fs->children, fs->n_children * sizeof( int ), cudaMemcpyHostToDevice ) );
+    {   // the child lists once more as packed records (envelope + link word, node index in .w)
+        std::vector<CRec<R>> crec( fs->n_children > 0 ? fs->n_children : 1 );
+        for( int i = 0; i < fs->n_children; i++ )
+        {
+            const int c = fs->children[ i ];
+            crec[ i ].env = env[ c ]; crec[ i ].link = link[ c ]; crec[ i ].link.w = c;
+        }
+        if( ( rc = dev_alloc( &d_crec, crec.size() ) ) ) return rc;
+        ACN_CUDA( cudaMemcpy( d_crec, crec.data(), crec.size() * sizeof( CRec<R> ), cudaMemcpyHostToDevice ) );
+    }
 
     // ---- CSG interval programs
     {
@@ -1522,7 +1532,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     }
 
     // ---- params
-    prm.sv.env = d_env; prm.sv.link = d_link; prm.sv.geo = d_geo; prm.sv.children = d_children;
+    prm.sv.env = d_env; prm.sv.link = d_link; prm.sv.geo = d_geo; prm.sv.children = d_children; prm.sv.crec = d_crec;
     prm.sv.prog = d_prog; prm.sv.prog_ref = d_prog_ref; prm.sv.parent = d_parent; prm.n_prog = n_prog;
     prm.sv.eps = ( R )eps; prm.sv.light_root = fs->light_root; prm.sv.matter_root = fs->matter_root;
     prm.sv.seed_mode = opt->seed_mode;
@@ -1576,7 +1586,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     }
 
     // shared-memory staging of the node table
-    size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )( fs->n_children + n_prog ) * sizeof( int );
+    size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )fs->n_children * sizeof( CRec<R> ) + ( size_t )n_prog * sizeof( int );
     prm.stage_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
     smem_bytes = prm.stage_bytes + ( int )csg_mem_bytes<R>( ACN_BLOCK );      // staged tables, then the CSG interval lists
     if( smem_bytes > 40 * 1024 )
