@@ -184,50 +184,63 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
         unsigned long long vars = 0;
         int nv = 0, ne = 0;
         bool dropped = false;
-        // ---- pass 1: classify the ray against every leaf
+        // ---- pass 1: classify the ray against every leaf.  The lanes of a warp that evaluate this object walk
+        // the program in LOCKSTEP: a lane whose ray misses a sub-envelope does not jump ahead (it would then
+        // execute other program words than its neighbours and serialise against them) but idles through the
+        // subtree; the subtree is skipped only when no lane needs it.  The envelope's own crossings are the
+        // CLIP variable's events, so the envelope is intersected once, at the ENV word.
+        int skip_to = pr.x;                         // this lane idles while pc < skip_to
         #pragma unroll 1
         for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
         {
             const int ins = sv.prog[ pc ];
             const int op = ins & 15, n = ins >> 4;
-            R t0 = R( 0 ), t1 = R( 0 ); int s0 = 0, c = 0, id0 = CSG_VIRTUAL, id1 = CSG_VIRTUAL;
-            if( op == CSG_LEAF ) { c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; }
-            else if( op == CSG_CLIP ) { const R4<R> e = sv.env[ n ]; c = sphere_events( xyz( e ), e.w, ray, &s0, &t0, &t1 ); }
+            const bool act = pc >= skip_to;
+            R t0 = R( 0 ), t1 = R( 0 ); int s0 = 0, c = 0, id0 = CSG_VIRTUAL, id1 = CSG_VIRTUAL, var = nv;
+            if( op == CSG_LEAF ) { if( act ) { c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; } nv++; }
             else if( op == CSG_RUN )
             {
-                R lo = R( -1 ), hi = inf;
-                #pragma unroll 1
-                for( int m = 1; m <= n; m++ )
+                if( act )
                 {
-                    const int w = sv.prog[ pc + m ];
-                    const int node = w >> 4;
-                    R a0 = R( 0 ), a1 = R( 0 ); int ms0;
-                    const int mc = leaf_events( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
-                    if( ( w & 15 ) == CSG_MEMBER_NEG ) ms0 ^= 1;
-                    R mlo, mhi;
-                    member_interval( ms0, mc, a0, a1, &mlo, &mhi );
-                    if( mlo > lo ) { lo = mlo; id0 = pc + m - pr.x; }
-                    if( mhi < hi ) { hi = mhi; id1 = pc + m - pr.x; }
+                    R lo = R( -1 ), hi = inf;
+                    #pragma unroll 1
+                    for( int m = 1; m <= n; m++ )
+                    {
+                        const int w = sv.prog[ pc + m ];
+                        const int node = w >> 4;
+                        R a0 = R( 0 ), a1 = R( 0 ); int ms0;
+                        const int mc = leaf_events( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
+                        if( ( w & 15 ) == CSG_MEMBER_NEG ) ms0 ^= 1;
+                        R mlo, mhi;
+                        member_interval( ms0, mc, a0, a1, &mlo, &mhi );
+                        if( mlo > lo ) { lo = mlo; id0 = pc + m - pr.x; }
+                        if( mhi < hi ) { hi = mhi; id1 = pc + m - pr.x; }
+                    }
+                    if( lo < R( 0 ) )   { s0 = 1; if( hi < inf ) { c = 1; t0 = hi; id0 = id1; } }
+                    else if( lo < hi )  { s0 = 0; c = 1; t0 = lo; if( hi < inf ) { c = 2; t1 = hi; } }
                 }
-                pc += n;
-                if( lo < R( 0 ) )   { s0 = 1; if( hi < inf ) { c = 1; t0 = hi; id0 = id1; } }
-                else if( lo < hi )  { s0 = 0; c = 1; t0 = lo; if( hi < inf ) { c = 2; t1 = hi; } }
+                pc += n; nv++;
             }
-            else
+            else if( op == CSG_ENV )
             {
-                if( op == CSG_ENV )
+                const int w2 = sv.prog[ ++pc ];
+                const int sub_end = pc + 1 + ( w2 & 0xFFFF );            // first word behind the subtree's CLIP
+                var = nv + ( w2 >> 16 ) - 1;                             // the CLIP variable closes the subtree
+                if( act )
                 {
-                    const int w2 = sv.prog[ ++pc ];
-                    if( !envelope_hits( sv.env[ n ], ray ) ) { pc += w2 & 0xFFFF; nv += w2 >> 16; }
+                    const R4<R> e = sv.env[ n ];
+                    c = sphere_events( xyz( e ), e.w, ray, &s0, &t0, &t1 );
+                    if( c == 0 ) { s0 = 0; skip_to = sub_end; }         // objects.c:264: the ray misses the envelope
                 }
-                continue;
+                if( !__any_sync( __activemask(), pc + 1 >= skip_to ) ) { nv += w2 >> 16; pc = sub_end - 1; }
             }
+            else { if( op == CSG_CLIP ) nv++; continue; }               // CLIP: events were taken at ENV; NEG / AND / OR: pass 2
             #pragma unroll 1
             for( int k = 0; k < c; k++ )
             {
                 const R t = k ? t1 : t0;
                 if( t <= t_floor ) { s0 ^= 1; continue; }                  // swept in an earlier round
-                const unsigned short iv = ( unsigned short )( ( k ? id1 : id0 ) | ( nv << 8 ) );
+                const unsigned short iv = ( unsigned short )( ( k ? id1 : id0 ) | ( var << 8 ) );
                 if( ne < CSG_E ) { cm.t[ ne * cm.stride ] = t; cm.iv[ ne * cm.stride ] = iv; ne++; }
                 else
                 {   // keep the CSG_E smallest
@@ -237,8 +250,7 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
                     if( t < tmax ) { cm.t[ kmax * cm.stride ] = t; cm.iv[ kmax * cm.stride ] = iv; }
                 }
             }
-            vars |= ( unsigned long long )s0 << nv;
-            nv++;
+            vars |= ( unsigned long long )s0 << var;
         }
         // ---- sweep: crossings in order of t until the solid's state flips at a real one
         int id = CSG_VIRTUAL;
