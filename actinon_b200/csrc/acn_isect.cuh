@@ -173,8 +173,11 @@ template <typename R> __device__ __forceinline__ void member_interval( int s0, i
 // each round keeps the CSG_E smallest crossings beyond t_floor; crossings at or before t_floor only
 // toggle their variable (they were swept in an earlier round).
 template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
-                                                             const CsgMem<R>& cm )
+                                                             const CsgMem<R>& cm, const R t_far )
 {
+    // t_far: the caller's horizon (+ slack).  Crossings beyond it cannot become the reported hit and the state of
+    // the solid beyond it is of no interest, so they are dropped at once; a convex run whose interval is empty or
+    // starts beyond the horizon stops testing its remaining members (slab clipping's early exit).
     const R inf = Num<R>::inf();
     const I4 pr = sv.prog_ref[ root ];          // start, length, truth table offset (-1: interpret), variables
     R t_floor = R( 0 );
@@ -215,6 +218,7 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
                         member_interval( ms0, mc, a0, a1, &mlo, &mhi );
                         if( mlo > lo ) { lo = mlo; id0 = pc + m - pr.x; }
                         if( mhi < hi ) { hi = mhi; id1 = pc + m - pr.x; }
+                        if( !( lo < hi ) || lo > t_far ) { lo = inf; break; }       // empty, or not before the horizon
                     }
                     if( lo < R( 0 ) )   { s0 = 1; if( hi < inf ) { c = 1; t0 = hi; id0 = id1; } }
                     else if( lo < hi )  { s0 = 0; c = 1; t0 = lo; if( hi < inf ) { c = 2; t1 = hi; } }
@@ -239,6 +243,7 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
             for( int k = 0; k < c; k++ )
             {
                 const R t = k ? t1 : t0;
+                if( t > t_far ) continue;                                  // beyond the caller's horizon
                 if( t <= t_floor ) { s0 ^= 1; continue; }                  // swept in an earlier round
                 const unsigned short iv = ( unsigned short )( ( k ? id1 : id0 ) | ( var << 8 ) );
                 if( ne < CSG_E ) { cm.t[ ne * cm.stride ] = t; cm.iv[ ne * cm.stride ] = iv; ne++; }
@@ -306,12 +311,12 @@ template <typename R> __device__ __noinline__ R march_hit( const SceneView<R>& s
 
 // obj_ray_hit after the envelope test (objects.c:261-284): fp_ray_hit + roughness
 template <typename R, bool MARCH> __device__ __forceinline__ R elem_hit( const SceneView<R>& sv, const I4& lk, int c, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
-                                                                         const CsgMem<R>& cm )
+                                                                         const CsgMem<R>& cm, const R t_far )
 {
     const int kind = node_kind( lk );
     R a;
     if( kind == K_PLANE || kind == K_SPHERE || kind == K_SQUAROID ) a = prim_hit( sv, kind, c, ray, nor );
-    else if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval( sv, c, ray, nor, ctx, cm );
+    else if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval( sv, c, ray, nor, ctx, cm, t_far );
     else if( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) a = dist_hit( sv, kind, c, ray, nor );
     else if( MARCH ) a = march_hit( sv, c, ray, nor, ctx );
     else a = Num<R>::inf();                 // unreachable: such scenes run the MARCH instantiation
@@ -382,20 +387,17 @@ template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( cons
                 const CRec<R> rec = sv.crec[ beg++ ];
                 const I4 lk = rec.link;
                 const int c = lk.w;
-                if( node_flags( lk ) & F_ENV )
-                {
-                    // horizon: an element must come within eps of the root's minimum to matter (merge rule);
-                    // inside a nested element it must also beat that element's own minimum
-                    const R hor = want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 );
-                    if( !envelope_hits_before( rec.env, ray, hor + slack ) ) continue;
-                }
+                // horizon: an element must come within eps of the root's minimum to matter (merge rule);
+                // inside a nested element it must also beat that element's own minimum
+                const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;
+                if( ( node_flags( lk ) & F_ENV ) && !envelope_hits_before( rec.env, ray, hor ) ) continue;
                 if( node_kind( lk ) == K_COMPOUND )
                 {
                     if( sp < COMPOUND_STACK ) { sb[ sp ] = beg; se[ sp ] = end; sp++; beg = lk.y; end = lk.y + lk.z; }
                     continue;
                 }
                 V3<R> n;
-                const R a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm );
+                const R a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm, hor );
                 if( !want_trans )
                 {
                     if( a < min_a ) { min_a = a; if( a <= t_far ) return a; }

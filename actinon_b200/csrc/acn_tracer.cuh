@@ -485,7 +485,7 @@ template <typename R, bool MARCH> __device__ __noinline__ R light_hit_cold( cons
 {
     const I4 lk = sv.link[ node ];
     if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ node ], ray ) ) return Num<R>::inf();
-    return elem_hit<R, MARCH>( sv, lk, node, ray, nullptr, ctx, cm );
+    return elem_hit<R, MARCH>( sv, lk, node, ray, nullptr, ctx, cm, Num<R>::inf() );
 }
 
 template <typename R, bool MARCH> __device__ __forceinline__ R light_hit( const SceneView<R>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
@@ -583,6 +583,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
     extern __shared__ __align__( 32 ) unsigned char smem[];
     const unsigned long long first = w.sc->prim_first, count = w.sc->prim_count;
     if( count == 0 || w.sc->overflow ) return;
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks: no need to stage the scene
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
@@ -623,6 +624,7 @@ k_rays( Wave<R> w, RayBuf<R> in )
     __shared__ unsigned long long ring_all[ ACN_BLOCK / 32 ][ ACN_PEND ];
     const unsigned long long count = w.sc->ray_take;
     if( count == 0 || w.sc->overflow ) return;
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const int lane = threadIdx.x & 31;
@@ -691,6 +693,7 @@ k_shade( Wave<R> w, HitBuf<R> in )
     unsigned long long count = w.sc->hits;
     if( count > w.hits_cap ) count = w.hits_cap;
     if( count == 0 || w.sc->overflow ) return;
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const int lane = threadIdx.x & 31;
     for( ;; )
@@ -737,6 +740,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     extern __shared__ __align__( 32 ) unsigned char smem[];
     const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
     if( total == 0 || w.sc->overflow ) return;
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= total ) return;     // more warps than chunks
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
@@ -819,6 +823,7 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     const unsigned long long blk_lo = w.sc->path_blk_lo, blk_hi = w.sc->path_blk_hi;
     if( blk_hi <= blk_lo || w.sc->overflow ) return;
     const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * ACN_CHUNK >= blk_hi - blk_lo ) return;   // more warps than chunks
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
