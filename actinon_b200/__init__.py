@@ -28,6 +28,9 @@ from .api import (  # noqa: F401
     SEED_INDEX_KEYED,
     PRECISION_F32,
     PRECISION_F64,
+    CSG_AUTO,
+    CSG_INTERVALS,
+    CSG_MARCH,
 )
 from . import scenes  # noqa: F401
 
@@ -35,4 +38,5 @@ __all__ = [
     "AcnError", "FlatScene", "Image", "Options", "Scene", "Stats", "Tracer", "device_count",
     "library_path", "load_library", "lum_machine_run", "measure_fp32_peak_tflops", "render_image",
     "scenes", "SEED_POSITION_HASH", "SEED_INDEX_KEYED", "PRECISION_F32", "PRECISION_F64",
+    "CSG_AUTO", "CSG_INTERVALS", "CSG_MARCH",
 ]

@@ -98,7 +98,7 @@ class Stats(C.Structure):
         ("rays_chromatic", C.c_uint64), ("rays_refraction", C.c_uint64), ("rays_path", C.c_uint64),
         ("rays_shadow", C.c_uint64), ("rays_light", C.c_uint64), ("diffuse_hits", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("waves", C.c_uint64), ("device_ms", C.c_double),
-        ("kernel_ms", C.c_double * 4), ("kernel_launches_by_class", C.c_uint64 * 4),
+        ("kernel_ms", C.c_double * 8), ("kernel_launches_by_class", C.c_uint64 * 8),
     ]
 
     @property

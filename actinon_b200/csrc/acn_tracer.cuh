@@ -1682,7 +1682,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
 
     uint64_t launches = 0;
     // optional per-kernel timing (ACN_PROFILE_KERNELS=1): an event pair around every launch of the four tracing kernels
-    struct KProf { bool on = false; std::vector<cudaEvent_t> a[ 4 ], b[ 4 ]; } kp;
+    struct KProf { bool on = false; std::vector<cudaEvent_t> a[ 8 ], b[ 8 ]; } kp;
     { const char* e = getenv( "ACN_PROFILE_KERNELS" ); kp.on = e && e[ 0 ] == '1'; }
     auto kp_begin = [ & ]( int c ) { if( kp.on ) { cudaEvent_t e; cudaEventCreate( &e ); cudaEventRecord( e, st ); kp.a[ c ].push_back( e ); } };
     auto kp_end = [ & ]( int c ) { if( kp.on ) { cudaEvent_t e; cudaEventCreate( &e ); cudaEventRecord( e, st ); kp.b[ c ].push_back( e ); } };
@@ -1693,10 +1693,12 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     // one k_sched + the kernels it planned; nothing here depends on device-side counts
     auto enqueue = [ & ]( int mode, uint64_t first, uint64_t cnt )
     {
+        kp_begin( 6 );
         k_sched<<< 1, 32, 0, st >>>( d_sc, task_stack.cum, d_pdir, budget, ray_min, mode, first, cnt );
         launches++;
         if( mode == SCHED_PRIMARY )
         {
+            kp_end( 6 );
             kp_begin( 0 );
             kp_primary<<< grid_trace[ 0 ], ACN_BLOCK, smem_bytes, st >>>( w, d_xy );
             kp_end( 0 );
@@ -1705,6 +1707,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         else
         {
             k_pop<R><<< grid_util, 256, 0, st >>>( d_sc, ray_stack, ray_cur );
+            kp_end( 6 );
             kp_begin( 1 );
             kp_rays<<< grid_trace[ 1 ], ACN_BLOCK, smem_bytes, st >>>( w, ray_cur );
             kp_end( 1 );
@@ -1713,9 +1716,13 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
             kp_end( 2 );
             launches += 3;
         }
+        kp_begin( 4 );
         k_shade<R><<< grid_trace[ 4 ], ACN_BLOCK, smem_bytes, st >>>( w, hit_q );
+        kp_end( 4 );
+        kp_begin( 5 );
         k_index<R><<< grid_util, 256, 0, st >>>( d_sc, task_new, task_new_cap, prm.n_lights, d_dl_cum, d_dl_slot, d_dl_dir, task_new_cap, dl_dir_cap,
                                                  task_stack, d_pdir, task_stack_cap, pdir_cap );
+        kp_end( 5 );
         kp_begin( 3 );
         kp_direct<<< grid_trace[ 3 ], ACN_BLOCK, smem_bytes, st >>>( w, task_new, d_dl_cum, d_dl_slot, d_dl_dir );
         kp_end( 3 );
@@ -1766,7 +1773,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     }
     if( kp.on )
     {
-        for( int c = 0; c < 4; c++ )
+        for( int c = 0; c < 8; c++ )
         {
             double tot = 0;
             for( size_t i = 0; i < kp.a[ c ].size() && i < kp.b[ c ].size(); i++ )

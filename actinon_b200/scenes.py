@@ -16,18 +16,19 @@ def _camera(sc: Scene, pos, look_at=(0.0, 0.0, 0.0), focal=4.0):
            camera_top_direction=(0, 0, 1), camera_focal_length=focal)
 
 
-def primitives(width=320, height=240, direct_samples=10, path_samples=0, gradient_cycles=0) -> Scene:
+def primitives(width=320, height=240, direct_samples=10, path_samples=0, gradient_cycles=0,
+               radiance_scale=1.0, background_scale=1.0) -> Scene:
     """config C1: primitives.acn at 320x240, direct_samples=10, path_samples=0."""
     sc = Scene()
     sc.set(threads=30, image_width=width, image_height=height, gamma=1.0,
            gradient_cycles=gradient_cycles, gradient_samples=2, gradient_threshold=0.03,
            trace_depth=25, trace_min_intensity=0.03, direct_samples=direct_samples, path_samples=path_samples,
-           max_path_length=1.0, background_color=(0.4, 0.4, 0.4))
+           max_path_length=1.0, background_color=tuple(0.4 * background_scale for _ in range(3)))
     _camera(sc, (0.0, -10.0, 0.0))
 
     # create_light( 0.5, 30 ) + vec( 0, -4, 4 )   (primitives.acn:45-51,100)
     light = sc.create_sphere(1.0) * 0.5
-    light.set_radiance(30)
+    light.set_radiance(30 * radiance_scale)
     light.move((0, -4, 4))
 
     # create_floor( -1 )   (primitives.acn:53-61)

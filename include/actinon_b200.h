@@ -183,9 +183,10 @@ typedef struct acn_stats
     uint64_t waves;              /* wavefront iterations                                            */
     double   device_ms;          /* CUDA-event time of the device work of this call                 */
     /* per-kernel CUDA-event times, filled when the environment has ACN_PROFILE_KERNELS=1
-       (index 0 primary, 1 explicit rays, 2 path children, 3 direct lighting) */
-    double   kernel_ms[4];
-    uint64_t kernel_launches_by_class[4];
+       (index 0 primary, 1 explicit rays, 2 path children, 3 direct lighting, 4 surface response,
+       5 list building, 6 scheduler + ray pop, 7 unused) */
+    double   kernel_ms[8];
+    uint64_t kernel_launches_by_class[8];
 } acn_stats;
 
 typedef struct acn_tracer acn_tracer;   /* opaque: device copy of one scene + queues */
