@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 SRC=actinon_b200/csrc
 OUT=actinon_b200/libactinon_b200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude"
+FLAGS="-std=c++17 -O3 -use_fast_math -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude"
 mkdir -p build
 pids=()
 $NVCC $FLAGS -c $SRC/acn_tracer.cu -o build/acn_tracer.o & pids+=($!)
