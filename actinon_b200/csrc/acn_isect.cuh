@@ -47,18 +47,26 @@ namespace acn {
 #define ACN_CSG_INLINE __forceinline__
 #endif
 
-template <typename R> struct CsgMem { R* t; unsigned short* iv; int stride; };     // iv = leaf id | variable << 8
-
-template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthreads )
+// per-thread scratch of a scene query in shared memory, [slot][thread]: the CSG events and the traversal stack
+template <typename R> struct CsgMem
 {
-    return ( size_t )( sizeof( R ) + 2 ) * CSG_E * nthreads;
+    R* t; unsigned short* iv;                   // CSG_E events: crossing, leaf id | variable << 8
+    int* sb; int* se;                           // per nesting level of compounds: where the walk of the parent list resumes, its end
+    int stride;
+};
+
+template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthreads, int levels )
+{
+    return ( size_t )( sizeof( R ) + 2 ) * CSG_E * nthreads + ( size_t )8 * levels * nthreads;
 }
 
-template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned char* base, int nthreads, int tid )
+template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned char* base, int nthreads, int tid, int levels )
 {
     CsgMem<R> m;
     m.t = reinterpret_cast<R*>( base ) + tid;
     m.iv = reinterpret_cast<unsigned short*>( base + sizeof( R ) * CSG_E * nthreads ) + tid;
+    int* stk = reinterpret_cast<int*>( base + ( sizeof( R ) + 2 ) * CSG_E * nthreads );
+    m.sb = stk + tid; m.se = stk + levels * nthreads + tid;
     m.stride = nthreads;
     return m;
 }
@@ -374,7 +382,6 @@ template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( cons
         const I4 rl = sv.link[ root ];
         const R far0 = r_min( t_far, best );                 // strict '<' between the roots: matter must beat the lights
         if( ( node_flags( rl ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + slack ) ) continue;
-        int sb[ COMPOUND_STACK ], se[ COMPOUND_STACK ];
         int sp = 0;
         int beg = rl.y, end = rl.y + rl.z;
         R min_a = inf;
@@ -393,7 +400,7 @@ template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( cons
                 if( ( node_flags( lk ) & F_ENV ) && !envelope_hits_before( rec.env, ray, hor ) ) continue;
                 if( node_kind( lk ) == K_COMPOUND )
                 {
-                    if( sp < COMPOUND_STACK ) { sb[ sp ] = beg; se[ sp ] = end; sp++; beg = lk.y; end = lk.y + lk.z; }
+                    cm.sb[ sp * cm.stride ] = beg; cm.se[ sp * cm.stride ] = end; sp++; beg = lk.y; end = lk.y + lk.z;     // depth checked at upload
                     continue;
                 }
                 V3<R> n;
@@ -409,7 +416,7 @@ template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( cons
                 else trans_commit( sv, ray, a, n, c, &min_a, &tl );
             }
             if( sp == 0 ) break;
-            sp--; beg = sb[ sp ]; end = se[ sp ];
+            sp--; beg = cm.sb[ sp * cm.stride ]; end = cm.se[ sp * cm.stride ];
             if( sp == 0 && want_trans ) { trans_commit( sv, ray, el_a, el_n, el_obj, &min_a, &tl ); el_a = inf; el_obj = -1; }
         }
         if( min_a < best ) { best = min_a; if( want_trans ) *trans = tl; }

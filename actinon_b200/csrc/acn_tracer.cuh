@@ -82,6 +82,7 @@ template <typename R> struct DParams
     R     max_path_length;
     R     eps_rel;                            // per-ray shell thickness = max( sv.eps, eps_rel * |origin|_inf ); 0: constant
     int   stage_bytes;                        // node table bytes staged into shared memory (0: none)
+    int   stk_levels;                         // levels of the traversal stack in shared memory (deepest compound nesting + 1)
     int   n_heavy;                            // envelopes of the expensive top-level objects (CSG, distance fields); -1: no split
     int   heavy[ 8 ];
     const u64* skipA;                         // LCG skip table: state after 2k steps = s*A[k] + C[k]
@@ -585,7 +586,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
     if( count == 0 || w.sc->overflow ) return;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks: no need to stage the scene
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     unsigned long long n_rays = 0;
@@ -626,7 +627,7 @@ k_rays( Wave<R> w, RayBuf<R> in )
     if( count == 0 || w.sc->overflow ) return;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const int lane = threadIdx.x & 31;
     unsigned long long* ring = ring_all[ threadIdx.x >> 5 ];
     int pend_head = 0, pend_n = 0;
@@ -742,7 +743,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     if( total == 0 || w.sc->overflow ) return;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= total ) return;     // more warps than chunks
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const unsigned long long n_blocks = ( total + 31 ) >> 5;
@@ -825,7 +826,7 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * ACN_CHUNK >= blk_hi - blk_lo ) return;   // more warps than chunks
     const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x );
+    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const int L = prm.n_lights;
@@ -1593,7 +1594,11 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     // shared-memory staging of the node table
     size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )fs->n_children * sizeof( CRec<R> ) + ( size_t )n_prog * sizeof( int );
     prm.stage_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
-    smem_bytes = prm.stage_bytes + ( int )csg_mem_bytes<R>( ACN_BLOCK );      // staged tables, then the CSG interval lists
+    {
+        const int dl = compound_depth( fs, fs->light_root, 0 ), dm = compound_depth( fs, fs->matter_root, 0 );
+        prm.stk_levels = ( dl > dm ? dl : dm ) + 1;
+    }
+    smem_bytes = prm.stage_bytes + ( int )csg_mem_bytes<R>( ACN_BLOCK, prm.stk_levels );      // staged tables, then the per-thread query scratch
     if( smem_bytes > 40 * 1024 )
     {
         ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
