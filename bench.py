@@ -350,6 +350,15 @@ def main():
             "kernel_launches_per_step": {class_names[i]: kernel_cnt[i] / args.steps for i in range(7)},
             "kernel_share_of_step": {class_names[i]: kernel_ms[i] / args.steps / prof_step_ms for i in range(7)},
             "kernel_timing": "CUDA-event pairs around every launch of the four tracing kernels in one extra untimed step"}
+    # DRAM traffic of the dominant kernel per launch: from the committed ncu capture (dram__bytes_read + write), not live
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        k = tr["kernels"].get(class_names[dom])
+        if k:
+            roof["traffic"] = k["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["source"] + f"; that launch took {k['launch_us']:.0f} us under ncu"
+    except Exception:
+        pass
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from tests.oracle_lib import Oracle
