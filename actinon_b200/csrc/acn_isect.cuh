@@ -195,6 +195,7 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
         unsigned long long vars = 0;
         int nv = 0, ne = 0;
         bool dropped = false;
+        R tmin0 = inf; int kmin0 = -1;              // smallest crossing appended so far (-1: unknown, scan)
         // ---- pass 1: classify the ray against every leaf.  The lanes of a warp that evaluate this object walk
         // the program in LOCKSTEP: a lane whose ray misses a sub-envelope does not jump ahead (it would then
         // execute other program words than its neighbours and serialise against them) but idles through the
@@ -247,20 +248,26 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
                 if( !__any_sync( __activemask(), pc + 1 >= skip_to ) ) { nv += w2 >> 16; pc = sub_end - 1; }
             }
             else { if( op == CSG_CLIP ) nv++; continue; }               // CLIP: events were taken at ENV; NEG / AND / OR: pass 2
-            #pragma unroll 1
-            for( int k = 0; k < c; k++ )
+            // append the (<= 2) crossings: beyond the horizon -> dropped; at or before t_floor -> swept in an earlier
+            // round, only toggles the variable; the smallest crossing of the round is tracked on the way
+            #pragma unroll
+            for( int k = 0; k < 2; k++ )
             {
                 const R t = k ? t1 : t0;
-                if( t > t_far ) continue;                                  // beyond the caller's horizon
-                if( t <= t_floor ) { s0 ^= 1; continue; }                  // swept in an earlier round
+                if( k >= c || t > t_far ) continue;
+                if( t <= t_floor ) { s0 ^= 1; continue; }
                 const unsigned short iv = ( unsigned short )( ( k ? id1 : id0 ) | ( var << 8 ) );
-                if( ne < CSG_E ) { cm.t[ ne * cm.stride ] = t; cm.iv[ ne * cm.stride ] = iv; ne++; }
+                if( ne < CSG_E )
+                {
+                    if( t < tmin0 ) { tmin0 = t; kmin0 = ne; }
+                    cm.t[ ne * cm.stride ] = t; cm.iv[ ne * cm.stride ] = iv; ne++;
+                }
                 else
                 {   // keep the CSG_E smallest
                     dropped = true;
                     int kmax = 0; R tmax = cm.t[ 0 ];
                     for( int q = 1; q < CSG_E; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq > tmax ) { tmax = tq; kmax = q; } }
-                    if( t < tmax ) { cm.t[ kmax * cm.stride ] = t; cm.iv[ kmax * cm.stride ] = iv; }
+                    if( t < tmax ) { cm.t[ kmax * cm.stride ] = t; cm.iv[ kmax * cm.stride ] = iv; kmin0 = -1; }
                 }
             }
             vars |= ( unsigned long long )s0 << var;
@@ -274,8 +281,9 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
             const int s2 = csg_state( sv, pr, vars );
             if( s >= 0 && s2 != s && id != CSG_VIRTUAL ) { hit = true; break; }
             s = s2;
-            int kmin = -1; R tmin = inf;
-            for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } }
+            int kmin = kmin0; R tmin = tmin0;
+            if( kmin < 0 ) { tmin = inf; for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } } }
+            kmin0 = -1;                             // only the first crossing is known in advance
             if( kmin < 0 ) break;
             const unsigned int iv = cm.iv[ kmin * cm.stride ];
             cm.t[ kmin * cm.stride ] = inf;
