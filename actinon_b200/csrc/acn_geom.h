@@ -37,16 +37,38 @@ enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
 enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5, CSG_RUN = 6, CSG_MEMBER = 7, CSG_MEMBER_NEG = 8 };   // word = op | arg << 4, see acn_isect.cuh
 enum { CSG_E = 16, CSG_VIRTUAL = 255, CSG_MAX_VARS = 48, CSG_TABLE_VARS = 12 };   // crossings kept per ray, id of envelope crossings, variable limits
 
-template <typename R> struct SceneView
+// A scene table: element i by value.  SH = false: a pointer (device global memory, or host memory in scene
+// construction).  SH = true: the table was staged into shared memory and is addressed by its 32-bit
+// shared-window byte address — the compiler keeps such bases in uniform registers and emits LDS, so the
+// seven tables cost the tracing kernels no vector registers (as generic 64-bit pointers they were spilled
+// to local memory at the 96-register cap and re-read before every table access).
+template <typename T, bool SH> struct Tab
 {
-    const R4<R>* env;
-    const I4*    link;
-    const R4<R>* geo;
-    const int*   children;  // child node indices of all compounds (host / march)
-    const CRec<R>* crec;    // the same lists as packed records (device traversal)
-    const int*   prog;      // postfix CSG programs (interval evaluator), see acn_isect.cuh: csg_eval
-    const I4*    prog_ref;  // per node: program start, length (0: none -> reference march), truth table offset (-1: none), variables
-    const int*   parent;    // per node: CSG parent (-1 at the top of an object)
+    const T* p;
+    ACN_HD T operator[]( int i ) const { return p[ i ]; }
+    ACN_HD Tab& operator=( const T* q ) { p = q; return *this; }
+};
+#if defined(__CUDACC__)
+template <typename T> struct Tab<T, true>
+{
+    unsigned int a;
+    __device__ __forceinline__ T operator[]( int i ) const
+    {
+        return *reinterpret_cast<const T*>( __cvta_shared_to_generic( a + ( unsigned int )i * ( unsigned int )sizeof( T ) ) );
+    }
+};
+#endif
+
+template <typename R, bool SH = false> struct SceneView
+{
+    Tab<R4<R>, SH>   env;
+    Tab<I4, SH>      link;
+    Tab<R4<R>, SH>   geo;
+    Tab<int, SH>     children;  // child node indices of all compounds (host / march)
+    Tab<CRec<R>, SH> crec;      // the same lists as packed records (device traversal)
+    Tab<int, SH>     prog;      // postfix CSG programs (interval evaluator), see acn_isect.cuh: csg_eval
+    Tab<I4, SH>      prog_ref;  // per node: program start, length (0: none -> reference march), truth table offset (-1: none), variables
+    Tab<int, SH>     parent;    // per node: CSG parent (-1 at the top of an object)
     R   eps;            // shell thickness (f3_eps, vectors.h:33)
     int light_root;
     int matter_root;
@@ -125,7 +147,7 @@ template <typename R> ACN_HD R dist_fn( int kind, R ex_radius, V3<R> p )
     return r_sqrt( x * x + y * y + p.z * p.z ) - ex_radius;
 }
 
-template <typename R> ACN_HD M3<R> node_rax( const SceneView<R>& sv, int n )
+template <typename R, bool SH> ACN_HD M3<R> node_rax( const SceneView<R, SH>& sv, int n )
 {
     M3<R> m;
     m.x = xyz( sv.geo[ n * GEO_STRIDE + 1 ] );
@@ -136,7 +158,7 @@ template <typename R> ACN_HD M3<R> node_rax( const SceneView<R>& sv, int n )
 
 // distance-field objects (objects.c:903-959): sphere tracing in the scaled object frame.  Kept out of line:
 // it is the heaviest and most divergent primitive and must not bloat every intersection site.
-template <typename R> ACN_NOINLINE R dist_hit( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, V3<R>* nor )
+template <typename R, bool SH> ACN_HD R dist_hit_body( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, V3<R>* nor )
 {
     const R inf = Num<R>::inf();
     const R eps = sv.eps;
@@ -216,11 +238,31 @@ template <typename R> ACN_NOINLINE R dist_hit( const SceneView<R>& sv, int kind,
     return inf;
 }
 
+// Out-of-line entry.  Everything crosses the call BY VALUE: a reference parameter would take the address of the
+// caller's ray / scene view / normal, which pins them to local memory for the whole kernel — the hot loops then
+// re-read the ray from the stack before every envelope test (seen as LDL in the SASS of every tracing kernel).
+template <typename R> struct HitN { R a; V3<R> n; };
+
+template <typename R, bool SH> ACN_NOINLINE HitN<R> dist_hit_ool( SceneView<R, SH> sv, int kind, int n, Ray<R> ray, bool want_nor )
+{
+    HitN<R> h;
+    h.n = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    h.a = dist_hit_body( sv, kind, n, ray, want_nor ? &h.n : nullptr );
+    return h;
+}
+
+template <typename R, bool SH> ACN_HD R dist_hit( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, V3<R>* nor )
+{
+    const HitN<R> h = dist_hit_ool( sv, kind, n, ray, nor != nullptr );
+    if( nor ) *nor = h.n;
+    return h.a;
+}
+
 // ---------------------------------------------------------------------------------------------
 // primitives: fp_ray_hit of plane / sphere / squaroid / distance objects
 // (gmath.h:38-45, objects.c:529-537,649-657,778-821,903-959).  No envelope test, no roughness.
 // ---------------------------------------------------------------------------------------------
-template <typename R> ACN_HD R prim_hit( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, V3<R>* nor )
+template <typename R, bool SH> ACN_HD R prim_hit( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, V3<R>* nor )
 {
     const R inf = Num<R>::inf();
     const R eps = sv.eps;
@@ -289,7 +331,7 @@ template <typename R> ACN_HD R prim_hit( const SceneView<R>& sv, int kind, int n
 }
 
 // fp_side of the primitives (gmath.h:52-55,93-97, objects.c:823-827,961-966)
-template <typename R> ACN_HD int prim_side( const SceneView<R>& sv, int kind, int n, V3<R> x )
+template <typename R, bool SH> ACN_HD int prim_side( const SceneView<R, SH>& sv, int kind, int n, V3<R> x )
 {
     const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
     const V3<R> pos = xyz( g0 );
@@ -310,26 +352,29 @@ template <typename R> ACN_HD int prim_side( const SceneView<R>& sv, int kind, in
 // obj_ray_hit / obj_side (objects.c:261-284,365-370) over the whole object algebra.
 // CSG nodes recurse (device stack); the recursion depth is the CSG nesting depth.
 // ---------------------------------------------------------------------------------------------
-template <typename R> ACN_HDN int obj_side( const SceneView<R>& sv, int n, V3<R> x );
-template <typename R> ACN_HDN R   obj_ray_hit( const SceneView<R>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx );
+template <typename R, bool SH> ACN_HDN int obj_side( const SceneView<R, SH>& sv, int n, V3<R> x );
+template <typename R, bool SH> ACN_HDN R   obj_ray_hit( const SceneView<R, SH>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx );
 
-// roughness perturbation of the normal (objects.c:266-282)
-template <typename R> ACN_NOINLINE void roughen( const SceneView<R>& sv, int n, const Ray<R>& ray, R a, V3<R>* nor, HitCtx ctx )
+// roughness perturbation of the normal (objects.c:266-282); out of line, arguments and result by value (see dist_hit_ool)
+template <typename R> ACN_NOINLINE V3<R> roughen_ool( R rough, int seed_mode, V3<R> hit_pos, V3<R> v, u64 key, int n )
 {
-    R rough = sv.geo[ n * GEO_STRIDE + 4 ].x;
-    u64 rv = sv.seed_mode == SEED_POSITION_HASH ? random_seed( madd( ray.p, ray.d, a ), ( u64 )1246 )
-                                                : mix64( mix64( ctx.key, KEY_ROUGH ), ( u64 )n );
-    V3<R> v = *nor;
+    u64 rv = seed_mode == SEED_POSITION_HASH ? random_seed( hit_pos, ( u64 )1246 )
+                                             : mix64( mix64( key, KEY_ROUGH ), ( u64 )n );
     R f;
     f = rnd0<R>( &rv ) * R( 0.99 ); v.x += rough * r_log( ( R( 1 ) - f ) / ( R( 1 ) + f ) );
     f = rnd0<R>( &rv ) * R( 0.99 ); v.y += rough * r_log( ( R( 1 ) - f ) / ( R( 1 ) + f ) );
     f = rnd0<R>( &rv ) * R( 0.99 ); v.z += rough * r_log( ( R( 1 ) - f ) / ( R( 1 ) + f ) );
-    *nor = unit( v );
+    return unit( v );
+}
+
+template <typename R, bool SH> ACN_HD void roughen( const SceneView<R, SH>& sv, int n, const Ray<R>& ray, R a, V3<R>* nor, HitCtx ctx )
+{
+    *nor = roughen_ool<R>( sv.geo[ n * GEO_STRIDE + 4 ].x, sv.seed_mode, madd( ray.p, ray.d, a ), *nor, ctx.key, n );
 }
 
 // A&B (want = -1) and A|B (want = +1): first boundary point of either child lying on the wanted
 // side of the other; alternating march with 2*eps steps (objects.c:1052-1094,1209-1251)
-template <typename R> ACN_HDN R pair_hit( const SceneView<R>& sv, int o1, int o2, int want, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+template <typename R, bool SH> ACN_HDN R pair_hit( const SceneView<R, SH>& sv, int o1, int o2, int want, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     const R inf = Num<R>::inf();
     V3<R> n1, n2;
@@ -367,7 +412,7 @@ template <typename R> ACN_HDN R pair_hit( const SceneView<R>& sv, int o1, int o2
 
 
 // fp_ray_hit dispatch without the own-envelope test and without roughness
-template <typename R> ACN_HD R shape_hit( const SceneView<R>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+template <typename R, bool SH> ACN_HD R shape_hit( const SceneView<R, SH>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     const int kind = node_kind( lk );
     if( kind <= K_DIST_TORUS ) return prim_hit( sv, kind, n, ray, nor );
@@ -402,14 +447,14 @@ template <typename R> ACN_HD R shape_hit( const SceneView<R>& sv, const I4& lk, 
 }
 
 // obj_ray_hit body after the envelope test: shape + roughness
-template <typename R> ACN_HD R obj_hit_noenv( const SceneView<R>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+template <typename R, bool SH> ACN_HD R obj_hit_noenv( const SceneView<R, SH>& sv, const I4& lk, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     R a = shape_hit( sv, lk, n, ray, nor, ctx );
     if( nor && ( node_flags( lk ) & F_ROUGH ) && a < Num<R>::inf() ) roughen( sv, n, ray, a, nor, ctx );
     return a;
 }
 
-template <typename R> ACN_HDN R obj_ray_hit( const SceneView<R>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+template <typename R, bool SH> ACN_HDN R obj_ray_hit( const SceneView<R, SH>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     const I4 lk = sv.link[ n ];
     if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ n ], ray ) ) return Num<R>::inf();
@@ -417,7 +462,7 @@ template <typename R> ACN_HDN R obj_ray_hit( const SceneView<R>& sv, int n, cons
 }
 
 // obj_side (objects.c:365-370): "outside" whenever outside the own envelope — also for negations
-template <typename R> ACN_HDN int obj_side( const SceneView<R>& sv, int n, V3<R> x )
+template <typename R, bool SH> ACN_HDN int obj_side( const SceneView<R, SH>& sv, int n, V3<R> x )
 {
     const I4 lk = sv.link[ n ];
     if( node_flags( lk ) & F_ENV )
@@ -443,7 +488,7 @@ template <typename R> ACN_HDN int obj_side( const SceneView<R>& sv, int n, V3<R>
 // sphere objects.c:619-637; plane :520-527; pairs :1035-1044,1192-1201 (envelope_s_fov :70-88)
 // returns false for shapes without a fov function (rejected at upload for lights)
 // ---------------------------------------------------------------------------------------------
-template <typename R> ACN_HD bool obj_fov( const SceneView<R>& sv, int n, V3<R> pos, V3<R>* axis, R* cos_rs )
+template <typename R, bool SH> ACN_HD bool obj_fov( const SceneView<R, SH>& sv, int n, V3<R> pos, V3<R>* axis, R* cos_rs )
 {
     const I4 lk = sv.link[ n ];
     const int kind = node_kind( lk );
@@ -476,7 +521,7 @@ template <typename R> ACN_HD bool obj_fov( const SceneView<R>& sv, int n, V3<R> 
 }
 
 // obj_projection for the chess texture (objects.c:514-518,602-617,892-895)
-template <typename R> ACN_HD void obj_projection( const SceneView<R>& sv, int n, V3<R> pos, R* u, R* v )
+template <typename R, bool SH> ACN_HD void obj_projection( const SceneView<R, SH>& sv, int n, V3<R> pos, R* u, R* v )
 {
     const int kind = node_kind( sv.link[ n ] );
     const V3<R> c = xyz( sv.geo[ n * GEO_STRIDE ] );

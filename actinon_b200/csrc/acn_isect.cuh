@@ -48,10 +48,20 @@ namespace acn {
 #endif
 
 // per-thread scratch of a scene query in shared memory, [slot][thread]: the CSG events and the traversal stack
+// element i of an array in shared memory, addressed by its 32-bit shared-window byte address (LDS/STS, no 64-bit pointer registers)
+template <typename T> struct SPtr
+{
+    unsigned int a;
+    __device__ __forceinline__ T& operator[]( int i ) const
+    {
+        return *reinterpret_cast<T*>( __cvta_shared_to_generic( a + ( unsigned int )i * ( unsigned int )sizeof( T ) ) );
+    }
+};
+
 template <typename R> struct CsgMem
 {
-    R* t; unsigned short* iv;                   // CSG_E events: crossing, leaf id | variable << 8
-    int* sb; int* se;                           // per nesting level of compounds: where the walk of the parent list resumes, its end
+    SPtr<R> t; SPtr<unsigned short> iv;         // CSG_E events: crossing, leaf id | variable << 8
+    SPtr<int> sb, se;                           // per nesting level of compounds: where the walk of the parent list resumes, its end
     int stride;
 };
 
@@ -63,10 +73,11 @@ template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthre
 template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned char* base, int nthreads, int tid, int levels )
 {
     CsgMem<R> m;
-    m.t = reinterpret_cast<R*>( base ) + tid;
-    m.iv = reinterpret_cast<unsigned short*>( base + sizeof( R ) * CSG_E * nthreads ) + tid;
-    int* stk = reinterpret_cast<int*>( base + ( sizeof( R ) + 2 ) * CSG_E * nthreads );
-    m.sb = stk + tid; m.se = stk + levels * nthreads + tid;
+    const unsigned int b = ( unsigned int )__cvta_generic_to_shared( base );
+    m.t.a  = b + ( unsigned int )( tid * sizeof( R ) );
+    m.iv.a = b + ( unsigned int )( sizeof( R ) * CSG_E * nthreads + tid * 2 );
+    const unsigned int stk = b + ( unsigned int )( ( sizeof( R ) + 2 ) * CSG_E * nthreads );
+    m.sb.a = stk + ( unsigned int )( tid * 4 ); m.se.a = stk + ( unsigned int )( ( levels * nthreads + tid ) * 4 );
     m.stride = nthreads;
     return m;
 }
@@ -92,7 +103,7 @@ template <typename R> __device__ __forceinline__ int sphere_events( V3<R> c, R r
     return 0;
 }
 
-template <typename R> __device__ __forceinline__ int leaf_events( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, int* s0, R* t0, R* t1 )
+template <typename R, bool SH> __device__ __forceinline__ int leaf_events( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, int* s0, R* t0, R* t1 )
 {
     const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
     const V3<R> pos = xyz( g0 );
@@ -134,7 +145,7 @@ template <typename R> __device__ __forceinline__ int leaf_events( const SceneVie
 }
 
 // outward normal of a leaf at ray parameter t (the unshortened crossing), as its fp_ray_hit reports it
-template <typename R> __device__ __forceinline__ V3<R> leaf_normal( const SceneView<R>& sv, int kind, int n, const Ray<R>& ray, R t )
+template <typename R, bool SH> __device__ __forceinline__ V3<R> leaf_normal( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, R t )
 {
     const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
     const V3<R> pos = xyz( g0 );
@@ -148,7 +159,7 @@ template <typename R> __device__ __forceinline__ V3<R> leaf_normal( const SceneV
 }
 
 // state of the solid for a variable assignment: truth table, or the postfix program on a bit stack
-template <typename R> __device__ __forceinline__ int csg_state( const SceneView<R>& sv, const I4& pr, unsigned long long vars )
+template <typename R, bool SH> __device__ __forceinline__ int csg_state( const SceneView<R, SH>& sv, const I4& pr, unsigned long long vars )
 {
     if( pr.z >= 0 ) return ( sv.prog[ pr.z + ( int )( vars >> 5 ) ] >> ( ( unsigned int )vars & 31u ) ) & 1;
     unsigned int stk = 0;
@@ -180,7 +191,7 @@ template <typename R> __device__ __forceinline__ void member_interval( int s0, i
 // returns the hit parameter or +inf for a miss.  A ray with more than CSG_E crossings is swept in rounds:
 // each round keeps the CSG_E smallest crossings beyond t_floor; crossings at or before t_floor only
 // toggle their variable (they were swept in an earlier round).
-template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
+template <typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R, SH>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
                                                              const CsgMem<R>& cm, const R t_far )
 {
     // t_far: the caller's horizon (+ slack).  Crossings beyond it cannot become the reported hit and the state of
@@ -319,14 +330,14 @@ template <typename R> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R>& 
 // recursive march, out of line.  Only the MARCH instantiation of the kernels contains it — the mutually
 // recursive obj_ray_hit / pair_hit / obj_side want ~250 registers, which would otherwise set the
 // register count (and the occupancy) of every tracing kernel.
-template <typename R> __device__ __noinline__ R march_hit( const SceneView<R>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
+template <typename R, bool SH> __device__ __noinline__ R march_hit( const SceneView<R, SH>& sv, int n, const Ray<R>& ray, V3<R>* nor, HitCtx ctx )
 {
     const I4 lk = sv.link[ n ];
     return shape_hit( sv, lk, n, ray, nor, ctx );
 }
 
 // obj_ray_hit after the envelope test (objects.c:261-284): fp_ray_hit + roughness
-template <typename R, bool MARCH> __device__ __forceinline__ R elem_hit( const SceneView<R>& sv, const I4& lk, int c, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
+template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R elem_hit( const SceneView<R, SH>& sv, const I4& lk, int c, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
                                                                          const CsgMem<R>& cm, const R t_far )
 {
     const int kind = node_kind( lk );
@@ -354,7 +365,7 @@ template <typename R, bool MARCH> __device__ __forceinline__ R elem_hit( const S
 // ---------------------------------------------------------------------------------------------
 enum { Q_LIGHT = 1, Q_MATTER = 2, Q_TRANS = 4 };
 
-template <typename R> __device__ __forceinline__ void trans_commit( const SceneView<R>& sv, const Ray<R>& ray, R a, V3<R> nor, int obj, R* min_a, Trans<R>* tl )
+template <typename R, bool SH> __device__ __forceinline__ void trans_commit( const SceneView<R, SH>& sv, const Ray<R>& ray, R a, V3<R> nor, int obj, R* min_a, Trans<R>* tl )
 {
     if( !( a < Num<R>::inf() ) ) return;
     if( a < *min_a - sv.eps )
@@ -371,7 +382,7 @@ template <typename R> __device__ __forceinline__ void trans_commit( const SceneV
     }
 }
 
-template <typename R, bool MARCH> __device__ __forceinline__ R scene_query( const SceneView<R>& sv, const Ray<R>& ray, const int flags, const R t_far,
+template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,
                                                                             Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
 {
     // t_far: hits at a >= t_far are of no interest to the caller (the shadow test's light distance, a path

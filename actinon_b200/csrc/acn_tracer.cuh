@@ -255,35 +255,48 @@ template <typename R> __device__ __forceinline__ void add_sample( const Wave<R>&
     atomic_add_r( a + 2, c.z );
 }
 
-// stage the node table into shared memory when it fits (C1/C2/C4: a few KB); big scenes stay in L2
-template <typename R> __device__ __forceinline__ SceneView<R> stage_scene( const DParams<R>& prm, unsigned char* smem )
+// the node table of the kernel instantiation: SH = true copies it into shared memory (C1/C2/C4: a few KB; the host
+// launches these instantiations only when it fits), SH = false reads it where it lies (many_spheres: 1.3 MB in L2)
+template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> stage_scene( const DParams<R>& prm, unsigned char* smem )
 {
-    SceneView<R> sv = prm.sv;
-    if( prm.stage_bytes <= 0 ) return sv;
-    const int n = prm.n_nodes;
-    R4<R>* s_env  = reinterpret_cast<R4<R>*>( smem );
-    R4<R>* s_geo  = s_env + n;
-    I4*    s_link = reinterpret_cast<I4*>( s_geo + n * GEO_STRIDE );
-    I4*    s_pref = s_link + n;
-    CRec<R>* s_crec = reinterpret_cast<CRec<R>*>( s_pref + n );
-    int*   s_par  = reinterpret_cast<int*>( s_crec + prm.n_children );
-    int*   s_prog = s_par + n;
-    for( int i = threadIdx.x; i < n; i += blockDim.x )
+    if constexpr( !SH ) return prm.sv;
+    else
     {
-        s_env[ i ] = prm.sv.env[ i ]; s_link[ i ] = prm.sv.link[ i ];
-        s_pref[ i ] = prm.sv.prog_ref[ i ]; s_par[ i ] = prm.sv.parent[ i ];
+        const int n = prm.n_nodes;
+        R4<R>* s_env  = reinterpret_cast<R4<R>*>( smem );
+        R4<R>* s_geo  = s_env + n;
+        I4*    s_link = reinterpret_cast<I4*>( s_geo + n * GEO_STRIDE );
+        I4*    s_pref = s_link + n;
+        CRec<R>* s_crec = reinterpret_cast<CRec<R>*>( s_pref + n );
+        int*   s_par  = reinterpret_cast<int*>( s_crec + prm.n_children );
+        int*   s_prog = s_par + n;
+        for( int i = threadIdx.x; i < n; i += blockDim.x )
+        {
+            s_env[ i ] = prm.sv.env[ i ]; s_link[ i ] = prm.sv.link[ i ];
+            s_pref[ i ] = prm.sv.prog_ref[ i ]; s_par[ i ] = prm.sv.parent[ i ];
+        }
+        for( int i = threadIdx.x; i < n * GEO_STRIDE; i += blockDim.x ) s_geo[ i ] = prm.sv.geo[ i ];
+        for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_crec[ i ] = prm.sv.crec[ i ];
+        for( int i = threadIdx.x; i < prm.n_prog; i += blockDim.x ) s_prog[ i ] = prm.sv.prog[ i ];
+        __syncthreads();
+        SceneView<R, true> sv;
+        const unsigned int base = ( unsigned int )__cvta_generic_to_shared( smem );
+        const unsigned int un = ( unsigned int )n;
+        sv.env.a      = base;
+        sv.geo.a      = sv.env.a + un * ( unsigned int )sizeof( R4<R> );
+        sv.link.a     = sv.geo.a + un * GEO_STRIDE * ( unsigned int )sizeof( R4<R> );
+        sv.prog_ref.a = sv.link.a + un * ( unsigned int )sizeof( I4 );
+        sv.crec.a     = sv.prog_ref.a + un * ( unsigned int )sizeof( I4 );
+        sv.parent.a   = sv.crec.a + ( unsigned int )prm.n_children * ( unsigned int )sizeof( CRec<R> );
+        sv.prog.a     = sv.parent.a + un * ( unsigned int )sizeof( int );
+        sv.children.a = 0;                       // march / host only
+        sv.eps = prm.sv.eps; sv.light_root = prm.sv.light_root; sv.matter_root = prm.sv.matter_root; sv.seed_mode = prm.sv.seed_mode;
+        return sv;
     }
-    for( int i = threadIdx.x; i < n * GEO_STRIDE; i += blockDim.x ) s_geo[ i ] = prm.sv.geo[ i ];
-    for( int i = threadIdx.x; i < prm.n_children; i += blockDim.x ) s_crec[ i ] = prm.sv.crec[ i ];
-    for( int i = threadIdx.x; i < prm.n_prog; i += blockDim.x ) s_prog[ i ] = prm.sv.prog[ i ];
-    __syncthreads();
-    sv.env = s_env; sv.geo = s_geo; sv.link = s_link; sv.crec = s_crec;
-    sv.prog_ref = s_pref; sv.parent = s_par; sv.prog = s_prog;
-    return sv;
 }
 
 // obj_color (objects.c:411-422) with txm_plain / txm_chess (textures.c:99-102,142-148)
-template <typename R> __device__ __forceinline__ V3<R> obj_color( const DParams<R>& prm, const SceneView<R>& sv0, int node, V3<R> pos )
+template <typename R, bool SH> __device__ __forceinline__ V3<R> obj_color( const DParams<R>& prm, const SceneView<R, SH>& sv0, int node, V3<R> pos )
 {
     const DMat<R>& m = prm.mats[ sv0.link[ node ].w ];
     if( m.tex_kind == ACN_TEX_NONE )  return v3<R>( m.color[ 0 ], m.color[ 1 ], m.color[ 2 ] );
@@ -298,9 +311,9 @@ template <typename R> __device__ __forceinline__ V3<R> obj_color( const DParams<
 // The reference's shell thickness is an absolute 1e-6 in FP64.  In FP32 a hit distance carries an error
 // of a few ulp of the ray origin's magnitude, so the product path scales the shell with the origin
 // (16 ulp) and never goes below the reference's 1e-6; see DESIGN.md "eps".
-template <typename R> __device__ __forceinline__ SceneView<R> ray_view( const DParams<R>& prm, const SceneView<R>& sv0, V3<R> o )
+template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> ray_view( const DParams<R>& prm, const SceneView<R, SH>& sv0, V3<R> o )
 {
-    SceneView<R> sv = sv0;
+    SceneView<R, SH> sv = sv0;
     if( prm.eps_rel > R( 0 ) ) sv.eps = r_max( sv.eps, prm.eps_rel * r_max( r_max( r_abs( o.x ), r_abs( o.y ) ), r_abs( o.z ) ) );
     return sv;
 }
@@ -328,7 +341,7 @@ template <typename R> __device__ __forceinline__ void emit_ray( const Wave<R>& w
 // ---------------------------------------------------------------------------------------------
 // scene_s_lum (scene.c:420-667) for one hit: emits child rays and at most one diffuse task.
 // ---------------------------------------------------------------------------------------------
-template <typename R> __device__ void shade_hit( const Wave<R>& w, const SceneView<R>& sv0, const Ray<R>& ray, R a, R hit_eps, const Trans<R>& tr,
+template <typename R, bool SH> __device__ void shade_hit( const Wave<R>& w, const SceneView<R, SH>& sv0, const Ray<R>& ray, R a, R hit_eps, const Trans<R>& tr,
                                                  int depth, R I, V3<R> tp, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
@@ -426,13 +439,13 @@ template <typename R> __device__ void shade_hit( const Wave<R>& w, const SceneVi
 //   cls != RC_PATH: scene_s_trans_hit (lights + matter)
 //   cls == RC_PATH: matter only; "leaves" = nothing closer than max_path_length        (scene.c:606-616)
 //   probe: the hit's shading would return 0 (depth 0 or I < Imin) — only "anything hit?" matters
-template <typename R, bool MARCH> __device__ __forceinline__ bool trace_ray( const Wave<R>& w, const SceneView<R>& sv0, const CsgMem<R>& cm, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
+template <typename R, bool MARCH, bool SH> __device__ __forceinline__ bool trace_ray( const Wave<R>& w, const SceneView<R, SH>& sv0, const CsgMem<R>& cm, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
                                                                 bool probe, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
     const R inf = Num<R>::inf();
     HitCtx ctx; ctx.key = key;
-    const SceneView<R> sv = ray_view( prm, sv0, ray.p );
+    const SceneView<R, SH> sv = ray_view( prm, sv0, ray.p );
     const bool path = cls == RC_PATH;
     // probe: "anything at all?" (path children: "anything closer than max_path_length?")
     const int flags = ( path ? Q_MATTER : ( Q_LIGHT | Q_MATTER ) ) | ( probe ? 0 : Q_TRANS );
@@ -465,7 +478,7 @@ template <typename R, bool MARCH> __device__ __forceinline__ bool trace_ray( con
 // into a small ring in shared memory and traces them only when a full group of 32 has collected (or the
 // input is exhausted): cheap groups run without them, expensive groups run dense.
 #define ACN_PEND 64
-template <typename R> __device__ __forceinline__ bool ray_is_heavy( const DParams<R>& prm, const SceneView<R>& sv0, const Ray<R>& ray )
+template <typename R, bool SH> __device__ __forceinline__ bool ray_is_heavy( const DParams<R>& prm, const SceneView<R, SH>& sv0, const Ray<R>& ray )
 {
     bool h = false;
     for( int k = 0; k < prm.n_heavy; k++ ) h = h || envelope_hits( sv0.env[ prm.heavy[ k ] ], ray );
@@ -482,14 +495,14 @@ __device__ __forceinline__ void pend_push( unsigned long long* ring, int head, i
 }
 
 // obj_ray_hit of a light for a direct sample (scene.c:564): spheres in line, any other shape out of line
-template <typename R, bool MARCH> __device__ __noinline__ R light_hit_cold( const SceneView<R>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
+template <typename R, bool MARCH, bool SH> __device__ __noinline__ R light_hit_cold( SceneView<R, SH> sv, int node, Ray<R> ray, HitCtx ctx, CsgMem<R> cm )
 {
     const I4 lk = sv.link[ node ];
     if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ node ], ray ) ) return Num<R>::inf();
-    return elem_hit<R, MARCH>( sv, lk, node, ray, nullptr, ctx, cm, Num<R>::inf() );
+    return elem_hit<R, MARCH>( sv, lk, node, ray, ( V3<R>* )nullptr, ctx, cm, Num<R>::inf() );
 }
 
-template <typename R, bool MARCH> __device__ __forceinline__ R light_hit( const SceneView<R>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
+template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R light_hit( const SceneView<R, SH>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
 {
     const I4 lk = sv.link[ node ];
     if( node_kind( lk ) == K_SPHERE )
@@ -578,15 +591,15 @@ k_pop( const Sched* __restrict__ s, RayBuf<R> stack, RayBuf<R> cur )
 }
 
 // camera rays (scene.c:976-990) fused with their first trace + shade
-template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK )
+template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK )
 k_primary( Wave<R> w, const double* __restrict__ xy )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     const unsigned long long first = w.sc->prim_first, count = w.sc->prim_count;
     if( count == 0 || w.sc->overflow ) return;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks: no need to stage the scene
-    const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     unsigned long long n_rays = 0;
@@ -618,7 +631,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
 }
 
 // explicit rays popped from the ray stack
-template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_RAYS )
+template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_RAYS )
 k_rays( Wave<R> w, RayBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -626,8 +639,8 @@ k_rays( Wave<R> w, RayBuf<R> in )
     const unsigned long long count = w.sc->ray_take;
     if( count == 0 || w.sc->overflow ) return;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks
-    const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const int lane = threadIdx.x & 31;
     unsigned long long* ring = ring_all[ threadIdx.x >> 5 ];
     int pend_head = 0, pend_n = 0;
@@ -687,7 +700,7 @@ k_rays( Wave<R> w, RayBuf<R> in )
 }
 
 // scene_s_lum (scene.c:420-667) over the hits of the iteration: emits child rays and diffuse tasks
-template <typename R> __global__ void __launch_bounds__( ACN_BLOCK )
+template <typename R, bool SH> __global__ void __launch_bounds__( ACN_BLOCK )
 k_shade( Wave<R> w, HitBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -695,7 +708,7 @@ k_shade( Wave<R> w, HitBuf<R> in )
     if( count > w.hits_cap ) count = w.hits_cap;
     if( count == 0 || w.sc->overflow ) return;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks
-    const SceneView<R> sv0 = stage_scene( w.prm, smem );
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
     const int lane = threadIdx.x & 31;
     for( ;; )
     {
@@ -734,7 +747,7 @@ __device__ __forceinline__ ListWindow list_window( const u64* __restrict__ cum, 
 
 // direct lighting (scene.c:542-581): one lane per (task, light, sample); the shadow rays exist only
 // as (entry, child index) and are regenerated from the task with an O(1) LCG skip-ahead
-template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_DIRECT )
+template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_DIRECT )
 k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
           const unsigned int* __restrict__ dl_dir )
 {
@@ -742,8 +755,8 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
     if( total == 0 || w.sc->overflow ) return;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= total ) return;     // more warps than chunks
-    const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const unsigned long long n_blocks = ( total + 31 ) >> 5;
@@ -773,7 +786,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
                 const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
                 const DLight<R>& lg = prm.lights[ li ];
 
-                const SceneView<R> sv = ray_view( prm, sv0, pos );
+                const SceneView<R, SH> sv = ray_view( prm, sv0, pos );
                 V3<R> axis; R cos_rs;
                 obj_fov( sv, lg.node, pos, &axis, &cos_rs );
                 const Basis<R> bs = basis_con_z( axis );
@@ -816,7 +829,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
 
 // indirect rays (scene.c:584-621): one lane per (task, path sample); the child ray is generated,
 // traced and shaded in place, never stored.
-template <typename R, bool MARCH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_PATH )
+template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_PATH )
 k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -825,8 +838,8 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     if( blk_hi <= blk_lo || w.sc->overflow ) return;
     const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * ACN_CHUNK >= blk_hi - blk_lo ) return;   // more warps than chunks
-    const SceneView<R> sv0 = stage_scene( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + w.prm.stage_bytes, ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const int L = prm.n_lights;
@@ -1117,6 +1130,12 @@ template <typename R> struct Tracer : TracerBase
     void ( *kp_rays )( Wave<R>, RayBuf<R> ) = nullptr;
     void ( *kp_path )( Wave<R>, TaskBuf<R>, const unsigned int* ) = nullptr;
     void ( *kp_direct )( Wave<R>, TaskBuf<R>, const u64*, const unsigned int*, const unsigned int* ) = nullptr;
+    void ( *kp_shade )( Wave<R>, HitBuf<R> ) = nullptr;
+    template <bool MARCH, bool SH> void select_kernels()
+    {
+        kp_primary = k_primary<R, MARCH, SH>; kp_rays = k_rays<R, MARCH, SH>; kp_path = k_path<R, MARCH, SH>;
+        kp_direct = k_direct<R, MARCH, SH>; kp_shade = k_shade<R, SH>;
+    }
 
     ~Tracer() override
     {
@@ -1450,14 +1469,6 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             }
         };
         walk( fs->light_root ); walk( fs->matter_root );
-        if( march )
-        {
-            kp_primary = k_primary<R, true>; kp_rays = k_rays<R, true>; kp_path = k_path<R, true>; kp_direct = k_direct<R, true>;
-        }
-        else
-        {
-            kp_primary = k_primary<R, false>; kp_rays = k_rays<R, false>; kp_path = k_path<R, false>; kp_direct = k_direct<R, false>;
-        }
     }
 
     // ---- materials
@@ -1593,7 +1604,14 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
 
     // shared-memory staging of the node table
     size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )fs->n_children * sizeof( CRec<R> ) + ( size_t )n_prog * sizeof( int );
-    prm.stage_bytes = table <= 96 * 1024 ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
+    // (f32 only: the FP64 validation instantiations read the tables from global memory)
+    prm.stage_bytes = ( sizeof( R ) == 4 && table <= 96 * 1024 && !getenv( "ACN_NO_STAGING" ) ) ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
+    if constexpr( sizeof( R ) == 4 )
+    {
+        if( prm.stage_bytes > 0 ) { if( march ) select_kernels<true, true>(); else select_kernels<false, true>(); }
+        else                      { if( march ) select_kernels<true, false>(); else select_kernels<false, false>(); }
+    }
+    else { if( march ) select_kernels<true, false>(); else select_kernels<false, false>(); }
     {
         const int dl = compound_depth( fs, fs->light_root, 0 ), dm = compound_depth( fs, fs->matter_root, 0 );
         prm.stk_levels = ( dl > dm ? dl : dm ) + 1;
@@ -1605,7 +1623,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
         ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
         ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_path, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
-        ACN_CUDA( cudaFuncSetAttribute( k_shade<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
+        ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
     }
 
     // device stack for the CSG recursion (obj_ray_hit <-> pair_hit <-> obj_side)
@@ -1657,7 +1675,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_rays, ACN_BLOCK, smem_bytes ) );    grid_trace[ 1 ] = sms * ( b > 0 ? b : 1 );
         ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_path, ACN_BLOCK, smem_bytes ) );    grid_trace[ 2 ] = sms * ( b > 0 ? b : 1 );
         ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_direct, ACN_BLOCK, smem_bytes ) );  grid_trace[ 3 ] = sms * ( b > 0 ? b : 1 );
-        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, k_shade<R>, ACN_BLOCK, smem_bytes ) );   grid_trace[ 4 ] = sms * ( b > 0 ? b : 1 );
+        ACN_CUDA( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &b, ( const void* )kp_shade, ACN_BLOCK, smem_bytes ) );   grid_trace[ 4 ] = sms * ( b > 0 ? b : 1 );
         grid_util = sms * 4;
     }
     return ACN_OK;
@@ -1722,7 +1740,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
             launches += 3;
         }
         kp_begin( 4 );
-        k_shade<R><<< grid_trace[ 4 ], ACN_BLOCK, smem_bytes, st >>>( w, hit_q );
+        kp_shade<<< grid_trace[ 4 ], ACN_BLOCK, smem_bytes, st >>>( w, hit_q );
         kp_end( 4 );
         kp_begin( 5 );
         k_index<R><<< grid_util, 256, 0, st >>>( d_sc, task_new, task_new_cap, prm.n_lights, d_dl_cum, d_dl_slot, d_dl_dir, task_new_cap, dl_dir_cap,
