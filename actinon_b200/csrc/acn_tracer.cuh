@@ -82,6 +82,7 @@ template <typename R> struct DParams
     R     max_path_length;
     R     eps_rel;                            // per-ray shell thickness = max( sv.eps, eps_rel * |origin|_inf ); 0: constant
     int   stage_bytes;                        // node table bytes staged into shared memory (0: none)
+    unsigned int off_geo, off_link, off_pref, off_crec, off_par, off_prog;   // byte offsets of the staged tables (env at 0)
     int   stk_levels;                         // levels of the traversal stack in shared memory (deepest compound nesting + 1)
     int   n_heavy;                            // envelopes of the expensive top-level objects (CSG, distance fields); -1: no split
     int   heavy[ 8 ];
@@ -263,13 +264,15 @@ template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> stage
     else
     {
         const int n = prm.n_nodes;
+        // table offsets come from the host through the parameter bank: a table address is then one constant-bank add
+        // away from the element index (computed here from n they were re-derived, ~40 instructions, before every access)
         R4<R>* s_env  = reinterpret_cast<R4<R>*>( smem );
-        R4<R>* s_geo  = s_env + n;
-        I4*    s_link = reinterpret_cast<I4*>( s_geo + n * GEO_STRIDE );
-        I4*    s_pref = s_link + n;
-        CRec<R>* s_crec = reinterpret_cast<CRec<R>*>( s_pref + n );
-        int*   s_par  = reinterpret_cast<int*>( s_crec + prm.n_children );
-        int*   s_prog = s_par + n;
+        R4<R>* s_geo  = reinterpret_cast<R4<R>*>( smem + prm.off_geo );
+        I4*    s_link = reinterpret_cast<I4*>( smem + prm.off_link );
+        I4*    s_pref = reinterpret_cast<I4*>( smem + prm.off_pref );
+        CRec<R>* s_crec = reinterpret_cast<CRec<R>*>( smem + prm.off_crec );
+        int*   s_par  = reinterpret_cast<int*>( smem + prm.off_par );
+        int*   s_prog = reinterpret_cast<int*>( smem + prm.off_prog );
         for( int i = threadIdx.x; i < n; i += blockDim.x )
         {
             s_env[ i ] = prm.sv.env[ i ]; s_link[ i ] = prm.sv.link[ i ];
@@ -280,15 +283,19 @@ template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> stage
         for( int i = threadIdx.x; i < prm.n_prog; i += blockDim.x ) s_prog[ i ] = prm.sv.prog[ i ];
         __syncthreads();
         SceneView<R, true> sv;
+#ifndef ACN_NO_OPAQUE_BASE
+        unsigned int base;      // opaque to the optimiser: held in one register instead of being re-derived from SR_CgaCtaId at every use
+        asm volatile( "{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"( base ) : "l"( smem ) );
+#else
         const unsigned int base = ( unsigned int )__cvta_generic_to_shared( smem );
-        const unsigned int un = ( unsigned int )n;
+#endif
         sv.env.a      = base;
-        sv.geo.a      = sv.env.a + un * ( unsigned int )sizeof( R4<R> );
-        sv.link.a     = sv.geo.a + un * GEO_STRIDE * ( unsigned int )sizeof( R4<R> );
-        sv.prog_ref.a = sv.link.a + un * ( unsigned int )sizeof( I4 );
-        sv.crec.a     = sv.prog_ref.a + un * ( unsigned int )sizeof( I4 );
-        sv.parent.a   = sv.crec.a + ( unsigned int )prm.n_children * ( unsigned int )sizeof( CRec<R> );
-        sv.prog.a     = sv.parent.a + un * ( unsigned int )sizeof( int );
+        sv.geo.a      = base + prm.off_geo;
+        sv.link.a     = base + prm.off_link;
+        sv.prog_ref.a = base + prm.off_pref;
+        sv.crec.a     = base + prm.off_crec;
+        sv.parent.a   = base + prm.off_par;
+        sv.prog.a     = base + prm.off_prog;
         sv.children.a = 0;                       // march / host only
         sv.eps = prm.sv.eps; sv.light_root = prm.sv.light_root; sv.matter_root = prm.sv.matter_root; sv.seed_mode = prm.sv.seed_mode;
         return sv;
@@ -521,7 +528,9 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R light_hi
 #ifndef ACN_CHUNK
 #define ACN_CHUNK 2        // 32-item groups per cursor fetch
 #endif
-// minimum resident blocks per SM the compiler must fit the registers of each tracing kernel into
+// minimum resident blocks per SM the compiler must fit the registers of each tracing kernel into.  Staged scenes
+// (tables in shared memory, latency ~30 cycles) run best at 5 blocks x 96 registers; scenes whose tables stay in
+// L2 (many_spheres) are latency-bound and want more resident warps at the price of fewer registers.
 #ifndef ACN_MINB_RAYS
 #define ACN_MINB_RAYS 5
 #endif
@@ -530,6 +539,15 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R light_hi
 #endif
 #ifndef ACN_MINB_DIRECT
 #define ACN_MINB_DIRECT 5
+#endif
+#ifndef ACN_MINB_RAYS_G
+#define ACN_MINB_RAYS_G 6
+#endif
+#ifndef ACN_MINB_PATH_G
+#define ACN_MINB_PATH_G 6
+#endif
+#ifndef ACN_MINB_DIRECT_G
+#define ACN_MINB_DIRECT_G 8
 #endif
 
 enum { SCHED_PRIMARY = 0, SCHED_WAVE = 1 };
@@ -631,7 +649,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
 }
 
 // explicit rays popped from the ray stack
-template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_RAYS )
+template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
 k_rays( Wave<R> w, RayBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -747,7 +765,7 @@ __device__ __forceinline__ ListWindow list_window( const u64* __restrict__ cum, 
 
 // direct lighting (scene.c:542-581): one lane per (task, light, sample); the shadow rays exist only
 // as (entry, child index) and are regenerated from the task with an O(1) LCG skip-ahead
-template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_DIRECT )
+template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
 k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
           const unsigned int* __restrict__ dl_dir )
 {
@@ -829,7 +847,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
 
 // indirect rays (scene.c:584-621): one lane per (task, path sample); the child ray is generated,
 // traced and shaded in place, never stored.
-template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, ACN_MINB_PATH )
+template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_PATH : ACN_MINB_PATH_G )
 k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -1604,6 +1622,15 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
 
     // shared-memory staging of the node table
     size_t table = ( size_t )n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )fs->n_children * sizeof( CRec<R> ) + ( size_t )n_prog * sizeof( int );
+    {   // layout: env | geo | link | prog_ref | crec | parent | prog — every table starts 16-byte aligned (32 for the R4<double> ones by construction)
+        size_t o = ( size_t )n * sizeof( R4<R> );
+        prm.off_geo  = ( unsigned int )o; o += ( size_t )n * GEO_STRIDE * sizeof( R4<R> );
+        prm.off_link = ( unsigned int )o; o += ( size_t )n * sizeof( I4 );
+        prm.off_pref = ( unsigned int )o; o += ( size_t )n * sizeof( I4 );
+        prm.off_crec = ( unsigned int )o; o += ( size_t )fs->n_children * sizeof( CRec<R> );
+        prm.off_par  = ( unsigned int )o; o += ( size_t )n * sizeof( int );
+        prm.off_prog = ( unsigned int )o;
+    }
     // (f32 only: the FP64 validation instantiations read the tables from global memory)
     prm.stage_bytes = ( sizeof( R ) == 4 && table <= 96 * 1024 && !getenv( "ACN_NO_STAGING" ) ) ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
     if constexpr( sizeof( R ) == 4 )
