@@ -389,54 +389,74 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
     // ray's max_path_length, +inf otherwise).  Without Q_TRANS a hit with a <= t_far ends the search at once.
     // Envelopes are culled against the best candidate so far: nothing inside an envelope that the ray enters
     // at t_env can be reported closer than t_env - eps, so skipping it when t_env > horizon + 2 eps changes nothing.
+    //
+    // The walk is LOCKSTEP over the lanes that enter the query together: one child record (or one pop of the
+    // range stack) per iteration and lane, a vote keeps everybody in the loop until the last lane is through.
+    // Written as a plain while-loop with `continue`s the lanes drifted apart for good — a lane whose ray misses an
+    // envelope went round the loop on its own while its neighbours tested a sphere, and from then on each drift
+    // group ran the same instructions at different times (many_spheres: 4-8 of 32 lanes active per instruction
+    // even on the loop head).
     const R inf = Num<R>::inf();
     const bool want_trans = ( flags & Q_TRANS ) != 0;
     const R slack = R( 2 ) * sv.eps;
+    const unsigned int mask = __activemask();
     R best = inf;
+    bool found = false;                                     // any-hit search satisfied
     #pragma unroll 1
     for( int pass = 0; pass < 2; pass++ )
     {
-        if( !( flags & ( pass == 0 ? Q_LIGHT : Q_MATTER ) ) ) continue;
+        bool act = !found && ( flags & ( pass == 0 ? Q_LIGHT : Q_MATTER ) ) != 0;
         const int root = pass == 0 ? sv.light_root : sv.matter_root;
         const I4 rl = sv.link[ root ];
         const R far0 = r_min( t_far, best );                 // strict '<' between the roots: matter must beat the lights
-        if( ( node_flags( rl ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + slack ) ) continue;
+        if( act && ( node_flags( rl ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + slack ) ) act = false;
         int sp = 0;
-        int beg = rl.y, end = rl.y + rl.z;
+        int beg = rl.y, end = act ? rl.y + rl.z : rl.y;
         R min_a = inf;
         Trans<R> tl; tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
         R el_a = inf; V3<R> el_n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); int el_obj = -1;     // closest hit inside the current nested element
         for( ;; )
         {
-            while( beg < end )
+            const bool more = !found && ( beg < end || sp > 0 );
+            if( !__any_sync( mask, more ) ) break;
+            if( more )
             {
-                const CRec<R> rec = sv.crec[ beg++ ];
-                const I4 lk = rec.link;
-                const int c = lk.w;
-                // horizon: an element must come within eps of the root's minimum to matter (merge rule);
-                // inside a nested element it must also beat that element's own minimum
-                const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;
-                if( ( node_flags( lk ) & F_ENV ) && !envelope_hits_before( rec.env, ray, hor ) ) continue;
-                if( node_kind( lk ) == K_COMPOUND )
-                {
-                    cm.sb[ sp * cm.stride ] = beg; cm.se[ sp * cm.stride ] = end; sp++; beg = lk.y; end = lk.y + lk.z;     // depth checked at upload
-                    continue;
+                if( beg >= end )
+                {   // a nested list is through: back to its parent list
+                    sp--; beg = cm.sb[ sp * cm.stride ]; end = cm.se[ sp * cm.stride ];
+                    if( sp == 0 && want_trans ) { trans_commit( sv, ray, el_a, el_n, el_obj, &min_a, &tl ); el_a = inf; el_obj = -1; }
                 }
-                V3<R> n;
-                const R a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm, hor );
-                if( !want_trans )
+                else
                 {
-                    if( a < min_a ) { min_a = a; if( a <= t_far ) return a; }
+                    const CRec<R> rec = sv.crec[ beg++ ];
+                    const I4 lk = rec.link;
+                    const int c = lk.w;
+                    // horizon: an element must come within eps of the root's minimum to matter (merge rule);
+                    // inside a nested element it must also beat that element's own minimum
+                    const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;
+                    if( !( node_flags( lk ) & F_ENV ) || envelope_hits_before( rec.env, ray, hor ) )
+                    {
+                        if( node_kind( lk ) == K_COMPOUND )
+                        {
+                            cm.sb[ sp * cm.stride ] = beg; cm.se[ sp * cm.stride ] = end; sp++; beg = lk.y; end = lk.y + lk.z;     // depth checked at upload
+                        }
+                        else
+                        {
+                            V3<R> n;
+                            const R a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm, hor );
+                            if( !want_trans )
+                            {
+                                if( a < min_a ) { min_a = a; if( a <= t_far ) found = true; }
+                            }
+                            else if( sp > 0 )
+                            {
+                                if( a < el_a ) { el_a = a; el_n = n; el_obj = c; }
+                            }
+                            else trans_commit( sv, ray, a, n, c, &min_a, &tl );
+                        }
+                    }
                 }
-                else if( sp > 0 )
-                {
-                    if( a < el_a ) { el_a = a; el_n = n; el_obj = c; }
-                }
-                else trans_commit( sv, ray, a, n, c, &min_a, &tl );
             }
-            if( sp == 0 ) break;
-            sp--; beg = cm.sb[ sp * cm.stride ]; end = cm.se[ sp * cm.stride ];
-            if( sp == 0 && want_trans ) { trans_commit( sv, ray, el_a, el_n, el_obj, &min_a, &tl ); el_a = inf; el_obj = -1; }
         }
         if( min_a < best ) { best = min_a; if( want_trans ) *trans = tl; }
     }
