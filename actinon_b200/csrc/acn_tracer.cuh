@@ -562,8 +562,9 @@ __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, uns
     unsigned long long nt = s->task_stack >> ACN_TASK_SHIFT, nt_cum = s->task_stack & ACN_TASK_MASK;
     s->stats[ ST_DIFFUSE ] += s->tasks_new;
     if( s->rays_out | s->tasks_new | s->ray_take | ( s->path_blk_hi - s->path_blk_lo ) | s->prim_count ) s->waves++;
-    s->rays_out = 0; s->tasks_new = 0; s->dl_packed = 0; s->hits = 0;
-    s->cur_pop = s->cur_rays = s->cur_path = s->cur_index = s->cur_direct = s->cur_primary = s->cur_shade = 0;
+    // dl_packed and cur_direct belong to k_direct, which may still be running on the second stream: k_shade resets them
+    s->rays_out = 0; s->tasks_new = 0; s->hits = 0;
+    s->cur_pop = s->cur_rays = s->cur_path = s->cur_index = s->cur_primary = s->cur_shade = 0;
     // ---- plan
     unsigned long long ray_take = 0, blk_lo = 0, blk_hi = 0, fix_slot = ACN_NONE64, fix_cum = 0;
     s->path_nt = nt; s->path_c_hi = nt_cum;
@@ -722,6 +723,9 @@ template <typename R, bool SH> __global__ void __launch_bounds__( ACN_BLOCK )
 k_shade( Wave<R> w, HitBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
+    // the previous iteration's k_direct is through (the host orders k_shade behind it), k_index of this iteration
+    // rebuilds the direct list after this kernel: the one place where its counters can be reset
+    if( blockIdx.x == 0 && threadIdx.x == 0 ) { w.sc->dl_packed = 0; w.sc->cur_direct = 0; }
     unsigned long long count = w.sc->hits;
     if( count > w.hits_cap ) count = w.hits_cap;
     if( count == 0 || w.sc->overflow ) return;
@@ -1060,6 +1064,10 @@ struct TracerBase
                         const volatile int* cancel, acn_stats* stats ) = 0;
     int width = 0, height = 0, device = 0;
     cudaStream_t own_stream = nullptr;
+    // second stream: k_path runs beside k_rays and k_direct beside the next iteration's k_sched/k_pop/k_rays, so the
+    // tail of one persistent kernel (last warps still tracing) is filled by the blocks of the next
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_sched = nullptr, ev_path = nullptr, ev_index = nullptr, ev_direct = nullptr;
     // staging for the host-pointer entry point
     double* d_xy_stage = nullptr; float* d_rgb_stage = nullptr; uint64_t stage_cap = 0;
 };
@@ -1167,6 +1175,9 @@ template <typename R> struct Tracer : TracerBase
         cudaFree( d_sc ); if( h_sc ) cudaFreeHost( h_sc );
         cudaFree( d_accum ); cudaFree( d_xy_stage ); cudaFree( d_rgb_stage );
         if( own_stream ) cudaStreamDestroy( own_stream );
+        if( side_stream ) cudaStreamDestroy( side_stream );
+        if( ev_sched ) cudaEventDestroy( ev_sched ); if( ev_path ) cudaEventDestroy( ev_path );
+        if( ev_index ) cudaEventDestroy( ev_index ); if( ev_direct ) cudaEventDestroy( ev_direct );
     }
 
     int init( const acn_flat_scene* fs, const acn_options* opt );
@@ -1441,6 +1452,11 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     cudaError_t ce = cudaSetDevice( device );
     if( ce != cudaSuccess ) { set_error( "cudaSetDevice(%d): %s", device, cudaGetErrorString( ce ) ); return ACN_ERR_NO_DEVICE; }
     ACN_CUDA( cudaStreamCreateWithFlags( &own_stream, cudaStreamNonBlocking ) );
+    ACN_CUDA( cudaStreamCreateWithFlags( &side_stream, cudaStreamNonBlocking ) );
+    ACN_CUDA( cudaEventCreateWithFlags( &ev_sched, cudaEventDisableTiming ) );
+    ACN_CUDA( cudaEventCreateWithFlags( &ev_path, cudaEventDisableTiming ) );
+    ACN_CUDA( cudaEventCreateWithFlags( &ev_index, cudaEventDisableTiming ) );
+    ACN_CUDA( cudaEventCreateWithFlags( &ev_direct, cudaEventDisableTiming ) );
 
     if( ( rc = dev_alloc( &d_env, n ) ) ) return rc;
     if( ( rc = dev_alloc( &d_link, n ) ) ) return rc;
@@ -1740,7 +1756,15 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     const Wave<R> w = make_wave( index_base );
     int result = ACN_OK;
 
-    // one k_sched + the kernels it planned; nothing here depends on device-side counts
+    // one k_sched + the kernels it planned; nothing here depends on device-side counts.  Two streams (unless the
+    // per-kernel timing is on, which needs the kernels one after the other):
+    //   st    k_sched  k_pop  k_rays ............. | k_shade  k_index
+    //   s2    [k_direct of the previous iteration]  k_path   |                  k_direct
+    // k_path needs k_sched's plan; k_shade needs the hits of k_rays and k_path and — because it clears the direct list
+    // and k_index rebuilds it — the previous k_direct, which precedes k_path on s2; k_direct needs k_index.
+    const bool two = !kp.on && !getenv( "ACN_ONE_STREAM" );
+    cudaStream_t s2 = two ? side_stream : st;
+    bool direct_pending = false;
     auto enqueue = [ & ]( int mode, uint64_t first, uint64_t cnt )
     {
         kp_begin( 6 );
@@ -1753,17 +1777,20 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
             kp_primary<<< grid_trace[ 0 ], ACN_BLOCK, smem_bytes, st >>>( w, d_xy );
             kp_end( 0 );
             launches++;
+            if( two && direct_pending ) cudaStreamWaitEvent( st, ev_direct, 0 );
         }
         else
         {
+            if( two ) { cudaEventRecord( ev_sched, st ); cudaStreamWaitEvent( s2, ev_sched, 0 ); }
             k_pop<R><<< grid_util, 256, 0, st >>>( d_sc, ray_stack, ray_cur );
             kp_end( 6 );
             kp_begin( 1 );
             kp_rays<<< grid_trace[ 1 ], ACN_BLOCK, smem_bytes, st >>>( w, ray_cur );
             kp_end( 1 );
             kp_begin( 2 );
-            kp_path<<< grid_trace[ 2 ], ACN_BLOCK, smem_bytes, st >>>( w, task_stack, d_pdir );
+            kp_path<<< grid_trace[ 2 ], ACN_BLOCK, smem_bytes, s2 >>>( w, task_stack, d_pdir );
             kp_end( 2 );
+            if( two ) { cudaEventRecord( ev_path, s2 ); cudaStreamWaitEvent( st, ev_path, 0 ); }
             launches += 3;
         }
         kp_begin( 4 );
@@ -1773,11 +1800,15 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         k_index<R><<< grid_util, 256, 0, st >>>( d_sc, task_new, task_new_cap, prm.n_lights, d_dl_cum, d_dl_slot, d_dl_dir, task_new_cap, dl_dir_cap,
                                                  task_stack, d_pdir, task_stack_cap, pdir_cap );
         kp_end( 5 );
+        if( two ) { cudaEventRecord( ev_index, st ); cudaStreamWaitEvent( s2, ev_index, 0 ); }
         kp_begin( 3 );
-        kp_direct<<< grid_trace[ 3 ], ACN_BLOCK, smem_bytes, st >>>( w, task_new, d_dl_cum, d_dl_slot, d_dl_dir );
+        kp_direct<<< grid_trace[ 3 ], ACN_BLOCK, smem_bytes, s2 >>>( w, task_new, d_dl_cum, d_dl_slot, d_dl_dir );
         kp_end( 3 );
+        if( two ) { cudaEventRecord( ev_direct, s2 ); direct_pending = true; }
         launches += 3;
     };
+    // everything on the side stream joins st: before the host reads the scheduler state for good, and before k_finish
+    auto join = [ & ]() { if( two && direct_pending ) { cudaStreamWaitEvent( st, ev_direct, 0 ); direct_pending = false; } };
 
     const int iters_per_poll = 4;
     for( uint64_t first = 0; first < n && result == ACN_OK; first += prim_chunk )
@@ -1799,6 +1830,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         }
     }
 
+    join();
     if( result == ACN_OK )
     {
         k_finish<R><<< grid_for( n * 3, 256 ), 256, 0, st >>>( d_accum, n, prm.gamma, d_rgb );
