@@ -526,8 +526,18 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R light_hi
 // ---------------------------------------------------------------------------------------------
 #define ACN_BLOCK 128
 #ifndef ACN_CHUNK
-#define ACN_CHUNK 2        // 32-item groups per cursor fetch
+#define ACN_CHUNK 2        // 32-item groups per cursor fetch when a launch has plenty of work
 #endif
+#ifndef ACN_CHUNK_MIN_GROUPS
+#define ACN_CHUNK_MIN_GROUPS 16
+#endif
+// Groups per cursor fetch of this launch.  Big launches (wine_glass: ~30 groups per warp) amortise the cursor atomic
+// over ACN_CHUNK groups; small ones (diamond: ~6 per warp) fetch single groups, because the last chunk a warp takes is
+// the tail the rest of the machine waits for (diamond 15.2 -> 14.0 ms/step).
+__device__ __forceinline__ int launch_chunk( unsigned long long groups )
+{
+    return groups >= ( unsigned long long )gridDim.x * ( ACN_BLOCK / 32 ) * ACN_CHUNK_MIN_GROUPS ? ACN_CHUNK : 1;
+}
 // minimum resident blocks per SM the compiler must fit the registers of each tracing kernel into.  Staged scenes
 // (tables in shared memory, latency ~30 cycles) run best at 5 blocks x 96 registers; scenes whose tables stay in
 // L2 (many_spheres) are latency-bound and want more resident warps at the price of fewer registers.
@@ -616,7 +626,8 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
     extern __shared__ __align__( 32 ) unsigned char smem[];
     const unsigned long long first = w.sc->prim_first, count = w.sc->prim_count;
     if( count == 0 || w.sc->overflow ) return;
-    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks: no need to stage the scene
+    const int chunk = launch_chunk( count >> 5 );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks: no need to stage the scene
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
@@ -624,9 +635,9 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
     unsigned long long n_rays = 0;
     for( ;; )
     {
-        const unsigned long long c0 = warp_fetch( &w.sc->cur_primary, 32ull * ACN_CHUNK, lane );
+        const unsigned long long c0 = warp_fetch( &w.sc->cur_primary, 32ull * chunk, lane );
         if( c0 >= count ) break;
-        for( int g = 0; g < ACN_CHUNK; g++ )
+        for( int g = 0; g < chunk; g++ )
         {
             const unsigned long long i = c0 + 32ull * g + lane;
             if( i >= count ) continue;
@@ -657,7 +668,8 @@ k_rays( Wave<R> w, RayBuf<R> in )
     __shared__ unsigned long long ring_all[ ACN_BLOCK / 32 ][ ACN_PEND ];
     const unsigned long long count = w.sc->ray_take;
     if( count == 0 || w.sc->overflow ) return;
-    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks
+    const int chunk = launch_chunk( count >> 5 );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const int lane = threadIdx.x & 31;
@@ -681,8 +693,8 @@ k_rays( Wave<R> w, RayBuf<R> in )
         {
             if( c_cur >= c_end )
             {
-                c_cur = warp_fetch( &w.sc->cur_rays, 32ull * ACN_CHUNK, lane );
-                c_end = c_cur + 32ull * ACN_CHUNK;
+                c_cur = warp_fetch( &w.sc->cur_rays, 32ull * chunk, lane );
+                c_end = c_cur + 32ull * chunk;
                 if( c_cur >= count ) { input_done = true; continue; }
             }
             i = c_cur + lane; c_cur += 32;
@@ -729,14 +741,15 @@ k_shade( Wave<R> w, HitBuf<R> in )
     unsigned long long count = w.sc->hits;
     if( count > w.hits_cap ) count = w.hits_cap;
     if( count == 0 || w.sc->overflow ) return;
-    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= count ) return;     // more warps than chunks
+    const int chunk = launch_chunk( count >> 5 );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
     const int lane = threadIdx.x & 31;
     for( ;; )
     {
-        const unsigned long long c0 = warp_fetch( &w.sc->cur_shade, 32ull * ACN_CHUNK, lane );
+        const unsigned long long c0 = warp_fetch( &w.sc->cur_shade, 32ull * chunk, lane );
         if( c0 >= count ) break;
-        for( int g = 0; g < ACN_CHUNK; g++ )
+        for( int g = 0; g < chunk; g++ )
         {
             const unsigned long long i = c0 + 32ull * g + lane;
             if( i >= count ) continue;
@@ -776,7 +789,8 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     extern __shared__ __align__( 32 ) unsigned char smem[];
     const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
     if( total == 0 || w.sc->overflow ) return;
-    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * ACN_CHUNK >= total ) return;     // more warps than chunks
+    const int chunk = launch_chunk( total >> 5 );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= total ) return;     // more warps than chunks
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
@@ -785,9 +799,9 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     unsigned long long n_shadow = 0;
     for( ;; )
     {
-        const unsigned long long b0 = warp_fetch( &w.sc->cur_direct, ACN_CHUNK, lane );
+        const unsigned long long b0 = warp_fetch( &w.sc->cur_direct, chunk, lane );
         if( b0 >= n_blocks ) break;
-        for( unsigned long long blk = b0; blk < b0 + ACN_CHUNK && blk < n_blocks; blk++ )
+        for( unsigned long long blk = b0; blk < b0 + chunk && blk < n_blocks; blk++ )
         {
             const ListWindow lw = list_window( dl_cum, dl_dir, blk, n_entries, lane );
             const unsigned long long idx = ( blk << 5 ) + lane;
@@ -859,7 +873,8 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     const unsigned long long blk_lo = w.sc->path_blk_lo, blk_hi = w.sc->path_blk_hi;
     if( blk_hi <= blk_lo || w.sc->overflow ) return;
     const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
-    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * ACN_CHUNK >= blk_hi - blk_lo ) return;   // more warps than chunks
+    const int chunk = launch_chunk( blk_hi - blk_lo );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * chunk >= blk_hi - blk_lo ) return;   // more warps than chunks
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
     const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
     const DParams<R>& prm = w.prm;
@@ -888,8 +903,8 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
         {
             if( b_cur >= b_end )
             {
-                b_cur = warp_fetch( &w.sc->cur_path, ACN_CHUNK, lane );
-                b_end = b_cur + ACN_CHUNK < n_blocks ? b_cur + ACN_CHUNK : n_blocks;
+                b_cur = warp_fetch( &w.sc->cur_path, chunk, lane );
+                b_end = b_cur + chunk < n_blocks ? b_cur + chunk : n_blocks;
                 if( b_cur >= n_blocks ) { input_done = true; continue; }
             }
             const unsigned long long blk = blk_lo + b_cur; b_cur++;
@@ -1815,8 +1830,9 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     {
         const uint64_t cnt = ( n - first < prim_chunk ) ? n - first : prim_chunk;
         enqueue( SCHED_PRIMARY, first, cnt );
-        for( ;; )
+        for( uint64_t polls = 0;; polls++ )
         {
+            if( polls > ( 1ull << 22 ) ) { set_error( "wavefront scheduler did not terminate" ); result = ACN_ERR_CUDA; break; }   // cannot happen; never spin forever
             for( int k = 0; k < iters_per_poll; k++ ) enqueue( SCHED_WAVE, 0, 0 );
             ACN_CUDA( cudaMemcpyAsync( h_sc, d_sc, sizeof( Sched ), cudaMemcpyDeviceToHost, st ) );
             ACN_CUDA( cudaStreamSynchronize( st ) );
