@@ -155,6 +155,7 @@ struct Sched
     unsigned long long prim_first, prim_count;
     // work cursors of the persistent kernels (units: chunks)
     unsigned long long cur_pop, cur_rays, cur_path, cur_index, cur_direct, cur_primary, cur_shade;
+    unsigned long long pop_front, pop_back;     // k_pop: rays placed at the front / the back of the wave buffer so far
     // per-iteration outputs
     unsigned long long rays_out;        // rays appended
     unsigned long long hits;            // hits appended to the hit queue by the tracing kernels
@@ -331,13 +332,11 @@ template <typename R> __device__ __forceinline__ u64 skip2( const DParams<R>& pr
     return lcg00_skip( s, 2ull * k );
 }
 
-template <typename R> __device__ __forceinline__ void emit_ray( const Wave<R>& w, V3<R> p, V3<R> d, R intensity, int depth,
-                                                              V3<R> tp, int cls, int sample, u64 key )
+template <typename R> __device__ __forceinline__ void write_ray( const Wave<R>& w, unsigned long long slot, V3<R> p, V3<R> d, R intensity, int depth,
+                                                               V3<R> tp, int cls, int sample, u64 key )
 {
     int flags = 0;
     if( depth == 0 || intensity < w.prm.min_intensity ) flags |= RAYF_PROBE;
-    unsigned long long slot = w.sc->ray_base + agg_inc( &w.sc->rays_out );
-    if( slot >= w.rays_cap ) { w.sc->overflow = 1; return; }
     R4<R> a; a.x = p.x; a.y = p.y; a.z = p.z; a.w = intensity;
     R4<R> b; b.x = d.x; b.y = d.y; b.z = d.z; b.w = R( 0 );
     R4<R> c; c.x = tp.x; c.y = tp.y; c.z = tp.z; c.w = R( 0 );
@@ -346,61 +345,100 @@ template <typename R> __device__ __forceinline__ void emit_ray( const Wave<R>& w
 }
 
 // ---------------------------------------------------------------------------------------------
-// scene_s_lum (scene.c:420-667) for one hit: emits child rays and at most one diffuse task.
+// scene_s_lum (scene.c:420-667) for one hit per lane: emits child rays and at most one diffuse task.
+// WARP-COOPERATIVE: all 32 lanes call it (live = this lane holds a hit).  The surface response is planned first —
+// which of the reflection / chromatic / refraction rays and the diffuse task this hit spawns, with the intensity
+// each stage passes on (scene.c updates `intensity` between the stages) — then the warp reserves the queue slots of
+// ALL its emissions with one atomic for the rays and one for the tasks, then the lanes write.  With an atomic per
+// emission site (up to four dependent round trips to one contended address per 32 hits) k_shade ran at the
+// latency of those atomics: 2 TB/s, and slower with more resident warps.
 // ---------------------------------------------------------------------------------------------
-template <typename R, bool SH> __device__ void shade_hit( const Wave<R>& w, const SceneView<R, SH>& sv0, const Ray<R>& ray, R a, R hit_eps, const Trans<R>& tr,
-                                                 int depth, R I, V3<R> tp, int sample, u64 key )
+template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const Wave<R>& w, const SceneView<R, SH>& sv0, bool live, const Ray<R>& ray, R a, R hit_eps,
+                                                                          const Trans<R>& tr, int depth, R I, V3<R> tp, int sample, u64 key, int lane )
 {
     const DParams<R>& prm = w.prm;
-    if( depth == 0 || I < prm.min_intensity ) return;                                    // scene.c:428
+    live = live && !( depth == 0 || I < prm.min_intensity );                             // scene.c:428
     const V3<R> pos = madd( ray.p, ray.d, a );
-
-    const DMat<R>* me = tr.enter_obj >= 0 ? &prm.mats[ sv0.link[ tr.enter_obj ].w ] : nullptr;
-    if( me && me->radiance > R( 0 ) )                                                    // scene.c:432-437
+    const DMat<R>* me = nullptr;
+    if( live && tr.enter_obj >= 0 ) me = &prm.mats[ sv0.link[ tr.enter_obj ].w ];
+    if( live && me && me->radiance > R( 0 ) )                                            // scene.c:432-437
     {
         R d2 = sqr( pos - xyz( sv0.geo[ tr.enter_obj * GEO_STRIDE ] ) );
         R li = d2 > R( 0 ) ? me->radiance / d2 : Num<R>::mag();
         add_sample( w, sample, mul( obj_color( prm, sv0, tr.enter_obj, pos ), tp ) * ( li * I ) );
         agg_count( &w.sc->stats[ ST_LIGHT ] );
-        return;
+        live = false;
     }
 
+    // ---- plan
     R nrel = R( 1 ), F = R( 0 ), C = R( 0 ), Dff = R( 0 ), on_a = R( 1 ), on_b = R( 0 );
     bool T = false;
-    if( me )
+    R I_refl = R( 0 ), I_chro = R( 0 ), I_diff = R( 0 ), I_refr = R( 0 );
+    bool do_refl = false, do_chro = false, do_diff = false, do_refr = false;
+    if( live )
     {
-        nrel = me->refr; F = me->fresnel01; C = me->chroma; Dff = me->diffuse;
-        T = me->transparent != 0; on_a = me->on_a; on_b = me->on_b;
-    }
-    if( tr.exit_obj >= 0 )                                                               // scene.c:464-470, 656-664
-    {
-        const DMat<R>& mx = prm.mats[ sv0.link[ tr.exit_obj ].w ];
-        nrel /= mx.refr; F = R( 1 ); C = R( 0 ); Dff = R( 0 ); T = true;
-        if( a > R( 0 ) )
+        if( me )
         {
-            tp.x *= r_pow( mx.transp[ 0 ], a );
-            tp.y *= r_pow( mx.transp[ 1 ], a );
-            tp.z *= r_pow( mx.transp[ 2 ], a );
+            nrel = me->refr; F = me->fresnel01; C = me->chroma; Dff = me->diffuse;
+            T = me->transparent != 0; on_a = me->on_a; on_b = me->on_b;
         }
+        if( tr.exit_obj >= 0 )                                                           // scene.c:464-470, 656-664
+        {
+            const DMat<R>& mx = prm.mats[ sv0.link[ tr.exit_obj ].w ];
+            nrel /= mx.refr; F = R( 1 ); C = R( 0 ); Dff = R( 0 ); T = true;
+            if( a > R( 0 ) )
+            {
+                tp.x *= r_pow( mx.transp[ 0 ], a );
+                tp.y *= r_pow( mx.transp[ 1 ], a );
+                tp.z *= r_pow( mx.transp[ 2 ], a );
+            }
+        }
+        if( F > R( 0 ) && I >= prm.min_intensity )                                       // scene.c:473-495
+        {
+            const R refl = fresnel_reflectance( ray.d, tr.exit_nor, nrel ) * F;
+            do_refl = true; I_refl = refl * I; I *= ( R( 1 ) - refl );
+        }
+        if( C > R( 0 ) && I >= prm.min_intensity )                                       // scene.c:498-523
+        {
+            do_chro = true; I_chro = C * I; I *= ( R( 1 ) - C );
+        }
+        if( tr.enter_obj >= 0 && I * Dff >= prm.min_intensity )                          // scene.c:526-630
+        {
+            do_diff = true; I_diff = I * Dff; I *= ( R( 1 ) - Dff );
+        }
+        if( T && I >= prm.min_intensity ) { do_refr = true; I_refr = I; }                // scene.c:633-653
     }
 
-    if( F > R( 0 ) && I >= prm.min_intensity )                                           // scene.c:473-495
+    // ---- reserve: one atomic per warp for the rays, one for the tasks (k_pop sorts the rays by class later on)
+    const unsigned int lt = ( 1u << lane ) - 1u;
+    const unsigned int nr = ( do_refl ? 1u : 0u ) + ( do_chro ? 1u : 0u ) + ( do_refr ? 1u : 0u );
+    unsigned int incl = nr;
+    #pragma unroll
+    for( int o = 1; o < 32; o <<= 1 ) { const unsigned int v = __shfl_up_sync( ACN_FULL, incl, o ); if( lane >= o ) incl += v; }
+    const unsigned int total_r = __shfl_sync( ACN_FULL, incl, 31 );
+    const unsigned int tmask = __ballot_sync( ACN_FULL, do_diff );
+    unsigned long long rbase = 0, tbase = 0;
+    if( lane == 0 )
     {
-        R refl = fresnel_reflectance( ray.d, tr.exit_nor, nrel ) * F;
-        emit_ray( w, pos, reflect( ray.d, tr.exit_nor ), refl * I, depth - 1, tp, RC_REFLECT, sample, mix64( key, KEY_REFLECT ) );
-        I *= ( R( 1 ) - refl );
+        if( total_r ) rbase = atomicAdd( &w.sc->rays_out, ( unsigned long long )total_r );
+        if( tmask ) tbase = atomicAdd( &w.sc->tasks_new, ( unsigned long long )__popc( tmask ) );
     }
+    rbase = __shfl_sync( ACN_FULL, rbase, 0 ); tbase = __shfl_sync( ACN_FULL, tbase, 0 );
+    if( !live ) return;
+    unsigned long long rslot = w.sc->ray_base + rbase + ( incl - nr );
+    if( nr && rslot + nr > w.rays_cap ) { w.sc->overflow = 1; return; }
 
-    if( C > R( 0 ) && I >= prm.min_intensity )                                           // scene.c:498-523
+    // ---- emit
+    if( do_refl )
+        write_ray( w, rslot++, pos, reflect( ray.d, tr.exit_nor ), I_refl, depth - 1, tp, RC_REFLECT, sample, mix64( key, KEY_REFLECT ) );
+    if( do_chro )
     {
         V3<R> col = obj_color( prm, sv0, tr.enter_obj, pos );
-        emit_ray( w, pos, reflect( ray.d, tr.exit_nor ), C * I, depth - 1, mul( tp, col ), RC_CHROMATIC, sample, mix64( key, KEY_CHROMATIC ) );
-        I *= ( R( 1 ) - C );
+        write_ray( w, rslot++, pos, reflect( ray.d, tr.exit_nor ), I_chro, depth - 1, mul( tp, col ), RC_CHROMATIC, sample, mix64( key, KEY_CHROMATIC ) );
     }
-
-    if( tr.enter_obj >= 0 && I * Dff >= prm.min_intensity )                              // scene.c:526-630
+    if( do_diff )
     {
-        const R Id = I * Dff;
+        const R Id = I_diff;
         const V3<R> nrm = -tr.exit_nor;
         const R cos_i = dot( ray.d, tr.exit_nor );
         const V3<R> prj = unit( ray.d - nrm * dot( ray.d, nrm ) );
@@ -416,7 +454,7 @@ template <typename R, bool SH> __device__ void shade_hit( const Wave<R>& w, cons
             np = ( unsigned long long )( ( double )prm.path_samples * ( double )Id );
             if( np == 0 ) np = 1;
         }
-        unsigned long long slot = agg_inc( &w.sc->tasks_new );
+        const unsigned long long slot = tbase + __popc( tmask & lt );
         if( slot < w.tasks_cap )
         {
             V3<R> tpc = mul( tp, col );
@@ -431,14 +469,10 @@ template <typename R, bool SH> __device__ void shade_hit( const Wave<R>& w, cons
             w.tasks_out.key[ slot ] = key;
         }
         else w.sc->overflow = 2;
-        I *= ( R( 1 ) - Dff );
     }
-
-    if( T && I >= prm.min_intensity )                                                    // scene.c:633-653
-    {
-        emit_ray( w, madd( ray.p, ray.d, a + R( 2 ) * hit_eps ), refract( ray.d, tr.exit_nor, nrel ), I, depth - 1, tp,
-                  RC_REFRACT, sample, mix64( key, KEY_REFRACT ) );
-    }
+    if( do_refr )
+        write_ray( w, rslot++, madd( ray.p, ray.d, a + R( 2 ) * hit_eps ), refract( ray.d, tr.exit_nor, nrel ), I_refr, depth - 1, tp,
+                   RC_REFRACT, sample, mix64( key, KEY_REFRACT ) );
 }
 
 // trace one ray of the tree and shade its hit; returns true when the ray leaves the scene, in which
@@ -575,6 +609,7 @@ __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, uns
     // dl_packed and cur_direct belong to k_direct, which may still be running on the second stream: k_shade resets them
     s->rays_out = 0; s->tasks_new = 0; s->hits = 0;
     s->cur_pop = s->cur_rays = s->cur_path = s->cur_index = s->cur_primary = s->cur_shade = 0;
+    s->pop_front = s->pop_back = 0;
     // ---- plan
     unsigned long long ray_take = 0, blk_lo = 0, blk_hi = 0, fix_slot = ACN_NONE64, fix_cum = 0;
     s->path_nt = nt; s->path_c_hi = nt_cum;
@@ -607,15 +642,43 @@ __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, uns
     s->fix_slot = fix_slot; s->fix_cum = fix_cum;
 }
 
-// pops the top ray_take rays of the stack into the current-wave buffer
+// pops the top ray_take rays of the stack into the current-wave buffer, PARTITIONED by class: reflection and
+// chromatic rays fill the buffer from the front, refraction rays from the back.  A k_rays warp then traces 32 rays of
+// one kind (reflections leave the solid they were born on, refractions cross it: different envelope gates, different
+// numbers of crossings), whatever order k_shade emitted them in.  One pair of atomics per block and round.
 template <typename R> __global__ void __launch_bounds__( 256 )
-k_pop( const Sched* __restrict__ s, RayBuf<R> stack, RayBuf<R> cur )
+k_pop( Sched* __restrict__ s, RayBuf<R> stack, RayBuf<R> cur )
 {
+    __shared__ unsigned int w_front[ 8 ], w_back[ 8 ];
+    __shared__ unsigned long long b_front, b_back;
     const unsigned long long n = s->ray_take, base = s->ray_base;
-    for( unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x; i < n; i += ( unsigned long long )gridDim.x * blockDim.x )
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int lt = ( 1u << lane ) - 1u;
+    for( unsigned long long i0 = ( unsigned long long )blockIdx.x * blockDim.x; i0 < n; i0 += ( unsigned long long )gridDim.x * blockDim.x )
     {
-        cur.o_i[ i ] = stack.o_i[ base + i ]; cur.d_[ i ] = stack.d_[ base + i ];
-        cur.tp[ i ] = stack.tp[ base + i ];   cur.meta[ i ] = stack.meta[ base + i ];
+        const unsigned long long i = i0 + threadIdx.x;
+        const bool live = i < n;
+        R4<R> a, b, c; I4 m; m.x = 0;
+        if( live ) { a = stack.o_i[ base + i ]; b = stack.d_[ base + i ]; c = stack.tp[ base + i ]; m = stack.meta[ base + i ]; }
+        const bool back = live && ( ( m.x >> 8 ) & 0xFF ) == RC_REFRACT, front = live && !back;
+        const unsigned int mf = __ballot_sync( ACN_FULL, front ), mb = __ballot_sync( ACN_FULL, back );
+        if( lane == 0 ) { w_front[ wid ] = __popc( mf ); w_back[ wid ] = __popc( mb ); }
+        __syncthreads();
+        if( threadIdx.x == 0 )
+        {
+            unsigned int tf = 0, tb = 0;
+            for( int k = 0; k < 8; k++ ) { const unsigned int f = w_front[ k ], q = w_back[ k ]; w_front[ k ] = tf; w_back[ k ] = tb; tf += f; tb += q; }
+            b_front = tf ? atomicAdd( &s->pop_front, ( unsigned long long )tf ) : 0ull;
+            b_back  = tb ? atomicAdd( &s->pop_back, ( unsigned long long )tb ) : 0ull;
+        }
+        __syncthreads();
+        if( live )
+        {
+            const unsigned long long d = front ? b_front + w_front[ wid ] + __popc( mf & lt )
+                                               : n - 1ull - ( b_back + w_back[ wid ] + __popc( mb & lt ) );
+            cur.o_i[ d ] = a; cur.d_[ d ] = b; cur.tp[ d ] = c; cur.meta[ d ] = m;
+        }
+        __syncthreads();
     }
 }
 
@@ -752,12 +815,14 @@ k_shade( Wave<R> w, HitBuf<R> in )
         for( int g = 0; g < chunk; g++ )
         {
             const unsigned long long i = c0 + 32ull * g + lane;
-            if( i >= count ) continue;
-            const R4<R> oa = in.o_a[ i ], di = in.d_i[ i ], ne = in.n_e[ i ], tp = in.tp[ i ];
-            const I4 m = in.meta[ i ];
+            if( c0 + 32ull * g >= count ) break;
+            const bool live = i < count;
+            const unsigned long long il = live ? i : count - 1;          // dead lanes of the last group read a valid record and ignore it
+            const R4<R> oa = in.o_a[ il ], di = in.d_i[ il ], ne = in.n_e[ il ], tp = in.tp[ il ];
+            const I4 m = in.meta[ il ];
             Ray<R> ray; ray.p = xyz( oa ); ray.d = xyz( di );
             Trans<R> tr; tr.exit_nor = xyz( ne ); tr.exit_obj = m.z; tr.enter_obj = m.w;
-            shade_hit( w, sv0, ray, oa.w, ne.w, tr, m.x, di.w, xyz( tp ), m.y, in.key[ i ] );
+            shade_hits( w, sv0, live, ray, oa.w, ne.w, tr, m.x, di.w, xyz( tp ), m.y, in.key[ il ], lane );
         }
     }
 }
