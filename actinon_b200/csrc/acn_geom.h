@@ -172,6 +172,7 @@ template <typename R, bool SH> ACN_HD R dist_hit_body( const SceneView<R, SH>& s
     const I4 lk = sv.link[ n ];
     Ray<R> rl = ray;
     R offs0 = R( 0 );
+    R lim = inf;                // march parameter (object frame) at which the ray has left the object's own envelope
     if( node_flags( lk ) & F_ENV )
     {
         const R4<R> e = sv.env[ n ];
@@ -181,6 +182,13 @@ template <typename R, bool SH> ACN_HD R dist_hit_body( const SceneView<R, SH>& s
             if( !( offs0 < inf ) ) return inf;
             rl.p = madd( ray.p, ray.d, offs0 );
         }
+        // The reference marches on for all `cycles` steps after the ray has passed the shape (objects.c:925-933) and
+        // then finds |dist| > eps: a miss.  The shape lies inside its envelope, so once the march is beyond the far
+        // side of the envelope (+1 % of its radius) the outcome is settled: stop there.  Same result, and a ray that
+        // crosses the envelope of a chain link without touching the torus costs ~10 steps instead of 200.
+        const V3<R> q = rl.p - xyz( e );
+        const R sq = dot( q, rl.d ), dq = e.w * e.w - sqr( q - rl.d * sq );
+        if( dq >= R( 0 ) ) lim = ( -sq + r_sqrt( dq ) + R( 0.01 ) * e.w ) * inv_scale;
     }
     V3<R> lp = mlv( rax, rl.p - pos ) * inv_scale;
     V3<R> ld = mlv( rax, rl.d );
@@ -193,6 +201,7 @@ template <typename R, bool SH> ACN_HD R dist_hit_body( const SceneView<R, SH>& s
             offs1 += dist + eps;
             dist = dist_fn( kind, ex_radius, madd( lp, ld, offs1 ) );
             if( dist < R( 0 ) || dist > Num<R>::mag() ) break;
+            if( offs1 > lim && dist > eps ) break;
         }
     }
     else
