@@ -360,11 +360,13 @@ def main():
     except Exception:
         pass
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
+        # N > 1: the oracle runs a smaller sample on rank 0 only to count the algorithmic FLOPs of rank 0's share (the
+        # roofline is per GPU); the cpu_baseline object itself is an N = 1 deliverable
         from tests.oracle_lib import Oracle
         orc = Oracle()
         threads = os.cpu_count() or 1
-        stride = cpu_probe_stride(orc, flat, xy_np, args.cpu_seconds, threads)
+        stride = cpu_probe_stride(orc, flat, xy_np, args.cpu_seconds if world == 1 else min(args.cpu_seconds, 4.0), threads)
         xs = cpu_sample(xy_np, stride)
         t0 = time.perf_counter()
         _, info = orc.render(flat, xs, seed_mode=0, threads=threads)
@@ -383,11 +385,13 @@ def main():
         roof["whole_step_tflops"] = info["flops"] * scale / (total_ms / args.steps * 1e-3) / 1e12
         roof["whole_step_frac"] = roof["whole_step_tflops"] / fp32_peak
         roof["sf_ops_per_step"] = info["sf_ops"] * scale
-        roof["queue_bytes_per_step"] = 56.0 * rays_total / args.steps
+        roof["queue_bytes_per_step"] = 56.0 * rays_total / args.steps / world
         roof["queue_gbs"] = roof["queue_bytes_per_step"] / (total_ms / args.steps * 1e-3) / 1e9
-        cpu = {"value": len(xs) / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{len(xs)} of the {n_local} samples of one step (every {stride}th), FP64 oracle, position-hash seeding",
-               "rays_per_sec": info["rays"] / dt, "oracle_rays_per_sample": info["rays"] / len(xs)}
+        roof["scope"] = "rank 0 (per GPU)"
+        if world == 1:
+          cpu = {"value": len(xs) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                 "sample": f"{len(xs)} of the {n_local} samples of one step (every {stride}th), FP64 oracle, position-hash seeding",
+                 "rays_per_sec": info["rays"] / dt, "oracle_rays_per_sample": info["rays"] / len(xs)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
