@@ -34,7 +34,7 @@ enum { F_ENV = 1, F_ROUGH = 2 };
 enum { GEO_STRIDE = 5 };
 enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
 enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
-enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5, CSG_RUN = 6, CSG_MEMBER = 7, CSG_MEMBER_NEG = 8 };   // word = op | arg << 4, see acn_isect.cuh
+enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5, CSG_RUN = 6, CSG_MEMBER = 7, CSG_MEMBER_NEG = 8, CSG_MORE = 9 };   // word = op | arg << 4, see acn_isect.cuh
 enum { CSG_E = 16, CSG_VIRTUAL = 255, CSG_MAX_VARS = 48, CSG_TABLE_VARS = 12 };   // crossings kept per ray, id of envelope crossings, variable limits
 
 // A scene table: element i by value.  SH = false: a pointer (device global memory, or host memory in scene
@@ -147,6 +147,34 @@ template <typename R> ACN_HD R dist_fn( int kind, R ex_radius, V3<R> p )
     return r_sqrt( x * x + y * y + p.z * p.z ) - ex_radius;
 }
 
+// gradient of a distance function at p (object frame): the normal of a distance-field hit before it is rotated back
+template <typename R> ACN_HD V3<R> dist_gradient( int kind, R ex_radius, V3<R> p, R eps )
+{
+    V3<R> g;
+    if( sizeof( R ) == 8 )
+    {
+        // the reference's forward differences with step eps (objects.c:947-953)
+        R d0 = dist_fn( kind, ex_radius, p );
+        g.x = ( dist_fn( kind, ex_radius, v3<R>( p.x + eps, p.y, p.z ) ) - d0 ) / eps;
+        g.y = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y + eps, p.z ) ) - d0 ) / eps;
+        g.z = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y, p.z + eps ) ) - d0 ) / eps;
+    }
+    else
+    {
+        // FP32: a difference quotient over eps would carry ~1e-3 rounding noise; both
+        // distance functions have a closed-form gradient, which the quotient approximates
+        // to O(eps) — use it.  torus: unit vector from the nearest point of the core circle.
+        g = p;
+        if( kind == K_DIST_TORUS )
+        {
+            R f = r_sqrt( p.x * p.x + p.y * p.y );
+            R fi = f > R( 0 ) ? R( 1 ) / f : R( 1 );
+            g = v3<R>( p.x - p.x * fi, p.y - p.y * fi, p.z );
+        }
+    }
+    return g;
+}
+
 template <typename R, bool SH> ACN_HD M3<R> node_rax( const SceneView<R, SH>& sv, int n )
 {
     M3<R> m;
@@ -217,30 +245,7 @@ template <typename R, bool SH> ACN_HD R dist_hit_body( const SceneView<R, SH>& s
     {
         if( nor )
         {
-            V3<R> p = madd( lp, ld, offs1 );
-            V3<R> g;
-            if( sizeof( R ) == 8 )
-            {
-                // the reference's forward differences with step eps (objects.c:947-953)
-                R d0 = dist_fn( kind, ex_radius, p );
-                g.x = ( dist_fn( kind, ex_radius, v3<R>( p.x + eps, p.y, p.z ) ) - d0 ) / eps;
-                g.y = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y + eps, p.z ) ) - d0 ) / eps;
-                g.z = ( dist_fn( kind, ex_radius, v3<R>( p.x, p.y, p.z + eps ) ) - d0 ) / eps;
-            }
-            else
-            {
-                // FP32: a difference quotient over eps would carry ~1e-3 rounding noise; both
-                // distance functions have a closed-form gradient, which the quotient approximates
-                // to O(eps) — use it.  torus: unit vector from the nearest point of the core circle.
-                g = p;
-                if( kind == K_DIST_TORUS )
-                {
-                    R f = r_sqrt( p.x * p.x + p.y * p.y );
-                    R fi = f > R( 0 ) ? R( 1 ) / f : R( 1 );
-                    g = v3<R>( p.x - p.x * fi, p.y - p.y * fi, p.z );
-                }
-            }
-            *nor = unit( tmlv( rax, g ) );
+            *nor = unit( tmlv( rax, dist_gradient( kind, ex_radius, madd( lp, ld, offs1 ), eps ) ) );
         }
         return offs0 + offs1 / inv_scale - eps;
     }

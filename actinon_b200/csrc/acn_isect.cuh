@@ -103,7 +103,29 @@ template <typename R> __device__ __forceinline__ int sphere_events( V3<R> c, R r
     return 0;
 }
 
-template <typename R, bool SH> __device__ __forceinline__ int leaf_events( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, int* s0, R* t0, R* t1 )
+// Crossings of a distance-field object (sphere-traced, objects.c:903-959) beyond ray parameter `from`, at most two per
+// call, and the state at `from`.  A torus has up to four crossings: the program carries a CSG_MORE word behind the
+// leaf that asks for the next two, starting behind the second one.  Each crossing is one march of the reference's
+// own hit function from where the previous one ended (+ eps), which is how its alternating march advances too
+// (objects.c:1087,1244: offs += a + 2 eps).
+template <typename R, bool SH> __device__ __forceinline__ int dist_events( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, R from, int* s0, R* t0, R* t1 )
+{
+    const R inf = Num<R>::inf();
+    Ray<R> r2; r2.d = ray.d; r2.p = madd( ray.p, ray.d, from );
+    *s0 = prim_side( sv, kind, n, r2.p ) < 0 ? 1 : 0;
+    const R a0 = dist_hit( sv, kind, n, r2, ( V3<R>* )nullptr );
+    if( !( a0 < inf ) ) return 0;
+    *t0 = from + a0 + sv.eps;
+    r2.p = madd( ray.p, ray.d, *t0 + sv.eps );
+    const R a1 = dist_hit( sv, kind, n, r2, ( V3<R>* )nullptr );
+    if( !( a1 < inf ) ) return 1;
+    *t1 = *t0 + sv.eps + a1 + sv.eps;
+    return 2;
+}
+
+// DIST: distance-field leaves compiled in (only the MARCH instantiations of the kernels: their register appetite must
+// not touch the lean kernels)
+template <bool DIST, typename R, bool SH> __device__ __forceinline__ int leaf_events( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, int* s0, R* t0, R* t1 )
 {
     const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
     const V3<R> pos = xyz( g0 );
@@ -119,6 +141,7 @@ template <typename R, bool SH> __device__ __forceinline__ int leaf_events( const
         if( tt > R( 0 ) ) { *t0 = tt; return 1; }
         return 0;
     }
+    if( DIST && ( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) ) return dist_events( sv, kind, n, ray, R( 0 ), s0, t0, t1 );
     // squaroid
     const M3<R> rax = node_rax( sv, n );
     const R qa = g0.w, qb = sv.geo[ n * GEO_STRIDE + 1 ].w, qc = sv.geo[ n * GEO_STRIDE + 2 ].w, qr = sv.geo[ n * GEO_STRIDE + 3 ].w;
@@ -145,13 +168,18 @@ template <typename R, bool SH> __device__ __forceinline__ int leaf_events( const
 }
 
 // outward normal of a leaf at ray parameter t (the unshortened crossing), as its fp_ray_hit reports it
-template <typename R, bool SH> __device__ __forceinline__ V3<R> leaf_normal( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, R t )
+template <bool DIST, typename R, bool SH> __device__ __forceinline__ V3<R> leaf_normal( const SceneView<R, SH>& sv, int kind, int n, const Ray<R>& ray, R t )
 {
     const R4<R> g0 = sv.geo[ n * GEO_STRIDE ];
     const V3<R> pos = xyz( g0 );
     if( kind == K_PLANE ) return xyz( sv.geo[ n * GEO_STRIDE + 3 ] );
     if( kind == K_SPHERE ) return unit( madd( ray.p - pos, ray.d, t - sv.eps ) );
     const M3<R> rax = node_rax( sv, n );
+    if( DIST && ( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) )
+    {   // gradient at the end point of the march = the unshortened crossing (objects.c:945-955)
+        const V3<R> lp = mlv( rax, madd( ray.p, ray.d, t ) - pos ) * g0.w;
+        return unit( tmlv( rax, dist_gradient( kind, sv.geo[ n * GEO_STRIDE + 1 ].w, lp, sv.eps ) ) );
+    }
     V3<R> p = mlv( rax, ray.p - pos );
     V3<R> d = mlv( rax, ray.d );
     V3<R> x = madd( p, d, t );
@@ -175,7 +203,7 @@ template <typename R, bool SH> __device__ __forceinline__ int csg_state( const S
         else if( op == CSG_NEG )  stk ^= 1u;
         else if( op == CSG_AND )  { const unsigned int t = stk & 1u; stk >>= 1; stk &= t | ~1u; }
         else if( op == CSG_OR )   { const unsigned int t = stk & 1u; stk >>= 1; stk |= t; }
-        else pc++;                                       // CSG_ENV: a skipped subtree is 0 through its CLIP variable
+        else if( op == CSG_ENV ) pc++;                   // a skipped subtree is 0 through its CLIP variable; CSG_MORE: no effect
     }
     return ( int )( stk & 1u );
 }
@@ -191,7 +219,7 @@ template <typename R> __device__ __forceinline__ void member_interval( int s0, i
 // returns the hit parameter or +inf for a miss.  A ray with more than CSG_E crossings is swept in rounds:
 // each round keeps the CSG_E smallest crossings beyond t_floor; crossings at or before t_floor only
 // toggle their variable (they were swept in an earlier round).
-template <typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R, SH>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
+template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const SceneView<R, SH>& sv, int root, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
                                                              const CsgMem<R>& cm, const R t_far )
 {
     // t_far: the caller's horizon (+ slack).  Crossings beyond it cannot become the reported hit and the state of
@@ -213,6 +241,7 @@ template <typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const Scene
         // subtree; the subtree is skipped only when no lane needs it.  The envelope's own crossings are the
         // CLIP variable's events, so the envelope is intersected once, at the ENV word.
         int skip_to = pr.x;                         // this lane idles while pc < skip_to
+        R more_from = inf;                          // second crossing of the distance-field leaf just classified (CSG_MORE continues there)
         #pragma unroll 1
         for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
         {
@@ -220,7 +249,23 @@ template <typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const Scene
             const int op = ins & 15, n = ins >> 4;
             const bool act = pc >= skip_to;
             R t0 = R( 0 ), t1 = R( 0 ); int s0 = 0, c = 0, id0 = CSG_VIRTUAL, id1 = CSG_VIRTUAL, var = nv;
-            if( op == CSG_LEAF ) { if( act ) { c = leaf_events( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; } nv++; }
+            if( op == CSG_LEAF )
+            {
+                more_from = inf;
+                if( act ) { c = leaf_events<DIST>( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; if( DIST && c == 2 ) more_from = t1; }
+                nv++;
+            }
+            else if( DIST && op == CSG_MORE )
+            {   // crossings 3 and 4 of the distance-field leaf in front (same variable); s0 collects toggles only
+                var = nv - 1;
+                if( act && more_from < t_far )
+                {
+                    int sd;
+                    c = dist_events( sv, node_kind( sv.link[ n ] ), n, ray, more_from + sv.eps, &sd, &t0, &t1 );
+                    id0 = id1 = pc - pr.x;
+                }
+                more_from = inf;
+            }
             else if( op == CSG_RUN )
             {
                 if( act )
@@ -232,7 +277,7 @@ template <typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const Scene
                         const int w = sv.prog[ pc + m ];
                         const int node = w >> 4;
                         R a0 = R( 0 ), a1 = R( 0 ); int ms0;
-                        const int mc = leaf_events( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
+                        const int mc = leaf_events<false>( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
                         if( ( w & 15 ) == CSG_MEMBER_NEG ) ms0 ^= 1;
                         R mlo, mhi;
                         member_interval( ms0, mc, a0, a1, &mlo, &mhi );
@@ -281,7 +326,7 @@ template <typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const Scene
                     if( t < tmax ) { cm.t[ kmax * cm.stride ] = t; cm.iv[ kmax * cm.stride ] = iv; kmin0 = -1; }
                 }
             }
-            vars |= ( unsigned long long )s0 << var;
+            if( DIST && op == CSG_MORE ) vars ^= ( unsigned long long )s0 << var; else vars |= ( unsigned long long )s0 << var;
         }
         // ---- sweep: crossings in order of t until the solid's state flips at a real one
         int id = CSG_VIRTUAL;
@@ -307,7 +352,7 @@ template <typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( const Scene
             if( nor )
             {
                 const int leaf = sv.prog[ pr.x + id ] >> 4;
-                V3<R> nn = leaf_normal( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
+                V3<R> nn = leaf_normal<DIST>( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
                 // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
                 for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
                 {
@@ -343,7 +388,7 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R elem_hit
     const int kind = node_kind( lk );
     R a;
     if( kind == K_PLANE || kind == K_SPHERE || kind == K_SQUAROID ) a = prim_hit( sv, kind, c, ray, nor );
-    else if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval( sv, c, ray, nor, ctx, cm, t_far );
+    else if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval<MARCH>( sv, c, ray, nor, ctx, cm, t_far );
     else if( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) a = dist_hit( sv, kind, c, ray, nor );
     else if( MARCH ) a = march_hit( sv, c, ray, nor, ctx );
     else a = Num<R>::inf();                 // unreachable: such scenes run the MARCH instantiation

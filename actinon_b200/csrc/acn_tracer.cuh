@@ -1316,7 +1316,8 @@ struct CsgBuilder
     std::vector<int> prog, parent;
     std::vector<I4>  prog_ref;
 
-    static bool is_leaf( int k ) { return k == ACN_KIND_PLANE || k == ACN_KIND_SPHERE || k == ACN_KIND_SQUAROID; }
+    static bool is_dist( int k ) { return k == ACN_KIND_DIST_SPHERE || k == ACN_KIND_DIST_TORUS; }
+    static bool is_leaf( int k ) { return k == ACN_KIND_PLANE || k == ACN_KIND_SPHERE || k == ACN_KIND_SQUAROID || is_dist( k ); }
     static bool is_pair( int k ) { return k == ACN_KIND_PAIR_INSIDE || k == ACN_KIND_PAIR_OUTSIDE; }
 
     bool eligible( int n, int guard ) const
@@ -1362,6 +1363,7 @@ struct CsgBuilder
     }
 
     int n_vars = 0;
+    bool has_dist_leaf = false;       // some program has a distance-field leaf: the kernels with that support (MARCH instantiation) are needed
 
     void emit( int n, bool root )
     {
@@ -1370,7 +1372,12 @@ struct CsgBuilder
         size_t skip_slot = 0;
         const int vars_before = n_vars;
         if( clip ) { prog.push_back( CSG_ENV | ( n << 4 ) ); skip_slot = prog.size(); prog.push_back( 0 ); }
-        if( is_leaf( nd.kind ) ) { prog.push_back( CSG_LEAF | ( n << 4 ) ); n_vars++; }
+        if( is_leaf( nd.kind ) )
+        {
+            prog.push_back( CSG_LEAF | ( n << 4 ) ); n_vars++;
+            if( nd.kind == ACN_KIND_DIST_TORUS ) prog.push_back( CSG_MORE | ( n << 4 ) );      // a torus has up to four crossings
+            if( is_dist( nd.kind ) ) has_dist_leaf = true;
+        }
         else if( nd.kind == ACN_KIND_NEG ) { emit( nd.child0, false ); prog.push_back( CSG_NEG | ( n << 4 ) ); }
         else
         {
@@ -1413,7 +1420,7 @@ struct CsgBuilder
             else if( op == CSG_NEG )  stk ^= 1ull;
             else if( op == CSG_AND )  { const unsigned long long t = stk & 1ull; stk >>= 1; stk &= t | ~1ull; }
             else if( op == CSG_OR )   { const unsigned long long t = stk & 1ull; stk >>= 1; stk |= t; }
-            else pc++;
+            else if( op == CSG_ENV ) pc++;
         }
         return ( int )( stk & 1ull );
     }
@@ -1583,6 +1590,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             }
         };
         walk( fs->light_root ); walk( fs->matter_root );
+        if( cb.has_dist_leaf ) march = true;
     }
 
     // ---- materials
