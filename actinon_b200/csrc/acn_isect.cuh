@@ -328,23 +328,63 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
             }
             if( DIST && op == CSG_MORE ) vars ^= ( unsigned long long )s0 << var; else vars |= ( unsigned long long )s0 << var;
         }
-        // ---- sweep: crossings in order of t until the solid's state flips at a real one
+        // ---- sweep: crossings in order of t until the solid's state flips at a real one.
+        // The reference accepts the boundary point of one child when it lies on the wanted side of the OTHER child, and
+        // takes that side at the shortened hit, eps in front of the boundary (objects.c:1063-1078,1220-1235).  A crossing is
+        // therefore judged ALONE against the state eps before it: other crossings closer than eps ahead of it do not
+        // count yet.  That matters where scripts butt pieces together on one cut plane: leaving piece A of A|B into
+        // piece B through their common plane is two crossings at the same t, and the reference reports the seam (the exit
+        // from A is tested against "not yet in B") — a sweep that applied the toggles one after the other saw the seam
+        // or not depending on their order.  Crossings within eps of the first one of their group are judged against the
+        // state before the group.
+        // The grouping is compiled into the full-featured (MARCH) instantiation only; the host selects it for scenes in
+        // which two leaves of one program share a surface (acn_tracer.cuh: CsgBuilder::coincident_leaves).
         int id = CSG_VIRTUAL;
         R tcur = t_floor;
         bool hit = false;
-        for( ;; )
+        if( DIST )
         {
-            const int s2 = csg_state( sv, pr, vars );
-            if( s >= 0 && s2 != s && id != CSG_VIRTUAL ) { hit = true; break; }
-            s = s2;
-            int kmin = kmin0; R tmin = tmin0;
-            if( kmin < 0 ) { tmin = inf; for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } } }
-            kmin0 = -1;                             // only the first crossing is known in advance
-            if( kmin < 0 ) break;
-            const unsigned int iv = cm.iv[ kmin * cm.stride ];
-            cm.t[ kmin * cm.stride ] = inf;
-            vars ^= 1ull << ( iv >> 8 );
-            tcur = tmin; id = ( int )( iv & 255u );
+            R t_group = -inf;
+            unsigned long long vars_pre = vars;
+            int s_pre = 0, s_last = -1;                 // F( vars_pre ); F( vars ) when known, else -1
+            for( ;; )
+            {
+                int kmin = kmin0; R tmin = tmin0;
+                if( kmin < 0 ) { tmin = inf; for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } } }
+                kmin0 = -1;                             // only the first crossing is known in advance
+                if( kmin < 0 ) break;
+                const unsigned int iv = cm.iv[ kmin * cm.stride ];
+                cm.t[ kmin * cm.stride ] = inf;
+                const unsigned long long bit = 1ull << ( iv >> 8 );
+                const bool first = !( tmin < t_group + sv.eps );
+                if( first ) { vars_pre = vars; t_group = tmin; s_pre = s_last >= 0 ? s_last : csg_state( sv, pr, vars_pre ); }
+                vars ^= bit;
+                tcur = tmin; id = ( int )( iv & 255u );
+                s_last = -1;
+                if( id != CSG_VIRTUAL )
+                {
+                    const int s1 = csg_state( sv, pr, vars_pre ^ bit );
+                    if( s1 != s_pre ) { hit = true; break; }
+                    if( first ) s_last = s1;            // vars == vars_pre ^ bit
+                }
+            }
+        }
+        else
+        {
+            for( ;; )
+            {
+                const int s2 = csg_state( sv, pr, vars );
+                if( s >= 0 && s2 != s && id != CSG_VIRTUAL ) { hit = true; break; }
+                s = s2;
+                int kmin = kmin0; R tmin = tmin0;
+                if( kmin < 0 ) { tmin = inf; for( int q = 0; q < ne; q++ ) { const R tq = cm.t[ q * cm.stride ]; if( tq < tmin ) { tmin = tq; kmin = q; } } }
+                kmin0 = -1;                             // only the first crossing is known in advance
+                if( kmin < 0 ) break;
+                const unsigned int iv = cm.iv[ kmin * cm.stride ];
+                cm.t[ kmin * cm.stride ] = inf;
+                vars ^= 1ull << ( iv >> 8 );
+                tcur = tmin; id = ( int )( iv & 255u );
+            }
         }
         if( hit )
         {

@@ -1324,6 +1324,7 @@ struct CsgBuilder
     {
         if( guard > 64 ) return false;
         const acn_flat_node& nd = fs->nodes[ n ];
+        if( is_dist( nd.kind ) && getenv( "ACN_NO_SWEEP_DIST" ) ) return false;      // diagnostics
         if( is_leaf( nd.kind ) ) return true;
         if( is_pair( nd.kind ) ) return eligible( nd.child0, guard + 1 ) && eligible( nd.child1, guard + 1 );
         if( nd.kind == ACN_KIND_NEG ) return eligible( nd.child0, guard + 1 );
@@ -1425,6 +1426,43 @@ struct CsgBuilder
         return ( int )( stk & 1ull );
     }
 
+    // Do two leaves below n lie on one surface (the same plane, the same sphere or quadric)?  Scripts butt the pieces of
+    // a solid together on common cut planes; a ray through such a seam has two crossings at one t, and those must be
+    // judged the way the reference's march judges them (csg_eval, "group of crossings").
+    void leaves_of( int n, int guard, std::vector<int>& out ) const
+    {
+        if( guard > 64 ) return;
+        const acn_flat_node& nd = fs->nodes[ n ];
+        if( is_pair( nd.kind ) ) { leaves_of( nd.child0, guard + 1, out ); leaves_of( nd.child1, guard + 1, out ); }
+        else if( nd.kind == ACN_KIND_NEG || nd.kind == ACN_KIND_SCALE ) leaves_of( nd.child0, guard + 1, out );
+        else out.push_back( n );
+    }
+    bool same_surface( int a, int b ) const
+    {
+        const acn_flat_node& x = fs->nodes[ a ]; const acn_flat_node& y = fs->nodes[ b ];
+        if( x.kind != y.kind ) return false;
+        const double tol = 4e-6;
+        auto near = [ & ]( double p, double q ) { return fabs( p - q ) <= tol * ( 1.0 + fabs( p ) ); };
+        if( x.kind == ACN_KIND_PLANE )
+        {   // same plane: parallel normals (rax row z) and one offset
+            double d = 0, ox = 0, oy = 0;
+            for( int k = 0; k < 3; k++ ) { d += x.rax[ 6 + k ] * y.rax[ 6 + k ]; ox += x.pos[ k ] * x.rax[ 6 + k ]; oy += y.pos[ k ] * x.rax[ 6 + k ]; }
+            return fabs( fabs( d ) - 1.0 ) < 1e-9 && fabs( ox - oy ) <= tol;
+        }
+        for( int k = 0; k < 3; k++ ) if( !near( x.pos[ k ], y.pos[ k ] ) ) return false;
+        for( int k = 0; k < 4; k++ ) if( !near( x.tail[ k ], y.tail[ k ] ) ) return false;
+        if( x.kind == ACN_KIND_SPHERE ) return true;
+        for( int k = 0; k < 9; k++ ) if( !near( x.rax[ k ], y.rax[ k ] ) ) return false;
+        return true;
+    }
+    bool coincident_leaves( int n ) const
+    {
+        std::vector<int> lv; leaves_of( n, 0, lv );
+        for( size_t i = 0; i < lv.size(); i++ ) for( size_t j = i + 1; j < lv.size(); j++ ) if( same_surface( lv[ i ], lv[ j ] ) ) return true;
+        return false;
+    }
+    bool has_coincident = false;      // some swept object has two leaves on one surface: crossings must be judged in groups
+
     int depth( int n, int guard ) const
     {
         if( guard > 64 ) return 64;
@@ -1453,6 +1491,8 @@ struct CsgBuilder
             if( nd.kind == ACN_KIND_COMPOUND ) { visit_compound( n, guard + 1, enable ); continue; }
             set_parents( n, 0 );
             // the bit stack of the interpreter holds 32 levels; a left-deep chain needs 2 however long it is
+            const char* skip = getenv( "ACN_NO_SWEEP_NODE" );       // diagnostics: keep one object on the reference march
+            if( skip && atoi( skip ) == n ) continue;
             if( enable && ( is_pair( nd.kind ) || nd.kind == ACN_KIND_NEG ) && eligible( n, 0 ) && depth( n, 0 ) < 30 && prog_ref[ n ].y == 0 )
             {
                 const size_t mark = prog.size();
@@ -1471,6 +1511,7 @@ struct CsgBuilder
                         prog.insert( prog.end(), tab.begin(), tab.end() );
                     }
                     prog_ref[ n ] = r;
+                    if( coincident_leaves( n ) ) has_coincident = true;
                 }
                 else prog.resize( mark );
             }
@@ -1590,7 +1631,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             }
         };
         walk( fs->light_root ); walk( fs->matter_root );
-        if( cb.has_dist_leaf ) march = true;
+        if( cb.has_dist_leaf || cb.has_coincident ) march = true;      // features compiled into the MARCH instantiation only
     }
 
     // ---- materials
