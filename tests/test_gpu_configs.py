@@ -246,3 +246,28 @@ def test_path_tracing_rmse_against_a_converged_reference_is_no_worse_than_the_cp
     print(f"{name}: RMSE vs 48-spp reference: cpu {rmse_cpu:.5f}, gpu {rmse_gpu:.5f}; channel-mean deviation at 48 spp {dm}")
     assert rmse_gpu <= 1.10 * rmse_cpu
     assert (dm < 5e-3).all()
+
+
+ALL_SCENES = ["caustic_of_caustic", "diamond", "diamond_video_000049", "hanging_lamp", "hanging_lamps_in_row", "many_spheres",
+              "paraffin_lamp", "paraffin_lamp_on_ledge", "primitives", "pyramid", "ruby_heart", "wine_glass"]
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_event_sweep_equals_the_reference_march_on_every_shipped_scene(orc, name):
+    """Every scene script the reference ships (flattened in scenes/), reduced sample counts, a grid of samples: the f64
+    event sweep (csg_mode INTERVALS: variables, crossings, truth tables, convex runs, envelope gates, distance-field
+    leaves, groups of coincident crossings) must find the boundaries the oracle's alternating march finds."""
+    big = name == "hanging_lamps_in_row"
+    flat = acn.scenes.load(name, direct_samples=3 if big else 6, path_samples=2 if big else 4)
+    xy = grid_samples(flat, 24 if big else 48, 24 if big else 48, 0.9)
+    ref, info = orc.render(flat, xy, seed_mode=acn.SEED_INDEX_KEYED)
+    t = acn.Tracer(flat, acn.Options(seed_mode=acn.SEED_INDEX_KEYED, precision=acn.PRECISION_F64, csg_mode=acn.CSG_INTERVALS,
+                                     wave_budget=1 << 18))
+    rgb = t.render_samples(xy)
+    st = t.last_stats
+    t.close()
+    e = rel_err(rgb, ref)
+    b5, b3 = float((e > 1e-5).mean()), float((e > 1e-3).mean())
+    print(f"{name}: sweep-vs-march samples beyond 1e-5: {b5:.4%}, beyond 1e-3: {b3:.4%}; rays {st.rays} vs {info['rays']}")
+    assert b5 <= 0.005 and b3 <= 0.002
+    assert abs(st.rays - info["rays"]) <= max(8, 1e-3 * info["rays"])
