@@ -1632,6 +1632,26 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         };
         walk( fs->light_root ); walk( fs->matter_root );
         if( cb.has_dist_leaf || cb.has_coincident ) march = true;      // features compiled into the MARCH instantiation only
+        if( getenv( "ACN_VERBOSE" ) )
+        {
+            int swept = 0, marched = 0;
+            std::function<void( int )> cnt = [ & ]( int c )
+            {
+                const acn_flat_node& cn = fs->nodes[ c ];
+                for( int i = 0; i < cn.child1; i++ )
+                {
+                    const int e = fs->children[ cn.child0 + i ];
+                    const acn_flat_node& nd = fs->nodes[ e ];
+                    if( nd.kind == ACN_KIND_COMPOUND ) { cnt( e ); continue; }
+                    if( nd.kind < ACN_KIND_PAIR_INSIDE ) continue;
+                    if( cb.prog_ref[ e ].y > 0 ) swept++;
+                    else { marched++; fprintf( stderr, "acn: object %d (kind %d) runs the reference march\n", e, nd.kind ); }
+                }
+            };
+            cnt( fs->light_root ); cnt( fs->matter_root );
+            fprintf( stderr, "acn: %d composite objects swept, %d marched; program words %d; dist leaves %d, coincident surfaces %d -> %s kernels\n",
+                     swept, marched, n_prog, ( int )cb.has_dist_leaf, ( int )cb.has_coincident, march ? "full-featured (MARCH)" : "lean" );
+        }
     }
 
     // ---- materials

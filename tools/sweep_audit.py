@@ -20,4 +20,7 @@ for name in names:
         rgb = t.render_samples(xy); st = t.last_stats; t.close()
         e = rel_err(rgb, ref)
         out.append(f"{tag}: >1e-5 {(e > 1e-5).mean():.4f} >1e-3 {(e > 1e-3).mean():.4f} >1e-2 {(e > 1e-2).mean():.4f} rays {st.rays - info['rays']:+d}")
+    wide, _ = orc.render(flat, xy, seed_mode=acn.SEED_INDEX_KEYED, eps=2e-5)      # the f32 path's shell thickness, in the FP64 oracle
+    ew = rel_err(wide, ref)
+    out.append(f"oracle eps 2e-5: >1e-3 {(ew > 1e-3).mean():.4f} >1e-2 {(ew > 1e-2).mean():.4f}")
     print(" | ".join(out), flush=True)
