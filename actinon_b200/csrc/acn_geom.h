@@ -272,6 +272,38 @@ template <typename R, bool SH> ACN_HD R dist_hit( const SceneView<R, SH>& sv, in
     return h.a;
 }
 
+// Roots ta <= tb of  f t^2 + 2 fs t + fq = 0  for the quadric qa x^2 + qb y^2 + qc z^2 + qr (p, d in the object frame,
+// ad = (qa dx, qb dy, qc dz), f = ad.d != 0).  s*s - q cancels catastrophically in FP32 when the origin is far from the
+// quadric (both terms ~ |p|^2), so the quadratic is re-expanded around the point of closest approach pm = p + t0*d,
+// where its coefficients are of the size of the object.  That needs t0 = -fs/f to be a sensible distance: for cones and
+// hyperboloids (a coefficient < 0) f itself cancels when the ray runs nearly along a generating line, t0 goes to
+// infinity and pm loses the near root.  In FP32 those rays take the textbook cancellation-free form
+// q = -(fs + sign(fs) sqrt(fs^2 - f fq)), roots q/f and fq/q, which stays accurate as f -> 0.
+template <typename R> ACN_HD bool quadric_roots( R qa, R qb, R qc, R qr, V3<R> p, V3<R> d, V3<R> ad, R f, R fs, R fq, R* ta, R* tb )
+{
+    if( sizeof( R ) == 4 && r_abs( f ) < R( 0.05 ) * ( r_abs( ad.x * d.x ) + r_abs( ad.y * d.y ) + r_abs( ad.z * d.z ) ) )
+    {
+        R disc = fs * fs - f * fq;
+        if( disc < R( 0 ) ) return false;
+        R sq = r_sqrt( disc );
+        R qq = -( fs + ( fs < R( 0 ) ? -sq : sq ) );
+        R t1 = qq / f;
+        R t2 = qq != R( 0 ) ? fq / qq : t1;
+        *ta = r_min( t1, t2 ); *tb = r_max( t1, t2 );
+        return true;
+    }
+    R fi = R( 1 ) / f;
+    R t0 = -fs * fi;
+    V3<R> pm = madd( p, d, t0 );
+    R s = dot( ad, pm ) * fi;                                                  // ~ 0
+    R q = ( qa * pm.x * pm.x + qb * pm.y * pm.y + qc * pm.z * pm.z + qr ) * fi;
+    R r = s * s - q;
+    if( r < R( 0 ) ) return false;
+    r = r_sqrt( r );
+    *ta = t0 - s - r; *tb = t0 - s + r;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // primitives: fp_ray_hit of plane / sphere / squaroid / distance objects
 // (gmath.h:38-45, objects.c:529-537,649-657,778-821,903-959).  No envelope test, no roughness.
@@ -312,19 +344,10 @@ template <typename R, bool SH> ACN_HD R prim_hit( const SceneView<R, SH>& sv, in
         R a;
         if( f != R( 0 ) )
         {
-            // s*s - q cancels catastrophically in FP32 when the origin is far from the quadric
-            // (both terms ~ |p|^2): re-expand the quadratic around the point of closest approach
-            // pm = p + t0*d, where its coefficients are of the size of the object.
-            R fi = R( 1 ) / f;
-            R t0 = -fs * fi;
-            V3<R> pm = madd( p, d, t0 );
-            R s = dot( ad, pm ) * fi;                                                  // ~ 0
-            R q = ( qa * pm.x * pm.x + qb * pm.y * pm.y + qc * pm.z * pm.z + qr ) * fi;
-            R r = s * s - q;
-            if( r < R( 0 ) ) return inf;
-            r = r_sqrt( r );
-            a = t0 - s - r;
-            if( a < R( 0 ) ) a = t0 - s + r;
+            R ta, tb;
+            if( !quadric_roots( qa, qb, qc, qr, p, d, ad, f, fs, fq, &ta, &tb ) ) return inf;
+            a = ta;
+            if( a < R( 0 ) ) a = tb;
             if( a < R( 0 ) ) return inf;
         }
         else

@@ -152,15 +152,8 @@ template <bool DIST, typename R, bool SH> __device__ __forceinline__ int leaf_ev
     R fq = qa * p.x * p.x + qb * p.y * p.y + qc * p.z * p.z + qr;
     *s0 = fq > R( 0 ) ? 0 : 1;
     if( f == R( 0 ) ) return 0;
-    R fi = R( 1 ) / f;
-    R tm = -fs * fi;
-    V3<R> pm = madd( p, d, tm );
-    R s = dot( ad, pm ) * fi;
-    R q = ( qa * pm.x * pm.x + qb * pm.y * pm.y + qc * pm.z * pm.z + qr ) * fi;
-    R r = s * s - q;
-    if( r < R( 0 ) ) return 0;
-    r = r_sqrt( r );
-    R ta = tm - s - r, tb = tm - s + r;
+    R ta, tb;
+    if( !quadric_roots( qa, qb, qc, qr, p, d, ad, f, fs, fq, &ta, &tb ) ) return 0;
     int c = 0;
     if( ta >= R( 0 ) ) { *t0 = ta; c = 1; }
     if( tb >= R( 0 ) ) { if( c ) *t1 = tb; else *t0 = tb; c++; }
