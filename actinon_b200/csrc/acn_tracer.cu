@@ -167,6 +167,7 @@ int acn_render_samples( acn_tracer* t, const double* xy, uint64_t n, uint64_t in
     if( !t || ( n && ( !xy || !rgb ) ) ) { set_error( "acn_render_samples: null argument" ); return ACN_ERR_INVALID_ARG; }
     TracerBase* tb = reinterpret_cast<TracerBase*>( t );
     if( n == 0 ) { if( stats ) memset( stats, 0, sizeof( *stats ) ); return ACN_OK; }
+    if( n > 0x7FFFFFFFull ) { set_error( "at most 2^31-1 samples per call" ); return ACN_ERR_INVALID_ARG; }      // before any staging allocation
     ACN_CUDA( cudaSetDevice( tb->device ) );
     if( tb->stage_cap < n )
     {

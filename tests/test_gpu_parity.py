@@ -128,6 +128,27 @@ def test_edge_cases_empty_ragged_and_out_of_frame():
     t.close()
 
 
+def test_maximum_size_and_null_arguments_are_rejected_not_attempted():
+    """More than 2^31-1 samples per call and null buffers come back as ACN_ERR_INVALID_ARG (-1) from both entry points —
+    before any allocation, never as an abort (the reference's only error path is bcore_err_fa, scene.c:1006)."""
+    import ctypes as C
+    import torch
+    flat, xy = full_pass(acn.scenes.primitives(16, 12, 2, 0))
+    t = acn.Tracer(flat, acn.Options())
+    lib = acn.load_library()
+    st = acn.Stats()
+    h_xy = np.zeros((4, 2)); h_rgb = np.zeros((4, 3), dtype=np.float32)
+    d_xy = torch.zeros((4, 2), dtype=torch.float64, device="cuda"); d_rgb = torch.zeros((4, 3), dtype=torch.float32, device="cuda")
+    big = 1 << 31
+    assert lib.acn_render_samples(t._p, h_xy.ctypes.data, big, 0, h_rgb.ctypes.data, None, C.byref(st)) == -1
+    assert lib.acn_render_samples_device(t._p, d_xy.data_ptr(), big, 0, d_rgb.data_ptr(), None, None, C.byref(st)) == -1
+    assert lib.acn_render_samples(t._p, None, 4, 0, h_rgb.ctypes.data, None, C.byref(st)) == -1
+    assert lib.acn_render_samples_device(t._p, d_xy.data_ptr(), 4, 0, None, None, None, C.byref(st)) == -1
+    assert b"2^31" in lib.acn_last_error() or b"null" in lib.acn_last_error()
+    assert np.isfinite(t.render_samples(xy[:4])).all()                     # the handle is still good
+    t.close()
+
+
 def test_tiny_wave_budget_exercises_the_scheduler(orc):
     """A wave budget far below the ray count forces many pops, stack slicing at exact child budgets and
     multiple primary chunks; the result must not change."""
