@@ -149,6 +149,28 @@ def test_maximum_size_and_null_arguments_are_rejected_not_attempted():
     t.close()
 
 
+def test_cancel_flag_abandons_the_pass_like_sigint_in_the_reference():
+    """scene.c:978,1143-1153: workers watch signal_received_g, stop early and the caller discards the pass.  Here the
+    caller's `cancel` flag is polled between wavefront iterations; a set flag ends the call with ACN_ERR_CANCELLED (-6),
+    and the next call on the same handle renders the pass in full."""
+    import ctypes as C
+    flat, xy = full_pass(acn.scenes.primitives(64, 48, 6, 5))              # needs ~17 wavefront iterations
+    t = acn.Tracer(flat, acn.Options(seed_mode=acn.SEED_INDEX_KEYED, wave_budget=4096))
+    lib = acn.load_library()
+    st = acn.Stats()
+    xs = np.ascontiguousarray(xy, dtype=np.float64)
+    rgb = np.zeros((len(xs), 3), dtype=np.float32)
+    flag = C.c_int(1)
+    rc = lib.acn_render_samples(t._p, xs.ctypes.data, len(xs), 0, rgb.ctypes.data, C.cast(C.byref(flag), C.c_void_p), C.byref(st))
+    assert rc == -6
+    flag.value = 0
+    rc = lib.acn_render_samples(t._p, xs.ctypes.data, len(xs), 0, rgb.ctypes.data, C.cast(C.byref(flag), C.c_void_p), C.byref(st))
+    assert rc == 0 and np.isfinite(rgb).all() and rgb.max() > 0
+    ref = t.render_samples(xy)
+    assert np.allclose(rgb, ref, rtol=1e-4, atol=1e-5)
+    t.close()
+
+
 def test_tiny_wave_budget_exercises_the_scheduler(orc):
     """A wave budget far below the ray count forces many pops, stack slicing at exact child budgets and
     multiple primary chunks; the result must not change."""
