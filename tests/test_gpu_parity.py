@@ -48,6 +48,7 @@ SCENES = {
     "primitives_path": lambda: acn.scenes.primitives(96, 72, 10, 4),
     "glass_ball_path": lambda: acn.scenes.glass_ball(64, 48, 6, 3),
     "csg_zoo_path": lambda: acn.scenes.csg_zoo(64, 48, 4, 3),
+    "textures": lambda: scenes_util.chess_floor_and_ball(8, 96, 72),        # §8 a22: chess / plain texture fields, both projections
 }
 
 
@@ -69,6 +70,7 @@ def test_f64_validation_mode_matches_oracle_everywhere(orc, name):
 @pytest.mark.parametrize("name,max_frac_1e3,max_frac_1e2", [
     ("primitives_c1", 0.010, 0.0015), ("glass_ball", 0.015, 0.0030), ("csg_zoo", 0.020, 0.0060),
     ("primitives_path", 0.015, 0.0040), ("glass_ball_path", 0.030, 0.0150), ("csg_zoo_path", 0.035, 0.0200),
+    ("textures", 0.020, 0.0100),               # + pixels on the edges between chess squares (llrint of an f32 coordinate)
 ])
 def test_f32_product_mode_vs_oracle(orc, name, max_frac_1e3, max_frac_1e2):
     flat, xy = full_pass(SCENES[name]())

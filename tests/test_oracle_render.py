@@ -75,3 +75,28 @@ def test_counters_give_flops(orc):
     assert c["rays_primary"] == 32 * 24 and c["camera"] == 32 * 24
     assert info["flops"] > 1000 * 32 * 24 and info["rays"] > 5 * 32 * 24
     assert c["dist_step"] > 0 and c["squaroid"] > 0 and c["plane"] > 0 and c["oren_nayar"] > 0
+
+
+def test_chess_and_plain_textures(orc):
+    """obj_color with a texture field (objects.c:411-422, textures.c:99-102,142-148): the colour of a diffuse hit is the
+    texture's, not prp.color.  Two floor points in neighbouring squares under the same lighting geometry differ exactly
+    by the ratio of the two chess colours; the plain-textured ball shows its texture colour's hue."""
+    sc = scenes_util.chess_floor_and_ball()
+    flat = sc.flatten()
+    W, H = 48, 36
+    ys, xs = np.mgrid[0:H, 0:W]
+    xy = np.stack([(xs + 0.5).ravel(), (ys + 0.5).ravel()], axis=1).astype(np.float64)
+    rgb, info = orc.render(flat, xy, seed_mode=1, want_linear=True)
+    img = info["linear"].reshape(H, W, 3)                                   # before gamma and the clamp to [0,1]
+    np.seterr(divide="ignore", invalid="ignore")                          # shadowed pixels are 0/0 in the ratios below
+    # every floor pixel is a multiple of one of the two chess colours (red-ish (9,1,1) or blue-ish (1,1,9))
+    floor_rows = img[H - 6:, :, :].reshape(-1, 3)
+    r_over_b = floor_rows[:, 0] / floor_rows[:, 2]
+    is_red = np.isclose(r_over_b, 9.0, rtol=1e-6); is_blue = np.isclose(r_over_b, 1.0 / 9.0, rtol=1e-6)
+    assert (is_red | is_blue).all() and is_red.any() and is_blue.any()
+    # plain texture: hue of (0.3, 0.8, 0.8) wherever the ball is hit directly, never the grey prp.color
+    g_over_r = img[:, :, 1] / img[:, :, 0]
+    assert np.isclose(g_over_r, 0.8 / 0.3, rtol=1e-6).sum() > 10
+    # chess ball: both of its colours occur
+    assert np.isclose(img[:, :, 0] / img[:, :, 2], 9.0, rtol=1e-6).sum() > 5          # (0.9, 0.9, 0.1)
+    assert np.isclose(img[:, :, 1] / img[:, :, 0], 6.0, rtol=1e-6).sum() > 5          # (0.1, 0.6, 0.1)
