@@ -118,7 +118,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "acn_options_default", "acn_tracer_create", "acn_tracer_destroy", "acn_render_samples",
     "acn_render_samples_device", "acn_accumulate_device", "acn_last_error", "acn_version", "acn_device_count",
-    "acn_measure_fp32_peak_tflops",
+    "acn_measure_fp32_peak_tflops", "acn_tracer_stream",
     "acn_scene_create", "acn_scene_destroy", "acn_scene_params",
     "acn_create_plane", "acn_create_sphere", "acn_create_squaroid", "acn_create_ellipsoid", "acn_create_cylinder",
     "acn_create_cone", "acn_create_hyperboloid1", "acn_create_hyperboloid2", "acn_create_torus", "acn_create_distance_sphere",
@@ -160,6 +160,7 @@ def load_library():
         "acn_render_samples_device": (I, [V, V, C.c_uint64, C.c_uint64, V, V, V, P(Stats)]),
         "acn_accumulate_device": (I, [V, V, V, C.c_uint64, V, V]),
         "acn_measure_fp32_peak_tflops": (D, [I]),
+        "acn_tracer_stream": (V, [V]),
         "acn_scene_create": (I, [P(V)]), "acn_scene_destroy": (None, [V]), "acn_scene_params": (P(FlatParams), [V]),
         "acn_create_plane": (I, [V]), "acn_create_sphere": (I, [V, D]), "acn_create_squaroid": (I, [V, D, D, D, D]),
         "acn_create_ellipsoid": (I, [V, D, D, D]), "acn_create_cylinder": (I, [V, D, D]), "acn_create_cone": (I, [V, D, D, D]),

@@ -157,8 +157,14 @@ int acn_render_samples_device( acn_tracer* t, const double* d_xy, uint64_t n, ui
 {
     if( !t || ( n && ( !d_xy || !d_rgb ) ) ) { set_error( "acn_render_samples_device: null argument" ); return ACN_ERR_INVALID_ARG; }
     TracerBase* tb = reinterpret_cast<TracerBase*>( t );
-    cudaStream_t st = stream ? ( cudaStream_t )stream : tb->own_stream;
-    return tb->render( d_xy, n, index_base, d_rgb, st, cancel, stats );
+    // stream 0 is what it is everywhere in CUDA: the legacy default stream (which is also PyTorch's default stream), so
+    // the kernels are ordered against the caller's other work on it.  The tracer's private stream: acn_tracer_stream().
+    return tb->render( d_xy, n, index_base, d_rgb, ( cudaStream_t )stream, cancel, stats );
+}
+
+void* acn_tracer_stream( acn_tracer* t )
+{
+    return t ? ( void* )reinterpret_cast<TracerBase*>( t )->own_stream : nullptr;
 }
 
 int acn_render_samples( acn_tracer* t, const double* xy, uint64_t n, uint64_t index_base,
@@ -192,10 +198,8 @@ int acn_accumulate_device( acn_tracer* t, const double* d_xy, const float* d_rgb
     TracerBase* tb = reinterpret_cast<TracerBase*>( t );
     if( n == 0 ) return ACN_OK;
     ACN_CUDA( cudaSetDevice( tb->device ) );
-    cudaStream_t st = stream ? ( cudaStream_t )stream : tb->own_stream;
-    k_accumulate<<< grid_for( n, 256 ), 256, 0, st >>>( d_xy, d_rgb, n, tb->width, tb->height, d_accum );
+    k_accumulate<<< grid_for( n, 256 ), 256, 0, ( cudaStream_t )stream >>>( d_xy, d_rgb, n, tb->width, tb->height, d_accum );
     ACN_CUDA( cudaGetLastError() );
-    if( !stream ) ACN_CUDA( cudaStreamSynchronize( st ) );
     return ACN_OK;
 }
 

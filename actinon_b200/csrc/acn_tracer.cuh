@@ -143,21 +143,21 @@ enum
 struct Sched
 {
     // stacks
-    unsigned long long nr;              // rays on the ray stack
+    unsigned long long nr_a, nr_b;      // rays on the two ends of the ray stack: A = reflection / chromatic (grows up from slot 0),
+                                        // B = refraction (grows down from the last slot)
     unsigned long long nt, nt_cum;      // tasks on the task stack, their outstanding path children
     // plan of the current iteration
-    unsigned long long ray_base;        // new rays are appended at ray_stack[ ray_base + rays_out++ ]
-    unsigned long long ray_take;        // rays popped into ray_cur for k_rays
+    unsigned long long base_a, base_b;  // new rays are appended at A[ base_a + out_a++ ] / B[ base_b + out_b++ ]
+    unsigned long long take_a, take_b;  // rays popped from the top of each end for k_rays (read in place)
     unsigned long long path_blk_lo, path_blk_hi;   // 32-child blocks of the task stack traced by k_path
     unsigned long long path_c_hi;       // first child index beyond the stack top
     unsigned long long path_nt;         // stack height seen by k_path (window bound)
     unsigned long long fix_slot, fix_cum;   // partially consumed task: cum[ fix_slot ] = fix_cum after k_path
     unsigned long long prim_first, prim_count;
     // work cursors of the persistent kernels (units: chunks)
-    unsigned long long cur_pop, cur_rays, cur_path, cur_index, cur_direct, cur_primary, cur_shade;
-    unsigned long long pop_front, pop_back;     // k_pop: rays placed at the front / the back of the wave buffer so far
+    unsigned long long cur_rays, cur_path, cur_index, cur_direct, cur_primary, cur_shade;
     // per-iteration outputs
-    unsigned long long rays_out;        // rays appended
+    unsigned long long out_a, out_b;    // rays appended to each end
     unsigned long long hits;            // hits appended to the hit queue by the tracing kernels
     unsigned long long tasks_new;       // diffuse hits appended to the new-task scratch
     unsigned long long dl_packed;       // direct list: entries << 38 | shadow children
@@ -169,6 +169,10 @@ struct Sched
     int overflow;
 };
 
+template <typename R> struct Acc;
+template <> struct Acc<float>  { typedef unsigned long long T; };
+template <> struct Acc<double> { typedef double T; };
+
 template <typename R> struct Wave       // everything a kernel needs
 {
     DParams<R>  prm;
@@ -176,7 +180,7 @@ template <typename R> struct Wave       // everything a kernel needs
     TaskBuf<R>  tasks_out;    // new-task scratch
     HitBuf<R>   hits_out;     // hit queue
     Sched*      sc;
-    R*          accum;        // per-sample RGB, 3 per sample
+    typename Acc<R>::T* accum; // per-sample sums: r, g, b, saturation flags (4 words per sample)
     unsigned long long rays_cap;
     unsigned long long tasks_cap;
     unsigned long long hits_cap;
@@ -188,8 +192,38 @@ template <typename R> struct Wave       // everything a kernel needs
 // ---------------------------------------------------------------------------------------------
 #define ACN_FULL 0xFFFFFFFFu
 
-__device__ __forceinline__ float atomic_add_r( float* p, float v )   { return atomicAdd( p, v ); }
-__device__ __forceinline__ double atomic_add_r( double* p, double v ) { return atomicAdd( p, v ); }
+// ---------------------------------------------------------------------------------------------
+// Per-sample accumulation.  A sample's colour is the sum of thousands of contributions that arrive in an order the
+// wavefront scheduler decides anew in every run.  The f32 product path therefore sums them as 64-bit FIXED-POINT
+// integers (Q28.36): integer addition is associative, so a sample's value is bit-identical from run to run, whatever
+// the wave budget, the chunking of the work lists or the number of GPUs the image is spread over — the property the
+// multi-GPU accumulation relies on.  Resolution 1.5e-11; a contribution of 1024 or more (the sample
+// saturates to 1 after cl_s_sat anyway) only sets the channel's saturation flag, so the integer cannot wrap.  The FP64
+// validation mode keeps plain double atomics (it is compared with the oracle to 1e-6, not run to run).
+// ---------------------------------------------------------------------------------------------
+#define ACN_ACC_SCALE   68719476736.0f          // 2^36
+#define ACN_ACC_INV     1.4551915228366852e-11  // 2^-36
+#define ACN_ACC_SAT     1024.0f
+__device__ __forceinline__ unsigned long long to_acc( float c, unsigned int* sat, int ch )
+{
+    if( !( c > 0.0f ) ) return 0ull;
+    if( c >= ACN_ACC_SAT ) { *sat |= 1u << ch; return 0ull; }
+    return ( unsigned long long )__float2ll_rn( c * ACN_ACC_SCALE );
+}
+__device__ __forceinline__ double to_acc( double c, unsigned int*, int ) { return c; }
+template <typename R> struct AccV { typename Acc<R>::T x, y, z; unsigned int sat; };
+template <typename R> __device__ __forceinline__ AccV<R> acc_of( V3<R> c )
+{
+    AccV<R> a; a.sat = 0;
+    a.x = to_acc( c.x, &a.sat, 0 ); a.y = to_acc( c.y, &a.sat, 1 ); a.z = to_acc( c.z, &a.sat, 2 );
+    return a;
+}
+template <typename R> __device__ __forceinline__ AccV<R> acc_zero() { AccV<R> a; a.x = a.y = a.z = 0; a.sat = 0; return a; }
+template <typename R> __device__ __forceinline__ bool acc_any( const AccV<R>& a ) { return a.x != 0 || a.y != 0 || a.z != 0 || a.sat != 0; }
+__device__ __forceinline__ void atomic_add_acc( unsigned long long* p, unsigned long long v ) { if( v ) atomicAdd( p, v ); }
+__device__ __forceinline__ void atomic_add_acc( double* p, double v ) { if( v != 0.0 ) atomicAdd( p, v ); }
+__device__ __forceinline__ void atomic_or_acc( unsigned long long* p, unsigned int v ) { atomicOr( p, ( unsigned long long )v ); }
+__device__ __forceinline__ void atomic_or_acc( double*, unsigned int ) {}
 
 // warp-aggregated counter increment: one atomic per converged group
 __device__ __forceinline__ unsigned long long agg_inc( unsigned long long* ctr )
@@ -249,12 +283,32 @@ template <typename T> __device__ __forceinline__ T seg_sum( T v, int key, int la
     return v;
 }
 
+// segmented sum of per-lane contributions over runs of equal keys (non-decreasing over the lanes); valid at the first
+// lane of a run.  Integer (or double) adds: the grouping of the children into warps does not change the total.
+template <typename R> __device__ __forceinline__ AccV<R> seg_sum_acc( AccV<R> v, int key, int lane )
+{
+    #pragma unroll
+    for( int o = 1; o < 32; o <<= 1 )
+    {
+        const int k2 = __shfl_down_sync( ACN_FULL, key, o );
+        const typename Acc<R>::T x2 = __shfl_down_sync( ACN_FULL, v.x, o ), y2 = __shfl_down_sync( ACN_FULL, v.y, o ), z2 = __shfl_down_sync( ACN_FULL, v.z, o );
+        const unsigned int s2 = __shfl_down_sync( ACN_FULL, v.sat, o );
+        if( lane + o < 32 && k2 == key ) { v.x += x2; v.y += y2; v.z += z2; v.sat |= s2; }
+    }
+    return v;
+}
+
+template <typename R> __device__ __forceinline__ void add_sample_acc( const Wave<R>& w, int sample, const AccV<R>& c )
+{
+    typename Acc<R>::T* a = w.accum + 4ull * ( unsigned long long )sample;
+    atomic_add_acc( a + 0, c.x );
+    atomic_add_acc( a + 1, c.y );
+    atomic_add_acc( a + 2, c.z );
+    if( c.sat ) atomic_or_acc( a + 3, c.sat );
+}
 template <typename R> __device__ __forceinline__ void add_sample( const Wave<R>& w, int sample, V3<R> c )
 {
-    R* a = w.accum + 3ull * ( unsigned long long )sample;
-    atomic_add_r( a + 0, c.x );
-    atomic_add_r( a + 1, c.y );
-    atomic_add_r( a + 2, c.z );
+    add_sample_acc( w, sample, acc_of( c ) );
 }
 
 // the node table of the kernel instantiation: SH = true copies it into shared memory (C1/C2/C4: a few KB; the host
@@ -409,32 +463,37 @@ template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const
         if( T && I >= prm.min_intensity ) { do_refr = true; I_refr = I; }                // scene.c:633-653
     }
 
-    // ---- reserve: one atomic per warp for the rays, one for the tasks (k_pop sorts the rays by class later on)
+    // ---- reserve: one atomic per warp and end of the ray stack, one for the tasks.  Reflection and chromatic rays go
+    // to end A of the stack, refraction rays to end B: a k_rays warp then traces 32 rays of one kind (reflections leave
+    // the solid they were born on, refractions cross it: different envelope gates, different numbers of crossings)
+    // without a separate partitioning pass over the wave.
     const unsigned int lt = ( 1u << lane ) - 1u;
-    const unsigned int nr = ( do_refl ? 1u : 0u ) + ( do_chro ? 1u : 0u ) + ( do_refr ? 1u : 0u );
-    unsigned int incl = nr;
-    #pragma unroll
-    for( int o = 1; o < 32; o <<= 1 ) { const unsigned int v = __shfl_up_sync( ACN_FULL, incl, o ); if( lane >= o ) incl += v; }
-    const unsigned int total_r = __shfl_sync( ACN_FULL, incl, 31 );
-    const unsigned int tmask = __ballot_sync( ACN_FULL, do_diff );
-    unsigned long long rbase = 0, tbase = 0;
+    const unsigned int m_refl = __ballot_sync( ACN_FULL, do_refl ), m_chro = __ballot_sync( ACN_FULL, do_chro );
+    const unsigned int m_refr = __ballot_sync( ACN_FULL, do_refr ), tmask = __ballot_sync( ACN_FULL, do_diff );
+    unsigned long long abase = 0, bbase = 0, tbase = 0;
     if( lane == 0 )
     {
-        if( total_r ) rbase = atomicAdd( &w.sc->rays_out, ( unsigned long long )total_r );
+        const unsigned int na = __popc( m_refl ) + __popc( m_chro ), nb = __popc( m_refr );
+        if( na ) abase = atomicAdd( &w.sc->out_a, ( unsigned long long )na );
+        if( nb ) bbase = atomicAdd( &w.sc->out_b, ( unsigned long long )nb );
         if( tmask ) tbase = atomicAdd( &w.sc->tasks_new, ( unsigned long long )__popc( tmask ) );
     }
-    rbase = __shfl_sync( ACN_FULL, rbase, 0 ); tbase = __shfl_sync( ACN_FULL, tbase, 0 );
+    abase = __shfl_sync( ACN_FULL, abase, 0 ); bbase = __shfl_sync( ACN_FULL, bbase, 0 ); tbase = __shfl_sync( ACN_FULL, tbase, 0 );
     if( !live ) return;
-    unsigned long long rslot = w.sc->ray_base + rbase + ( incl - nr );
-    if( nr && rslot + nr > w.rays_cap ) { w.sc->overflow = 1; return; }
+    // slots: end A counts up from slot 0, end B down from the last slot; the two ends must not meet (checked again, for
+    // the whole iteration, by k_sched: a lane only sees its own slots)
+    unsigned long long aslot = w.sc->base_a + abase + __popc( m_refl & lt ) + __popc( m_chro & lt );
+    const unsigned long long bidx = w.sc->base_b + bbase + __popc( m_refr & lt );
+    if( ( ( do_refl || do_chro ) && aslot + 2 > w.rays_cap ) || ( do_refr && bidx >= w.rays_cap ) ) { w.sc->overflow = 1; return; }
+    const unsigned long long bslot = w.rays_cap - 1ull - bidx;
 
     // ---- emit
     if( do_refl )
-        write_ray( w, rslot++, pos, reflect( ray.d, tr.exit_nor ), I_refl, depth - 1, tp, RC_REFLECT, sample, mix64( key, KEY_REFLECT ) );
+        write_ray( w, aslot++, pos, reflect( ray.d, tr.exit_nor ), I_refl, depth - 1, tp, RC_REFLECT, sample, mix64( key, KEY_REFLECT ) );
     if( do_chro )
     {
         V3<R> col = obj_color( prm, sv0, tr.enter_obj, pos );
-        write_ray( w, rslot++, pos, reflect( ray.d, tr.exit_nor ), I_chro, depth - 1, mul( tp, col ), RC_CHROMATIC, sample, mix64( key, KEY_CHROMATIC ) );
+        write_ray( w, aslot++, pos, reflect( ray.d, tr.exit_nor ), I_chro, depth - 1, mul( tp, col ), RC_CHROMATIC, sample, mix64( key, KEY_CHROMATIC ) );
     }
     if( do_diff )
     {
@@ -471,7 +530,7 @@ template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const
         else w.sc->overflow = 2;
     }
     if( do_refr )
-        write_ray( w, rslot++, madd( ray.p, ray.d, a + R( 2 ) * hit_eps ), refract( ray.d, tr.exit_nor, nrel ), I_refr, depth - 1, tp,
+        write_ray( w, bslot, madd( ray.p, ray.d, a + R( 2 ) * hit_eps ), refract( ray.d, tr.exit_nor, nrel ), I_refr, depth - 1, tp,
                    RC_REFRACT, sample, mix64( key, KEY_REFRACT ) );
 }
 
@@ -598,20 +657,20 @@ enum { SCHED_PRIMARY = 0, SCHED_WAVE = 1 };
 
 // one thread: closes the books of the previous iteration and plans the next one
 __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, unsigned long long budget,
-                         unsigned long long ray_min, int mode, unsigned long long prim_first, unsigned long long prim_count )
+                         unsigned long long ray_min, unsigned long long ray_cap, int mode, unsigned long long prim_first, unsigned long long prim_count )
 {
     if( threadIdx.x != 0 || blockIdx.x != 0 ) return;
     // ---- previous iteration
-    unsigned long long nr = s->ray_base + s->rays_out;
+    const unsigned long long nr_a = s->base_a + s->out_a, nr_b = s->base_b + s->out_b, nr = nr_a + nr_b;
+    if( nr > ray_cap && !s->overflow ) s->overflow = 1;            // the two ends of the ray stack met
     unsigned long long nt = s->task_stack >> ACN_TASK_SHIFT, nt_cum = s->task_stack & ACN_TASK_MASK;
     s->stats[ ST_DIFFUSE ] += s->tasks_new;
-    if( s->rays_out | s->tasks_new | s->ray_take | ( s->path_blk_hi - s->path_blk_lo ) | s->prim_count ) s->waves++;
+    if( s->out_a | s->out_b | s->tasks_new | s->take_a | s->take_b | ( s->path_blk_hi - s->path_blk_lo ) | s->prim_count ) s->waves++;
     // dl_packed and cur_direct belong to k_direct, which may still be running on the second stream: k_shade resets them
-    s->rays_out = 0; s->tasks_new = 0; s->hits = 0;
-    s->cur_pop = s->cur_rays = s->cur_path = s->cur_index = s->cur_primary = s->cur_shade = 0;
-    s->pop_front = s->pop_back = 0;
+    s->out_a = s->out_b = 0; s->tasks_new = 0; s->hits = 0;
+    s->cur_rays = s->cur_path = s->cur_index = s->cur_primary = s->cur_shade = 0;
     // ---- plan
-    unsigned long long ray_take = 0, blk_lo = 0, blk_hi = 0, fix_slot = ACN_NONE64, fix_cum = 0;
+    unsigned long long take_a = 0, take_b = 0, blk_lo = 0, blk_hi = 0, fix_slot = ACN_NONE64, fix_cum = 0;
     s->path_nt = nt; s->path_c_hi = nt_cum;
     s->prim_first = prim_first; s->prim_count = 0;
     if( mode == SCHED_PRIMARY )
@@ -621,7 +680,13 @@ __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, uns
     else
     {
         const bool path_avail = nt_cum > 0;
-        if( nr > 0 && ( nr >= ray_min || !path_avail ) ) ray_take = nr < budget ? nr : budget;
+        if( nr > 0 && ( nr >= ray_min || !path_avail ) )
+        {   // the newest rays of both ends; when they exceed the budget each end gets at least half of it
+            take_b = nr_b < budget ? nr_b : budget;
+            const unsigned long long room = budget - take_b, half = budget >> 1;
+            take_a = nr_a < ( room > half ? room : half ) ? nr_a : ( room > half ? room : half );
+            if( take_a + take_b > budget ) take_b = budget - take_a;
+        }
         if( path_avail )
         {
             const unsigned long long c_lo = nt_cum > budget ? ( ( nt_cum - budget ) & ~31ull ) : 0ull;
@@ -633,53 +698,13 @@ __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, uns
             nt = t0 + ( partial ? 1 : 0 ); nt_cum = c_lo;
             s->task_stack = ( nt << ACN_TASK_SHIFT ) | nt_cum;
         }
-        if( ray_take == 0 && !path_avail ) s->done = 1;
+        if( take_a + take_b == 0 && !path_avail ) s->done = 1;
     }
-    if( s->overflow ) { s->done = 1; ray_take = 0; blk_lo = blk_hi = 0; fix_slot = ACN_NONE64; s->prim_count = 0; }
-    s->nr = nr - ray_take; s->nt = nt; s->nt_cum = nt_cum;
-    s->ray_base = nr - ray_take; s->ray_take = ray_take;
+    if( s->overflow ) { s->done = 1; take_a = take_b = 0; blk_lo = blk_hi = 0; fix_slot = ACN_NONE64; s->prim_count = 0; }
+    s->nr_a = nr_a - take_a; s->nr_b = nr_b - take_b; s->nt = nt; s->nt_cum = nt_cum;
+    s->base_a = nr_a - take_a; s->base_b = nr_b - take_b; s->take_a = take_a; s->take_b = take_b;
     s->path_blk_lo = blk_lo; s->path_blk_hi = blk_hi;
     s->fix_slot = fix_slot; s->fix_cum = fix_cum;
-}
-
-// pops the top ray_take rays of the stack into the current-wave buffer, PARTITIONED by class: reflection and
-// chromatic rays fill the buffer from the front, refraction rays from the back.  A k_rays warp then traces 32 rays of
-// one kind (reflections leave the solid they were born on, refractions cross it: different envelope gates, different
-// numbers of crossings), whatever order k_shade emitted them in.  One pair of atomics per block and round.
-template <typename R> __global__ void __launch_bounds__( 256 )
-k_pop( Sched* __restrict__ s, RayBuf<R> stack, RayBuf<R> cur )
-{
-    __shared__ unsigned int w_front[ 8 ], w_back[ 8 ];
-    __shared__ unsigned long long b_front, b_back;
-    const unsigned long long n = s->ray_take, base = s->ray_base;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned int lt = ( 1u << lane ) - 1u;
-    for( unsigned long long i0 = ( unsigned long long )blockIdx.x * blockDim.x; i0 < n; i0 += ( unsigned long long )gridDim.x * blockDim.x )
-    {
-        const unsigned long long i = i0 + threadIdx.x;
-        const bool live = i < n;
-        R4<R> a, b, c; I4 m; m.x = 0;
-        if( live ) { a = stack.o_i[ base + i ]; b = stack.d_[ base + i ]; c = stack.tp[ base + i ]; m = stack.meta[ base + i ]; }
-        const bool back = live && ( ( m.x >> 8 ) & 0xFF ) == RC_REFRACT, front = live && !back;
-        const unsigned int mf = __ballot_sync( ACN_FULL, front ), mb = __ballot_sync( ACN_FULL, back );
-        if( lane == 0 ) { w_front[ wid ] = __popc( mf ); w_back[ wid ] = __popc( mb ); }
-        __syncthreads();
-        if( threadIdx.x == 0 )
-        {
-            unsigned int tf = 0, tb = 0;
-            for( int k = 0; k < 8; k++ ) { const unsigned int f = w_front[ k ], q = w_back[ k ]; w_front[ k ] = tf; w_back[ k ] = tb; tf += f; tb += q; }
-            b_front = tf ? atomicAdd( &s->pop_front, ( unsigned long long )tf ) : 0ull;
-            b_back  = tb ? atomicAdd( &s->pop_back, ( unsigned long long )tb ) : 0ull;
-        }
-        __syncthreads();
-        if( live )
-        {
-            const unsigned long long d = front ? b_front + w_front[ wid ] + __popc( mf & lt )
-                                               : n - 1ull - ( b_back + w_back[ wid ] + __popc( mb & lt ) );
-            cur.o_i[ d ] = a; cur.d_[ d ] = b; cur.tp[ d ] = c; cur.meta[ d ] = m;
-        }
-        __syncthreads();
-    }
 }
 
 // camera rays (scene.c:976-990) fused with their first trace + shade
@@ -723,13 +748,17 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
     warp_count( &w.sc->stats[ ST_PRIMARY ], n_rays, lane );
 }
 
-// explicit rays popped from the ray stack
+// explicit rays, read in place from the tops of the two ends of the ray stack: items [0, pad_a) are the take_a newest
+// rays of end A (reflection / chromatic), padded to a whole number of 32-ray groups so that no warp mixes the kinds,
+// items [pad_a, pad_a + take_b) the take_b newest of end B (refraction).  What k_shade spawns afterwards overwrites them.
 template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
 k_rays( Wave<R> w, RayBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     __shared__ unsigned long long ring_all[ ACN_BLOCK / 32 ][ ACN_PEND ];
-    const unsigned long long count = w.sc->ray_take;
+    const unsigned long long take_a = w.sc->take_a, take_b = w.sc->take_b, pad_a = ( take_a + 31ull ) & ~31ull;
+    const unsigned long long base_a = w.sc->base_a, top_b = w.rays_cap - 1ull - w.sc->base_b;      // slot of B's item j: top_b - j
+    const unsigned long long count = pad_a + take_b;
     if( count == 0 || w.sc->overflow ) return;
     const int chunk = launch_chunk( count >> 5 );
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks
@@ -761,7 +790,8 @@ k_rays( Wave<R> w, RayBuf<R> in )
                 if( c_cur >= count ) { input_done = true; continue; }
             }
             i = c_cur + lane; c_cur += 32;
-            if( i >= count ) i = ACN_NONE64;
+            if( i < pad_a ) i = i < take_a ? base_a + i : ACN_NONE64;                 // the ring and the trace below hold SLOTS
+            else            i = i < count ? top_b - ( i - pad_a ) : ACN_NONE64;
             if( split )
             {
                 bool heavy = false;
@@ -873,7 +903,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
             const bool live = idx < total;
             const int j = window_find( lw.incl, live ? idx : ( blk << 5 ) );
             const unsigned long long prev = __shfl_sync( ACN_FULL, lw.incl, ( j + 31 ) & 31 );
-            V3<R> sum = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+            AccV<R> sum = acc_zero<R>();
             int sample = -1;
             if( live )
             {
@@ -912,7 +942,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
                             R d2 = sqr( hp - v3<R>( lg.pos[ 0 ], lg.pos[ 1 ], lg.pos[ 2 ] ) );
                             R lint = d2 > R( 0 ) ? lg.radiance / d2 : Num<R>::mag();
                             R f = lint * wgt * pi.w * ( R( 2 ) * h / ( R )nd );               // scene.c:574,579
-                            sum = v3<R>( lg.color[ 0 ] * f * tb.x, lg.color[ 1 ] * f * tb.y, lg.color[ 2 ] * f * tb.z );
+                            sum = acc_of( v3<R>( lg.color[ 0 ] * f * tb.x, lg.color[ 1 ] * f * tb.y, lg.color[ 2 ] * f * tb.z ) );
                         }
                     }
                 }
@@ -920,9 +950,12 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
             __syncwarp();
             // one atomic triple per task segment of the block instead of one per shadow ray
             const int key = live ? j : -1;
-            sum.x = seg_sum( sum.x, key, lane ); sum.y = seg_sum( sum.y, key, lane ); sum.z = seg_sum( sum.z, key, lane );
-            const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
-            if( live && ( lane == 0 || kprev != key ) && ( sum.x != R( 0 ) || sum.y != R( 0 ) || sum.z != R( 0 ) ) ) add_sample( w, sample, sum );
+            if( __any_sync( ACN_FULL, acc_any( sum ) ) )
+            {
+                sum = seg_sum_acc( sum, key, lane );
+                const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
+                if( live && ( lane == 0 || kprev != key ) && acc_any( sum ) ) add_sample_acc( w, sample, sum );
+            }
         }
     }
     warp_count( &w.sc->stats[ ST_SHADOW ], n_shadow, lane );
@@ -1023,9 +1056,10 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
         const unsigned int has = __ballot_sync( ACN_FULL, miss != R( 0 ) );
         if( has )
         {
-            miss = seg_sum( miss, key, lane );
+            AccV<R> ms = miss != R( 0 ) ? acc_of( mul( prm.background, tpm ) * miss ) : acc_zero<R>();
+            ms = seg_sum_acc( ms, key, lane );
             const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
-            if( key >= 0 && ( lane == 0 || kprev != key ) && miss != R( 0 ) ) add_sample( w, sample, mul( prm.background, tpm ) * miss );
+            if( key >= 0 && ( lane == 0 || kprev != key ) && acc_any( ms ) ) add_sample_acc( w, sample, ms );
         }
     }
     warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
@@ -1111,11 +1145,18 @@ k_index( Sched* s, TaskBuf<R> in, unsigned long long in_cap, int n_lights,
 }
 
 // cl_s_sat (vectors.h:372-384, scene.c:1010): pow(c, gamma) then clamp, per sample
-template <typename R> __global__ void k_finish( const R* accum, unsigned long long n, R gamma, float* rgb )
+__device__ __forceinline__ float  acc_value( unsigned long long a, unsigned long long flags, int ch, float )
+{
+    return ( ( flags >> ch ) & 1ull ) ? ACN_ACC_SAT : ( float )( ( double )a * ACN_ACC_INV );
+}
+__device__ __forceinline__ double acc_value( double a, double, int, double ) { return a; }
+
+template <typename R> __global__ void k_finish( const typename Acc<R>::T* accum, unsigned long long n, R gamma, float* rgb )
 {
     unsigned long long i = ( unsigned long long )blockIdx.x * blockDim.x + threadIdx.x;
     if( i >= n * 3 ) return;
-    R v = r_pow( accum[ i ], gamma );
+    const unsigned long long smp = i / 3; const int ch = ( int )( i - smp * 3 );
+    R v = r_pow( acc_value( accum[ 4 * smp + ch ], accum[ 4 * smp + 3 ], ch, R( 0 ) ), gamma );
     v = v > R( 0 ) ? ( v < R( 1 ) ? v : R( 1 ) ) : R( 0 );
     rgb[ i ] = ( float )v;
 }
@@ -1144,10 +1185,11 @@ struct TracerBase
                         const volatile int* cancel, acn_stats* stats ) = 0;
     int width = 0, height = 0, device = 0;
     cudaStream_t own_stream = nullptr;
-    // second stream: k_path runs beside k_rays and k_direct beside the next iteration's k_sched/k_pop/k_rays, so the
+    // second stream: k_path runs beside k_rays and k_direct beside the next iteration's k_sched/k_rays, so the
     // tail of one persistent kernel (last warps still tracing) is filled by the blocks of the next
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_sched = nullptr, ev_path = nullptr, ev_index = nullptr, ev_direct = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // device time of a render call
     // staging for the host-pointer entry point
     double* d_xy_stage = nullptr; float* d_rgb_stage = nullptr; uint64_t stage_cap = 0;
 };
@@ -1219,14 +1261,14 @@ template <typename R> struct Tracer : TracerBase
     DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
     // queues
-    RayBuf<R>  ray_stack, ray_cur;
+    RayBuf<R>  ray_stack;
     TaskBuf<R> task_stack, task_new;
     HitBuf<R>  hit_q;
     u64* d_dl_cum = nullptr; unsigned int* d_dl_slot = nullptr; unsigned int* d_dl_dir = nullptr; unsigned int* d_pdir = nullptr;
     uint64_t   budget = 0, ray_min = 0, ray_cap = 0, task_stack_cap = 0, task_new_cap = 0, dl_dir_cap = 0, pdir_cap = 0, prim_chunk = 0;
     Sched*     d_sc = nullptr;
     Sched*     h_sc = nullptr;        // pinned
-    R*         d_accum = nullptr; uint64_t accum_cap = 0;
+    typename Acc<R>::T* d_accum = nullptr; uint64_t accum_cap = 0;
     int        smem_bytes = 0;
     int        max_csg_depth = 0;
     int        grid_trace[ 5 ] = { 0, 0, 0, 0, 0 };   // persistent grids: primary, rays, path, direct, shade
@@ -1249,7 +1291,7 @@ template <typename R> struct Tracer : TracerBase
         cudaFree( d_env ); cudaFree( d_link ); cudaFree( d_geo ); cudaFree( d_children ); cudaFree( d_crec );
         cudaFree( d_prog ); cudaFree( d_prog_ref ); cudaFree( d_parent );
         cudaFree( d_mats ); cudaFree( d_lights ); cudaFree( d_skipA ); cudaFree( d_skipC );
-        free_rays( ray_stack ); free_rays( ray_cur );
+        free_rays( ray_stack );
         free_tasks( task_stack ); free_tasks( task_new ); free_hits( hit_q );
         cudaFree( d_dl_cum ); cudaFree( d_dl_slot ); cudaFree( d_dl_dir ); cudaFree( d_pdir );
         cudaFree( d_sc ); if( h_sc ) cudaFreeHost( h_sc );
@@ -1258,6 +1300,7 @@ template <typename R> struct Tracer : TracerBase
         if( side_stream ) cudaStreamDestroy( side_stream );
         if( ev_sched ) cudaEventDestroy( ev_sched ); if( ev_path ) cudaEventDestroy( ev_path );
         if( ev_index ) cudaEventDestroy( ev_index ); if( ev_direct ) cudaEventDestroy( ev_direct );
+        if( ev_t0 ) cudaEventDestroy( ev_t0 ); if( ev_t1 ) cudaEventDestroy( ev_t1 );
     }
 
     int init( const acn_flat_scene* fs, const acn_options* opt );
@@ -1585,6 +1628,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     ACN_CUDA( cudaEventCreateWithFlags( &ev_path, cudaEventDisableTiming ) );
     ACN_CUDA( cudaEventCreateWithFlags( &ev_index, cudaEventDisableTiming ) );
     ACN_CUDA( cudaEventCreateWithFlags( &ev_direct, cudaEventDisableTiming ) );
+    ACN_CUDA( cudaEventCreate( &ev_t0 ) ); ACN_CUDA( cudaEventCreate( &ev_t1 ) );
 
     if( ( rc = dev_alloc( &d_env, n ) ) ) return rc;
     if( ( rc = dev_alloc( &d_link, n ) ) ) return rc;
@@ -1846,7 +1890,6 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         if( prim_chunk > lim ) prim_chunk = lim > 32 ? lim : 32;
     }
     if( ( rc = alloc_rays( ray_stack, ray_cap ) ) ) return rc;
-    if( ( rc = alloc_rays( ray_cur, budget ) ) ) return rc;
     if( ( rc = alloc_tasks( task_stack, task_stack_cap ) ) ) return rc;
     if( ( rc = alloc_tasks( task_new, task_new_cap ) ) ) return rc;
     if( ( rc = alloc_hits( hit_q, task_new_cap ) ) ) return rc;
@@ -1885,14 +1928,13 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     if( accum_cap < n )
     {
         cudaFree( d_accum ); d_accum = nullptr; accum_cap = 0;
-        int rc = dev_alloc( &d_accum, ( size_t )n * 3 );
+        int rc = dev_alloc( &d_accum, ( size_t )n * 4 );
         if( rc ) return rc;
         accum_cap = n;
     }
-    cudaEvent_t ev0, ev1;
-    ACN_CUDA( cudaEventCreate( &ev0 ) ); ACN_CUDA( cudaEventCreate( &ev1 ) );
+    const cudaEvent_t ev0 = ev_t0, ev1 = ev_t1;
     ACN_CUDA( cudaEventRecord( ev0, st ) );
-    ACN_CUDA( cudaMemsetAsync( d_accum, 0, ( size_t )n * 3 * sizeof( R ), st ) );
+    ACN_CUDA( cudaMemsetAsync( d_accum, 0, ( size_t )n * 4 * sizeof( typename Acc<R>::T ), st ) );
     ACN_CUDA( cudaMemsetAsync( d_sc, 0, sizeof( Sched ), st ) );
 
     uint64_t launches = 0;
@@ -1907,7 +1949,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
 
     // one k_sched + the kernels it planned; nothing here depends on device-side counts.  Two streams (unless the
     // per-kernel timing is on, which needs the kernels one after the other):
-    //   st    k_sched  k_pop  k_rays ............. | k_shade  k_index
+    //   st    k_sched  k_rays .................... | k_shade  k_index
     //   s2    [k_direct of the previous iteration]  k_path   |                  k_direct
     // k_path needs k_sched's plan; k_shade needs the hits of k_rays and k_path and — because it clears the direct list
     // and k_index rebuilds it — the previous k_direct, which precedes k_path on s2; k_direct needs k_index.
@@ -1917,7 +1959,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     auto enqueue = [ & ]( int mode, uint64_t first, uint64_t cnt )
     {
         kp_begin( 6 );
-        k_sched<<< 1, 32, 0, st >>>( d_sc, task_stack.cum, d_pdir, budget, ray_min, mode, first, cnt );
+        k_sched<<< 1, 32, 0, st >>>( d_sc, task_stack.cum, d_pdir, budget, ray_min, ray_cap, mode, first, cnt );
         launches++;
         if( mode == SCHED_PRIMARY )
         {
@@ -1931,16 +1973,15 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         else
         {
             if( two ) { cudaEventRecord( ev_sched, st ); cudaStreamWaitEvent( s2, ev_sched, 0 ); }
-            k_pop<R><<< grid_util, 256, 0, st >>>( d_sc, ray_stack, ray_cur );
             kp_end( 6 );
             kp_begin( 1 );
-            kp_rays<<< grid_trace[ 1 ], ACN_BLOCK, smem_bytes, st >>>( w, ray_cur );
+            kp_rays<<< grid_trace[ 1 ], ACN_BLOCK, smem_bytes, st >>>( w, ray_stack );
             kp_end( 1 );
             kp_begin( 2 );
             kp_path<<< grid_trace[ 2 ], ACN_BLOCK, smem_bytes, s2 >>>( w, task_stack, d_pdir );
             kp_end( 2 );
             if( two ) { cudaEventRecord( ev_path, s2 ); cudaStreamWaitEvent( st, ev_path, 0 ); }
-            launches += 3;
+            launches += 2;
         }
         kp_begin( 4 );
         kp_shade<<< grid_trace[ 4 ], ACN_BLOCK, smem_bytes, st >>>( w, hit_q );
@@ -1968,8 +2009,9 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         {
             if( polls > ( 1ull << 22 ) ) { set_error( "wavefront scheduler did not terminate" ); result = ACN_ERR_CUDA; break; }   // cannot happen; never spin forever
             for( int k = 0; k < iters_per_poll; k++ ) enqueue( SCHED_WAVE, 0, 0 );
-            ACN_CUDA( cudaMemcpyAsync( h_sc, d_sc, sizeof( Sched ), cudaMemcpyDeviceToHost, st ) );
-            ACN_CUDA( cudaStreamSynchronize( st ) );
+            cudaError_t ce = cudaMemcpyAsync( h_sc, d_sc, sizeof( Sched ), cudaMemcpyDeviceToHost, st );
+            if( ce == cudaSuccess ) ce = cudaStreamSynchronize( st );
+            if( ce != cudaSuccess ) { set_error( "wavefront iteration failed: %s", cudaGetErrorString( ce ) ); result = ACN_ERR_CUDA; break; }
             if( h_sc->overflow )
             {
                 set_error( "wavefront queue overflow (code %d): change acn_options.wave_budget", h_sc->overflow );
@@ -1986,13 +2028,16 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         k_finish<R><<< grid_for( n * 3, 256 ), 256, 0, st >>>( d_accum, n, prm.gamma, d_rgb );
         launches++;
     }
-    ACN_CUDA( cudaMemcpyAsync( h_sc, d_sc, sizeof( Sched ), cudaMemcpyDeviceToHost, st ) );
-    ACN_CUDA( cudaEventRecord( ev1, st ) );
-    ACN_CUDA( cudaStreamSynchronize( st ) );
+    // single exit: whatever happened above, both streams are drained before the call returns (a k_direct still pending
+    // on the side stream must not meet the next call's memsets)
+    cudaMemcpyAsync( h_sc, d_sc, sizeof( Sched ), cudaMemcpyDeviceToHost, st );
+    cudaEventRecord( ev1, st );
+    cudaError_t se = cudaStreamSynchronize( st );
+    if( two ) { const cudaError_t s2e = cudaStreamSynchronize( side_stream ); if( se == cudaSuccess ) se = s2e; }
+    if( se != cudaSuccess && result == ACN_OK ) { set_error( "render: %s", cudaGetErrorString( se ) ); result = ACN_ERR_CUDA; }
     cudaError_t le = cudaGetLastError();
     if( le != cudaSuccess ) { set_error( "kernel failure: %s", cudaGetErrorString( le ) ); result = ACN_ERR_CUDA; }
     float ms = 0; cudaEventElapsedTime( &ms, ev0, ev1 );
-    cudaEventDestroy( ev0 ); cudaEventDestroy( ev1 );
     if( stats )
     {
         const unsigned long long* ss = h_sc->stats;

@@ -214,7 +214,9 @@ int acn_render_samples( acn_tracer* t, const double* xy, uint64_t n, uint64_t in
                         float* rgb, const volatile int* cancel, acn_stats* stats );
 
 /* Same, with xy and rgb resident in device memory (used by the benchmark's device-resident leg
- * and by the multi-GPU accumulation path).  stream is a cudaStream_t cast to void* (0: default). */
+ * and by the multi-GPU accumulation path).  stream is a cudaStream_t cast to void*; 0 is CUDA's legacy
+ * default stream (also PyTorch's default stream), so the work is ordered against whatever else the caller
+ * enqueued there.  The call returns when the samples are traced (the wavefront scheduler is polled). */
 int acn_render_samples_device( acn_tracer* t, const double* d_xy, uint64_t n, uint64_t index_base,
                                float* d_rgb, void* stream, const volatile int* cancel, acn_stats* stats );
 
@@ -223,6 +225,9 @@ int acn_render_samples_device( acn_tracer* t, const double* d_xy, uint64_t n, ui
  * the sample position.  d_accum is a device pointer (reduced across GPUs by the caller, NCCL). */
 int acn_accumulate_device( acn_tracer* t, const double* d_xy, const float* d_rgb, uint64_t n,
                            float* d_accum, void* stream );
+
+/* The tracer's private non-blocking stream (cudaStream_t as void*), the one acn_render_samples uses. */
+void* acn_tracer_stream( acn_tracer* t );
 
 const char* acn_last_error( void );
 const char* acn_version( void );
