@@ -31,6 +31,10 @@ from .api import (  # noqa: F401
     CSG_AUTO,
     CSG_INTERVALS,
     CSG_MARCH,
+    SPECIALIZE_AUTO,
+    SPECIALIZE_ON,
+    SPECIALIZE_OFF,
+    spec_probe,
 )
 from . import scenes  # noqa: F401
 
@@ -38,5 +42,5 @@ __all__ = [
     "AcnError", "FlatScene", "Image", "Options", "Scene", "Stats", "Tracer", "device_count",
     "library_path", "load_library", "lum_machine_run", "measure_fp32_peak_tflops", "render_image",
     "scenes", "SEED_POSITION_HASH", "SEED_INDEX_KEYED", "PRECISION_F32", "PRECISION_F64",
-    "CSG_AUTO", "CSG_INTERVALS", "CSG_MARCH",
+    "CSG_AUTO", "CSG_INTERVALS", "CSG_MARCH", "SPECIALIZE_AUTO", "SPECIALIZE_ON", "SPECIALIZE_OFF", "spec_probe",
 ]

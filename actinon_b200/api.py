@@ -25,6 +25,7 @@ SEED_INDEX_KEYED = 1
 PRECISION_F32 = 0
 PRECISION_F64 = 1
 CSG_AUTO, CSG_INTERVALS, CSG_MARCH = 0, 1, 2
+SPECIALIZE_AUTO, SPECIALIZE_ON, SPECIALIZE_OFF = 0, 1, 2
 
 (KIND_COMPOUND, KIND_PLANE, KIND_SPHERE, KIND_SQUAROID, KIND_DIST_SPHERE, KIND_DIST_TORUS,
  KIND_PAIR_INSIDE, KIND_PAIR_OUTSIDE, KIND_NEG, KIND_SCALE) = range(10)
@@ -84,12 +85,15 @@ class Options(C.Structure):
     _fields_ = [
         ("seed_mode", C.c_int32), ("precision", C.c_int32), ("eps", C.c_double),
         ("wave_budget", C.c_int64), ("device", C.c_int32), ("csg_mode", C.c_int32),
+        ("specialize", C.c_int32), ("reserved", C.c_int32),
     ]
 
-    def __init__(self, seed_mode=SEED_POSITION_HASH, precision=PRECISION_F32, eps=0.0, wave_budget=0, device=-1, csg_mode=0):
+    def __init__(self, seed_mode=SEED_POSITION_HASH, precision=PRECISION_F32, eps=0.0, wave_budget=0, device=-1, csg_mode=0,
+                 specialize=0):
         super().__init__()
         self.seed_mode, self.precision, self.eps, self.wave_budget, self.device = seed_mode, precision, eps, wave_budget, device
         self.csg_mode = csg_mode
+        self.specialize = specialize       # SPECIALIZE_AUTO / _ON / _OFF: kernels compiled for this scene's structure (NVRTC)
 
 
 class Stats(C.Structure):
@@ -118,7 +122,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     "acn_options_default", "acn_tracer_create", "acn_tracer_destroy", "acn_render_samples",
     "acn_render_samples_device", "acn_accumulate_device", "acn_last_error", "acn_version", "acn_device_count",
-    "acn_measure_fp32_peak_tflops", "acn_tracer_stream",
+    "acn_measure_fp32_peak_tflops", "acn_tracer_stream", "acn_spec_probe",
     "acn_scene_create", "acn_scene_destroy", "acn_scene_params",
     "acn_create_plane", "acn_create_sphere", "acn_create_squaroid", "acn_create_ellipsoid", "acn_create_cylinder",
     "acn_create_cone", "acn_create_hyperboloid1", "acn_create_hyperboloid2", "acn_create_torus", "acn_create_distance_sphere",
@@ -161,6 +165,7 @@ def load_library():
         "acn_accumulate_device": (I, [V, V, V, C.c_uint64, V, V]),
         "acn_measure_fp32_peak_tflops": (D, [I]),
         "acn_tracer_stream": (V, [V]),
+        "acn_spec_probe": (I, [P(FlatSceneStruct), P(Options), I, C.c_char_p, C.c_uint64, P(C.c_uint64), P(D)]),
         "acn_scene_create": (I, [P(V)]), "acn_scene_destroy": (None, [V]), "acn_scene_params": (P(FlatParams), [V]),
         "acn_create_plane": (I, [V]), "acn_create_sphere": (I, [V, D]), "acn_create_squaroid": (I, [V, D, D, D, D]),
         "acn_create_ellipsoid": (I, [V, D, D, D]), "acn_create_cylinder": (I, [V, D, D]), "acn_create_cone": (I, [V, D, D, D]),
@@ -202,6 +207,19 @@ def _check(rc: int):
     if rc < 0:
         raise AcnError(rc, load_library().acn_last_error().decode("utf-8", "replace"))
     return rc
+
+
+def spec_probe(flat: "FlatScene", options: Optional["Options"] = None, compile: bool = False):
+    """The source the run-time specialiser writes for a scene's structure ('' if the scene does not qualify) and, with
+    compile=True, the NVRTC compile time in seconds.  Needs no GPU (NVRTC cross-compiles for sm_100a)."""
+    lib = load_library()
+    options = options or Options()
+    cap = 1 << 22
+    buf = C.create_string_buffer(cap)
+    n = C.c_uint64(0)
+    sec = C.c_double(0)
+    _check(lib.acn_spec_probe(flat.ptr, C.byref(options), 1 if compile else 0, buf, cap, C.byref(n), C.byref(sec)))
+    return buf.raw[: n.value].decode(), sec.value
 
 
 def device_count() -> int:

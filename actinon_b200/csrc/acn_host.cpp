@@ -404,6 +404,14 @@ int acn_image_add_sums( acn_image* im, const double* sums )
     return ACN_OK;
 }
 
+int acn_image_set_state( acn_image* im, int32_t cycle, uint64_t rval, const double* sums )
+{
+    if( !im || !sums || cycle < 0 ) return ACN_ERR_INVALID_ARG;
+    memcpy( im->arr.data(), sums, im->arr.size() * sizeof( double ) );
+    im->cycle = cycle; im->rval = im->rval_next = rval;
+    return ACN_OK;
+}
+
 int acn_image_write_pnm( const acn_image* im, const char* path, uint64_t* hash )
 {
     if( !im ) return ACN_ERR_INVALID_ARG;

@@ -209,6 +209,29 @@ template <typename R> __device__ __forceinline__ void member_interval( int s0, i
     else     { *lo = c >= 1 ? t0 : inf; *hi = c == 2 ? t1 : inf; }
 }
 
+// the crossing at tcur of the leaf with program-relative id `id` is the first boundary of the solid `root`: the hit
+// distance (shortened by eps, as every fp_ray_hit reports it) and, if asked for, the normal of the leaf carried up the tree
+template <bool DIST, typename R, bool SH> __device__ __forceinline__ R csg_report_hit( const SceneView<R, SH>& sv, int root, int prog_start, const Ray<R>& ray, R tcur, int id,
+                                                                                      V3<R>* nor, HitCtx ctx )
+{
+    const R a = tcur - sv.eps;
+    if( nor )
+    {
+        const int leaf = sv.prog[ prog_start + id ] >> 4;
+        V3<R> nn = leaf_normal<DIST>( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
+        // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
+        for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
+        {
+            const I4 lk = sv.link[ m ];
+            if( node_kind( lk ) == K_NEG ) nn = -nn;
+            if( node_flags( lk ) & F_ROUGH ) roughen( sv, m, ray, a, &nn, ctx );
+        }
+        if( node_kind( sv.link[ root ] ) == K_NEG ) nn = -nn;
+        *nor = nn;
+    }
+    return a;
+}
+
 // returns the hit parameter or +inf for a miss.  A ray with more than CSG_E crossings is swept in rounds:
 // each round keeps the CSG_E smallest crossings beyond t_floor; crossings at or before t_floor only
 // toggle their variable (they were swept in an earlier round).
@@ -379,25 +402,7 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
                 tcur = tmin; id = ( int )( iv & 255u );
             }
         }
-        if( hit )
-        {
-            const R a = tcur - sv.eps;
-            if( nor )
-            {
-                const int leaf = sv.prog[ pr.x + id ] >> 4;
-                V3<R> nn = leaf_normal<DIST>( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
-                // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
-                for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
-                {
-                    const I4 lk = sv.link[ m ];
-                    if( node_kind( lk ) == K_NEG ) nn = -nn;
-                    if( node_flags( lk ) & F_ROUGH ) roughen( sv, m, ray, a, &nn, ctx );
-                }
-                if( node_kind( sv.link[ root ] ) == K_NEG ) nn = -nn;
-                *nor = nn;
-            }
-            return a;
-        }
+        if( hit ) return csg_report_hit<DIST>( sv, root, pr.x, ray, tcur, id, nor, ctx );
         if( !dropped ) break;
         t_floor = tcur;                         // every kept crossing was swept: go on beyond the last one
     }
@@ -539,6 +544,24 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
         if( min_a < best ) { best = min_a; if( want_trans ) *trans = tl; }
     }
     return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scene-specialised build (NVRTC, acn_spec.h): the generated header restates the structure of ONE scene — its top-level
+// element lists and its CSG programs — as straight-line code over the same leaf functions, and replaces scene_query.
+// ---------------------------------------------------------------------------------------------
+#if defined(ACN_SPEC)
+#include "acn_spec_gen.h"
+#endif
+
+template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,
+                                                                      Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
+{
+#if defined(ACN_SPEC_SCENE)
+    return spec_scene_query<R, MARCH, SH>( sv, ray, flags, t_far, trans, ctx, cm );
+#else
+    return scene_query<R, MARCH, SH>( sv, ray, flags, t_far, trans, ctx, cm );
+#endif
 }
 
 } // namespace acn

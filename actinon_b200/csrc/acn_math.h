@@ -6,8 +6,19 @@
 // Oren-Nayar, rsqrt normalisation), not transcribed.
 #pragma once
 
+#if defined(__CUDACC_RTC__)
+// run-time compilation (NVRTC, acn_spec.h): no host headers; the math functions are built in
+typedef unsigned long long uint64_t;
+typedef long long          int64_t;
+typedef unsigned int       uint32_t;
+typedef int                int32_t;
+#ifndef INFINITY
+#define INFINITY ( __int_as_float( 0x7f800000 ) )
+#endif
+#else
 #include <stdint.h>
 #include <math.h>
+#endif
 
 #if defined(__CUDACC__)
 #define ACN_HD  __host__ __device__ __forceinline__

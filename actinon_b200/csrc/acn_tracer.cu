@@ -2,6 +2,7 @@
 // There is deliberately no CPU rendering path in this library: without a CUDA device every
 // tracer entry point fails with ACN_ERR_NO_DEVICE.
 #include "acn_tracer.cuh"
+#include "acn_dimage.cuh"
 
 #include <stdarg.h>
 #include <mutex>
@@ -90,6 +91,9 @@ __global__ void __launch_bounds__( 256 ) k_fma_peak( float* out, int iters, floa
 
 using namespace acn;
 
+static_assert( TEX_NONE == ACN_TEX_NONE && TEX_PLAIN == ACN_TEX_PLAIN && TEX_CHESS == ACN_TEX_CHESS, "texture kinds of the device code = C ABI" );
+static_assert( K_COMPOUND == ACN_KIND_COMPOUND && K_PLANE == ACN_KIND_PLANE && K_SCALE == ACN_KIND_SCALE, "node kinds of the device code = C ABI" );
+
 extern "C" {
 
 const char* acn_last_error( void ) { return g_error; }
@@ -105,6 +109,7 @@ void acn_options_default( acn_options* opt )
     opt->wave_budget = 0;
     opt->device = -1;
     opt->csg_mode = ACN_CSG_AUTO;
+    opt->specialize = ACN_SPECIALIZE_AUTO;
 }
 
 int acn_device_count( void )
@@ -162,6 +167,30 @@ int acn_render_samples_device( acn_tracer* t, const double* d_xy, uint64_t n, ui
     return tb->render( d_xy, n, index_base, d_rgb, ( cudaStream_t )stream, cancel, stats );
 }
 
+int acn_spec_probe( const acn_flat_scene* scene, const acn_options* opt, int compile, char* src, uint64_t cap, uint64_t* len, double* seconds )
+{
+    if( !scene ) { set_error( "acn_spec_probe: null scene" ); return ACN_ERR_INVALID_ARG; }
+    acn_options o;
+    if( opt ) o = *opt; else acn_options_default( &o );
+    int rc = validate_flat_scene( scene );
+    if( rc ) return rc;
+    const bool f64 = o.precision == ACN_PRECISION_F64;
+    CsgBuilder cb;
+    cb.build( scene, o.csg_mode == ACN_CSG_INTERVALS || ( o.csg_mode == ACN_CSG_AUTO && !f64 ) );
+    const SpecPlan pl = f64 ? plan_spec<double>( scene, cb ) : plan_spec<float>( scene, cb );
+    if( len ) *len = pl.src.size();
+    if( seconds ) *seconds = 0;
+    if( src && cap ) { const size_t k = pl.src.size() < cap - 1 ? pl.src.size() : ( size_t )cap - 1; memcpy( src, pl.src.data(), k ); src[ k ] = 0; }
+    if( compile && !pl.src.empty() )
+    {
+        const char* xo = getenv( "ACN_SPEC_OPTS" );
+        std::shared_ptr<SpecBinary> bin = spec_compile( pl.src, f64, pl.march, pl.sh, "sm_100a", xo ? xo : "" );
+        if( !bin ) return ACN_ERR_UNSUPPORTED;
+        if( seconds ) *seconds = bin->compile_seconds;
+    }
+    return ACN_OK;
+}
+
 void* acn_tracer_stream( acn_tracer* t )
 {
     return t ? ( void* )reinterpret_cast<TracerBase*>( t )->own_stream : nullptr;
@@ -200,6 +229,172 @@ int acn_accumulate_device( acn_tracer* t, const double* d_xy, const float* d_rgb
     ACN_CUDA( cudaSetDevice( tb->device ) );
     k_accumulate<<< grid_for( n, 256 ), 256, 0, ( cudaStream_t )stream >>>( d_xy, d_rgb, n, tb->width, tb->height, d_accum );
     ACN_CUDA( cudaGetLastError() );
+    return ACN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident image + pass controller (acn_dimage.cuh)
+// ---------------------------------------------------------------------------------------------
+int acn_dimage_create( int device, int32_t width, int32_t height, acn_dimage** out )
+{
+    if( !out || width <= 0 || height <= 0 || ( int64_t )width * height >= ( 1ll << 31 ) ) { set_error( "acn_dimage_create: bad arguments" ); return ACN_ERR_INVALID_ARG; }
+    *out = nullptr;
+    int nd = acn_device_count();
+    if( nd < 0 ) return nd;
+    if( device < 0 ) { if( cudaGetDevice( &device ) != cudaSuccess ) device = 0; }
+    if( device >= nd ) { set_error( "device %d out of range (%d devices)", device, nd ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( device ) );
+    DImage* di = new DImage();
+    di->device = device; di->width = width; di->height = height;
+    int rc = ACN_OK;
+    if( !rc ) rc = dev_alloc( &di->d_tot, di->words() );
+    if( !rc ) rc = dev_alloc( &di->d_delta, di->words() );
+    if( !rc ) rc = dev_alloc( &di->d_cnt, ( size_t )width * height );
+    if( !rc ) rc = dev_alloc( &di->d_blk, ( size_t )di->blocks() );
+    if( !rc ) rc = dev_alloc( &di->d_counts, 2 );
+    if( !rc && cudaMallocHost( ( void** )&di->h_counts, 2 * sizeof( unsigned long long ) ) != cudaSuccess ) rc = ACN_ERR_OUT_OF_MEMORY;
+    if( !rc && cudaStreamCreateWithFlags( &di->stream, cudaStreamNonBlocking ) != cudaSuccess ) rc = ACN_ERR_CUDA;
+    if( !rc && ( cudaMemset( di->d_tot, 0, di->words() * 8 ) != cudaSuccess || cudaMemset( di->d_delta, 0, di->words() * 8 ) != cudaSuccess ) ) rc = ACN_ERR_CUDA;
+    if( rc ) { delete di; return rc; }
+    *out = reinterpret_cast<acn_dimage*>( di );
+    return ACN_OK;
+}
+
+void acn_dimage_destroy( acn_dimage* d ) { if( d ) delete reinterpret_cast<DImage*>( d ); }
+
+int acn_dimage_set_shard( acn_dimage* d, int32_t n_ranks, int32_t rank, int32_t tile )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || n_ranks < 1 || rank < 0 || rank >= n_ranks || tile < 1 || di->in_pass ) { set_error( "acn_dimage_set_shard: bad arguments" ); return ACN_ERR_INVALID_ARG; }
+    di->n_ranks = n_ranks; di->rank = rank; di->tile = tile;
+    return ACN_OK;
+}
+
+int32_t  acn_dimage_cycle( const acn_dimage* d ) { return d ? reinterpret_cast<const DImage*>( d )->cycle : -1; }
+uint64_t acn_dimage_rval( const acn_dimage* d ) { return d ? reinterpret_cast<const DImage*>( d )->rval : 0; }
+void*    acn_dimage_stream( acn_dimage* d ) { return d ? ( void* )reinterpret_cast<DImage*>( d )->stream : nullptr; }
+
+int acn_dimage_begin_pass( acn_dimage* d, const acn_flat_params* prm, const double** d_xy, uint64_t* n_local, uint64_t* n_total )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || !prm || !n_local ) { set_error( "acn_dimage_begin_pass: null argument" ); return ACN_ERR_INVALID_ARG; }
+    if( di->in_pass ) { set_error( "acn_dimage_begin_pass: the previous pass was not ended" ); return ACN_ERR_INVALID_ARG; }
+    *n_local = 0; if( n_total ) *n_total = 0; if( d_xy ) *d_xy = nullptr;
+    if( di->cycle > prm->gradient_cycles ) return ACN_OK;              // all gradient_cycles + 1 passes done (scene.c:1103)
+    if( prm->gradient_samples < 0 || prm->gradient_samples > 0xFFFF ) { set_error( "gradient_samples out of range" ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    const int W = di->width, H = di->height, nb = di->blocks();
+    const double thr2 = prm->gradient_threshold * prm->gradient_threshold;
+    k_img_select<<< nb, 256, 0, di->stream >>>( di->d_tot, W, H, di->cycle, thr2, prm->gradient_samples, di->tile, di->n_ranks, di->rank, di->d_cnt, di->d_blk );
+    k_img_scan_blocks<<< 1, 1024, 0, di->stream >>>( di->d_blk, nb, di->d_counts );
+    ACN_CUDA( cudaMemcpyAsync( di->h_counts, di->d_counts, 2 * sizeof( unsigned long long ), cudaMemcpyDeviceToHost, di->stream ) );
+    ACN_CUDA( cudaStreamSynchronize( di->stream ) );
+    di->pass_total = di->h_counts[ 0 ]; di->pass_local = di->h_counts[ 1 ];
+    if( di->pass_local > di->xy_cap )
+    {
+        cudaFree( di->d_xy ); di->d_xy = nullptr; di->xy_cap = 0;
+        const uint64_t cap = di->pass_local + di->pass_local / 4 + 1024;
+        int rc = dev_alloc( &di->d_xy, ( size_t )cap * 2 );
+        if( rc ) return rc;
+        di->xy_cap = cap;
+    }
+    if( di->pass_local ) k_img_emit<<< nb, 256, 0, di->stream >>>( di->d_cnt, di->d_blk, W, H, di->cycle, di->rval, di->d_xy );
+    ACN_CUDA( cudaStreamSynchronize( di->stream ) );
+    di->in_pass = true;
+    *n_local = di->pass_local; if( n_total ) *n_total = di->pass_total; if( d_xy ) *d_xy = di->d_xy;
+    return ACN_OK;
+}
+
+int acn_dimage_accumulate( acn_dimage* d, const double* d_xy, const float* d_rgb, uint64_t n, void* stream )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || ( n && ( !d_xy || !d_rgb ) ) ) { set_error( "acn_dimage_accumulate: null argument" ); return ACN_ERR_INVALID_ARG; }
+    if( n == 0 ) return ACN_OK;
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    k_img_accumulate<<< grid_for( n, 256 ), 256, 0, ( cudaStream_t )stream >>>( d_xy, d_rgb, n, di->width, di->height, di->d_delta );
+    ACN_CUDA( cudaGetLastError() );
+    return ACN_OK;
+}
+
+uint64_t* acn_dimage_delta( acn_dimage* d, uint64_t* n_words )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di ) return nullptr;
+    if( n_words ) *n_words = di->words();
+    return ( uint64_t* )di->d_delta;
+}
+
+int acn_dimage_end_pass( acn_dimage* d, void* stream )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || !di->in_pass ) { set_error( "acn_dimage_end_pass: no pass in progress" ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    k_img_commit<<< grid_for( di->words(), 256 ), 256, 0, ( cudaStream_t )stream >>>( di->d_tot, di->d_delta, di->words() );
+    ACN_CUDA( cudaStreamSynchronize( ( cudaStream_t )stream ) );
+    if( di->cycle > 0 ) di->rval = lcg00_skip( di->rval, 2ull * di->pass_total );      // the jitter stream of the pass (scene.c:1130-1131)
+    di->cycle++;
+    di->in_pass = false;
+    return ACN_OK;
+}
+
+int acn_dimage_render_pass( acn_dimage* d, acn_tracer* t, const acn_flat_params* prm, uint64_t index_base, uint64_t* n_local, uint64_t* n_total,
+                            const volatile int* cancel, acn_stats* stats )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    TracerBase* tb = reinterpret_cast<TracerBase*>( t );
+    if( !di || !tb || !prm ) { set_error( "acn_dimage_render_pass: null argument" ); return ACN_ERR_INVALID_ARG; }
+    if( tb->device != di->device || tb->width != di->width || tb->height != di->height ) { set_error( "acn_dimage_render_pass: tracer and image differ in device or size" ); return ACN_ERR_INVALID_ARG; }
+    const double* xy = nullptr; uint64_t nl = 0, nt = 0;
+    int rc = acn_dimage_begin_pass( d, prm, &xy, &nl, &nt );
+    if( n_local ) *n_local = nl; if( n_total ) *n_total = nt;
+    if( stats ) memset( stats, 0, sizeof( *stats ) );
+    if( rc || !di->in_pass ) return rc;
+    if( nl > di->rgb_cap )
+    {
+        cudaFree( di->d_rgb ); di->d_rgb = nullptr; di->rgb_cap = 0;
+        const uint64_t cap = nl + nl / 4 + 1024;
+        if( ( rc = dev_alloc( &di->d_rgb, ( size_t )cap * 3 ) ) ) return rc;
+        di->rgb_cap = cap;
+    }
+    if( nl )
+    {
+        rc = tb->render( xy, nl, index_base, di->d_rgb, di->stream, cancel, stats );
+        if( rc ) { di->in_pass = false; cudaMemsetAsync( di->d_delta, 0, di->words() * 8, di->stream ); cudaStreamSynchronize( di->stream ); return rc; }   // the pass is discarded (scene.c:1143-1153)
+        if( ( rc = acn_dimage_accumulate( d, xy, di->d_rgb, nl, di->stream ) ) ) return rc;
+    }
+    if( di->n_ranks == 1 ) return acn_dimage_end_pass( d, di->stream );
+    ACN_CUDA( cudaStreamSynchronize( di->stream ) );       // several ranks: the caller sums the deltas (acn_dimage_delta), then acn_dimage_end_pass
+    return ACN_OK;
+}
+
+int acn_dimage_download( acn_dimage* d, acn_image* im )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || !im ) { set_error( "acn_dimage_download: null argument" ); return ACN_ERR_INVALID_ARG; }
+    int32_t w = 0, h = 0; acn_image_size( im, &w, &h );
+    if( w != di->width || h != di->height ) { set_error( "acn_dimage_download: image size differs" ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    std::vector<unsigned long long> raw( di->words() );
+    ACN_CUDA( cudaMemcpy( raw.data(), di->d_tot, raw.size() * 8, cudaMemcpyDeviceToHost ) );
+    std::vector<double> sums( raw.size() );
+    for( size_t i = 0; i < raw.size(); i++ ) sums[ i ] = ( i % PIX_STRIDE ) == 5 ? ( double )raw[ i ] : ( double )raw[ i ] * ACN_PIX_INV;
+    return acn_image_set_state( im, di->cycle, di->rval, sums.data() );
+}
+
+int acn_dimage_upload( acn_dimage* d, const acn_image* im )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || !im || di->in_pass ) { set_error( "acn_dimage_upload: bad argument" ); return ACN_ERR_INVALID_ARG; }
+    int32_t w = 0, h = 0; acn_image_size( im, &w, &h );
+    if( w != di->width || h != di->height ) { set_error( "acn_dimage_upload: image size differs" ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    std::vector<double> sums( di->words() );
+    int rc = acn_image_sums( im, sums.data() );
+    if( rc ) return rc;
+    std::vector<unsigned long long> raw( sums.size() );
+    for( size_t i = 0; i < raw.size(); i++ ) raw[ i ] = ( i % PIX_STRIDE ) == 5 ? ( unsigned long long )llrint( sums[ i ] ) : ( unsigned long long )llrint( sums[ i ] * ACN_PIX_SCALE );
+    ACN_CUDA( cudaMemcpy( di->d_tot, raw.data(), raw.size() * 8, cudaMemcpyHostToDevice ) );
+    di->cycle = acn_image_cycle( im ); di->rval = acn_image_rval( im );
     return ACN_OK;
 }
 

@@ -156,6 +156,14 @@ enum
     ACN_CSG_MARCH     = 2   /* the reference's alternating march (objects.c:1052-1094,1209-1251)      */
 };
 
+enum
+{
+    ACN_SPECIALIZE_AUTO = 0,  /* on when the environment has ACN_SPECIALIZE=1, else off                       */
+    ACN_SPECIALIZE_ON   = 1,  /* compile kernels for this scene's structure at acn_tracer_create (NVRTC, cached
+                                 in memory and under ACN_CACHE_DIR); fails with ACN_ERR_UNSUPPORTED if it cannot */
+    ACN_SPECIALIZE_OFF  = 2   /* the generic kernels, which interpret the scene tables                          */
+};
+
 typedef struct acn_options
 {
     int32_t seed_mode;        /* ACN_SEED_*                                                         */
@@ -165,6 +173,8 @@ typedef struct acn_options
     int64_t wave_budget;      /* max rays in flight per wavefront iteration; <=0: default           */
     int32_t device;           /* CUDA device ordinal; <0: current device                            */
     int32_t csg_mode;         /* ACN_CSG_*: how composite objects are intersected                   */
+    int32_t specialize;       /* ACN_SPECIALIZE_*: scene-specialised kernels (same results, faster)  */
+    int32_t reserved;
 } acn_options;
 
 /* counters filled per render call: rays by class */
@@ -225,6 +235,12 @@ int acn_render_samples_device( acn_tracer* t, const double* d_xy, uint64_t n, ui
  * the sample position.  d_accum is a device pointer (reduced across GPUs by the caller, NCCL). */
 int acn_accumulate_device( acn_tracer* t, const double* d_xy, const float* d_rgb, uint64_t n,
                            float* d_accum, void* stream );
+
+/* Diagnostics of the run-time specialisation (needs no GPU: NVRTC cross-compiles for sm_100a): writes the C++ source
+ * generated for the scene's structure to src (cap bytes, NUL-terminated; *len = its full length, 0 when the scene does
+ * not qualify) and, if compile != 0, compiles it (ACN_ERR_UNSUPPORTED + acn_last_error() on failure). */
+int acn_spec_probe( const acn_flat_scene* scene, const acn_options* opt, int compile, char* src, uint64_t cap,
+                    uint64_t* len, double* seconds );
 
 /* The tracer's private non-blocking stream (cudaStream_t as void*), the one acn_render_samples uses. */
 void* acn_tracer_stream( acn_tracer* t );
@@ -333,6 +349,44 @@ int  acn_image_write_pnm( const acn_image* im, const char* path, uint64_t* hash 
 /* checkpoint / resume (scene.c:1068-1106,1143-1153): own format, same fields */
 int  acn_image_save( const acn_image* im, const char* path );
 int  acn_image_load( const char* path, acn_image** out );
+/* replaces the whole state: sums as acn_image_sums returns them, pass counter, jitter stream */
+int  acn_image_set_state( acn_image* im, int32_t cycle, uint64_t rval, const double* sums );
+
+/* ---------------------------------------------------------------------------------------------
+ * The same pass controller with the image RESIDENT ON THE DEVICE (scene.c:804-862,1103-1159 as kernels): gradient
+ * selection, sample list (prefix sum + LCG skip-ahead: bit-identical to acn_image_next_pass), accumulation.  Sums are
+ * 64-bit fixed point, so an image is bit-identical however its samples are spread over GPUs.
+ *
+ *   one GPU:      while( acn_dimage_render_pass( d, t, prm, base, &n, 0, cancel, &st ) == 0 && n ) base += n;
+ *   several GPUs: acn_dimage_set_shard( d, n_ranks, rank, 4 ) on every rank's image, then per pass
+ *                 acn_dimage_render_pass (traces and accumulates the rank's own pixel tiles into the pass delta),
+ *                 sum acn_dimage_delta over the ranks (ncclAllReduce, ncclUint64, ncclSum), acn_dimage_end_pass.
+ *                 acn_group_* below does exactly that inside one process.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct acn_dimage acn_dimage;
+
+int  acn_dimage_create( int device, int32_t width, int32_t height, acn_dimage** out );     /* device < 0: current */
+void acn_dimage_destroy( acn_dimage* d );
+/* pixels are dealt to the ranks in tile x tile squares along a Morton curve; default: one rank */
+int  acn_dimage_set_shard( acn_dimage* d, int32_t n_ranks, int32_t rank, int32_t tile );
+int32_t  acn_dimage_cycle( const acn_dimage* d );
+uint64_t acn_dimage_rval( const acn_dimage* d );
+void*    acn_dimage_stream( acn_dimage* d );                                                /* cudaStream_t of its kernels */
+/* builds this rank's sample list of the next pass on the device (scene.c:1108-1139).  *n_local = 0 and *n_total = 0
+ * when all gradient_cycles + 1 passes are done; *d_xy (device, n_local pairs) stays valid until the next begin_pass */
+int  acn_dimage_begin_pass( acn_dimage* d, const acn_flat_params* prm, const double** d_xy, uint64_t* n_local, uint64_t* n_total );
+/* lum_image_s_push_arr into the pass delta (device pointers) */
+int  acn_dimage_accumulate( acn_dimage* d, const double* d_xy, const float* d_rgb, uint64_t n, void* stream );
+/* the pass delta: uint64[ width*height*6 ] = pos.x, pos.y, r, g, b (Q20.44), weight — device pointer */
+uint64_t* acn_dimage_delta( acn_dimage* d, uint64_t* n_words );
+/* totals += delta, delta = 0, advances the pass counter and the jitter stream */
+int  acn_dimage_end_pass( acn_dimage* d, void* stream );
+/* begin_pass + lum_machine_s_run on the device + accumulate (+ end_pass when the image has one rank) */
+int  acn_dimage_render_pass( acn_dimage* d, acn_tracer* t, const acn_flat_params* prm, uint64_t index_base, uint64_t* n_local,
+                             uint64_t* n_total, const volatile int* cancel, acn_stats* stats );
+/* to / from the host image (pnm output, checkpoint, resume) */
+int  acn_dimage_download( acn_dimage* d, acn_image* im );
+int  acn_dimage_upload( acn_dimage* d, const acn_image* im );
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,69 @@
+"""Scene-specialised kernels (NVRTC, acn_spec.h / acn_rtc.h) against the generic kernels and the oracle.  -m gpu.
+
+Specialisation restates the scene's structure as straight-line code over the SAME leaf functions, so it may change speed,
+never results: f32 spec vs f32 generic must agree sample for sample (up to exact ties of two crossings, which the two
+sweeps may order differently), and the f64 spec build must reproduce the oracle like the generic event sweep does."""
+import numpy as np
+import pytest
+
+import actinon_b200 as acn
+from tests.oracle_lib import Oracle
+from tests.parity_util import grid_samples, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "primitives":           (dict(image_width=320, image_height=240, direct_samples=10, path_samples=4), 96, 72, 1.0),
+    "wine_glass":           (dict(direct_samples=20, path_samples=10), 96, 96, 0.9),
+    "diamond":              (dict(direct_samples=10, path_samples=6), 96, 96, 0.6),
+    "diamond_video_000049": (dict(direct_samples=6, path_samples=4), 64, 48, 0.6),
+    "ruby_heart":           (dict(direct_samples=6, path_samples=4), 64, 64, 0.9),
+    "pyramid":              (dict(direct_samples=6, path_samples=4), 64, 64, 0.9),
+    "caustic_of_caustic":   (dict(direct_samples=6, path_samples=4), 64, 64, 0.9),
+}
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_specialised_f32_equals_generic_f32(name):
+    ov, nx, ny, frac = CASES[name]
+    flat = acn.scenes.load(name, **ov)
+    xy = grid_samples(flat, nx, ny, frac)
+    g = acn.Tracer(flat, acn.Options(seed_mode=acn.SEED_INDEX_KEYED, specialize=acn.SPECIALIZE_OFF))
+    a = g.render_samples(xy); sa = g.last_stats; g.close()
+    s = acn.Tracer(flat, acn.Options(seed_mode=acn.SEED_INDEX_KEYED, specialize=acn.SPECIALIZE_ON))
+    b = s.render_samples(xy); sb = s.last_stats
+    b2 = s.render_samples(xy); s.close()
+    e = rel_err(b, a)
+    bad = float((e > 1e-5).mean())
+    print(f"{name}: spec vs generic: samples beyond 1e-5 {bad:.4%}, max {e.max():.2e}; rays {sb.rays} vs {sa.rays}")
+    assert np.array_equal(b, b2)                      # fixed-point accumulation: bit-identical from run to run
+    assert bad <= 0.003
+    assert abs(sb.rays - sa.rays) <= max(4, 2e-4 * sa.rays)
+
+
+@pytest.mark.parametrize("name", ["wine_glass", "diamond", "primitives"])
+def test_specialised_f64_sweep_reproduces_the_oracle(orc, name):
+    ov, nx, ny, frac = CASES[name]
+    flat = acn.scenes.load(name, **ov)
+    xy = grid_samples(flat, 48, 48, frac)
+    ref, info = orc.render(flat, xy, seed_mode=acn.SEED_INDEX_KEYED)
+    t = acn.Tracer(flat, acn.Options(seed_mode=acn.SEED_INDEX_KEYED, precision=acn.PRECISION_F64, csg_mode=acn.CSG_INTERVALS,
+                                     wave_budget=1 << 18, specialize=acn.SPECIALIZE_ON))
+    rgb = t.render_samples(xy); st = t.last_stats; t.close()
+    e = rel_err(rgb, ref)
+    b5, b3 = float((e > 1e-5).mean()), float((e > 1e-3).mean())
+    print(f"{name}: f64 spec vs oracle march: beyond 1e-5 {b5:.4%}, beyond 1e-3 {b3:.4%}; rays {st.rays} vs {info['rays']}")
+    assert b5 <= 0.005 and b3 <= 0.002
+    assert abs(st.rays - info["rays"]) <= max(8, 1e-3 * info["rays"])
+
+
+def test_explicit_request_on_a_scene_that_does_not_qualify_fails_loudly():
+    flat = acn.scenes.load("many_spheres")
+    with pytest.raises(acn.AcnError) as e:
+        acn.Tracer(flat, acn.Options(specialize=acn.SPECIALIZE_ON))
+    assert e.value.code == -5
