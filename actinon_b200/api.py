@@ -135,7 +135,10 @@ EXPORTED_SYMBOLS = [
     "acn_scene_load_acn", "acn_scene_image_name", "acn_scene_select_image", "acn_scene_flatten",
     "acn_image_create", "acn_image_destroy", "acn_image_size", "acn_image_cycle", "acn_image_rval", "acn_image_next_pass",
     "acn_image_push", "acn_image_average", "acn_image_sums", "acn_image_add_sums", "acn_image_write_pnm",
-    "acn_image_save", "acn_image_load",
+    "acn_image_save", "acn_image_load", "acn_image_set_state",
+    "acn_dimage_create", "acn_dimage_destroy", "acn_dimage_set_shard", "acn_dimage_cycle", "acn_dimage_rval", "acn_dimage_stream",
+    "acn_dimage_begin_pass", "acn_dimage_accumulate", "acn_dimage_delta", "acn_dimage_end_pass", "acn_dimage_render_pass",
+    "acn_dimage_download", "acn_dimage_upload", "acn_dimage_copy_delta", "acn_dimage_set_delta", "acn_dimage_read_pass_xy",
 ]
 
 
@@ -194,6 +197,17 @@ def load_library():
         "acn_image_sums": (I, [V, V]), "acn_image_add_sums": (I, [V, V]),
         "acn_image_write_pnm": (I, [V, C.c_char_p, P(C.c_uint64)]),
         "acn_image_save": (I, [V, C.c_char_p]), "acn_image_load": (I, [C.c_char_p, P(V)]),
+        "acn_image_set_state": (I, [V, C.c_int32, C.c_uint64, V]),
+        "acn_dimage_create": (I, [I, C.c_int32, C.c_int32, P(V)]), "acn_dimage_destroy": (None, [V]),
+        "acn_dimage_set_shard": (I, [V, C.c_int32, C.c_int32, C.c_int32]),
+        "acn_dimage_cycle": (C.c_int32, [V]), "acn_dimage_rval": (C.c_uint64, [V]), "acn_dimage_stream": (V, [V]),
+        "acn_dimage_begin_pass": (I, [V, P(FlatParams), P(V), P(C.c_uint64), P(C.c_uint64)]),
+        "acn_dimage_accumulate": (I, [V, V, V, C.c_uint64, V]),
+        "acn_dimage_delta": (V, [V, P(C.c_uint64)]), "acn_dimage_end_pass": (I, [V, V]),
+        "acn_dimage_render_pass": (I, [V, V, P(FlatParams), C.c_uint64, P(C.c_uint64), P(C.c_uint64), V, P(Stats)]),
+        "acn_dimage_download": (I, [V, V]), "acn_dimage_upload": (I, [V, V]),
+        "acn_dimage_copy_delta": (I, [V, V, V]), "acn_dimage_set_delta": (I, [V, V, V]),
+        "acn_dimage_read_pass_xy": (I, [V, V]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -573,6 +587,111 @@ class Image:
         _check(lib.acn_image_size(p, C.byref(w), C.byref(h)))
         im.width, im.height = w.value, h.value
         return im
+
+
+class DeviceImage:
+    """lum_image_s + the pass controller resident on the device (acn_dimage): gradient selection, sample list and
+    accumulation run as kernels; sums are 64-bit fixed point (bit-identical images for any number of GPUs)."""
+
+    def __init__(self, width: int, height: int, device: int = -1):
+        self._l = load_library()
+        p = C.c_void_p()
+        _check(self._l.acn_dimage_create(device, width, height, C.byref(p)))
+        self._p = p
+        self.width, self.height = width, height
+        self.n_ranks = 1
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._l.acn_dimage_destroy(self._p); self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_shard(self, n_ranks: int, rank: int, tile: int = 4):
+        _check(self._l.acn_dimage_set_shard(self._p, n_ranks, rank, tile))
+        self.n_ranks = n_ranks
+
+    @property
+    def cycle(self) -> int:
+        return self._l.acn_dimage_cycle(self._p)
+
+    @property
+    def rval(self) -> int:
+        return self._l.acn_dimage_rval(self._p)
+
+    @property
+    def words(self) -> int:
+        return self.width * self.height * 6
+
+    def render_pass(self, tracer: "Tracer", params: FlatParams, index_base: int = 0):
+        """One pass (scene.c:1108-1159): builds this rank's sample list on the device, traces it, accumulates.  Returns
+        (n_local, n_total); (0, 0) when all passes are done.  With several ranks the caller then sums the deltas over the
+        ranks (copy_delta / all_reduce / set_delta) and calls end_pass()."""
+        nl, nt = C.c_uint64(0), C.c_uint64(0)
+        st = Stats()
+        _check(self._l.acn_dimage_render_pass(self._p, tracer._p, C.byref(params), index_base, C.byref(nl), C.byref(nt), None, C.byref(st)))
+        tracer.last_stats = st
+        return nl.value, nt.value
+
+    def pass_xy(self, n_local: int) -> np.ndarray:
+        xy = np.empty((n_local, 2), dtype=np.float64)
+        _check(self._l.acn_dimage_read_pass_xy(self._p, xy.ctypes.data))
+        return xy
+
+    def copy_delta(self, d_tensor):
+        _check(self._l.acn_dimage_copy_delta(self._p, d_tensor.data_ptr(), self._l.acn_dimage_stream(self._p)))
+
+    def set_delta(self, d_tensor):
+        _check(self._l.acn_dimage_set_delta(self._p, d_tensor.data_ptr(), self._l.acn_dimage_stream(self._p)))
+
+    def end_pass(self):
+        _check(self._l.acn_dimage_end_pass(self._p, self._l.acn_dimage_stream(self._p)))
+
+    def download(self, image: Optional["Image"] = None) -> "Image":
+        image = image or Image(self.width, self.height)
+        _check(self._l.acn_dimage_download(self._p, image._p))
+        return image
+
+    def upload(self, image: "Image"):
+        _check(self._l.acn_dimage_upload(self._p, image._p))
+
+
+def render_image_device(flat: "FlatScene", tracer: "Tracer", passes: Optional[int] = None, dist=None):
+    """scene_s_create_image_file with the image on the device; `dist` = torch.distributed (initialised, NCCL) shards the pixel
+    tiles over the ranks and all-reduces the per-pass deltas.  Returns (Image, samples, passes, rays of this rank)."""
+    prm = flat.params
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    dimg = DeviceImage(prm.image_width, prm.image_height, tracer.options.device)
+    buf = None
+    if world > 1:
+        import torch
+        dimg.set_shard(world, rank, 4)
+        dev = torch.device("cuda", tracer.options.device if tracer.options.device >= 0 else torch.cuda.current_device())
+        buf = torch.zeros(dimg.words, dtype=torch.int64, device=dev)
+    n_samples = n_pass = rays = 0
+    while passes is None or n_pass < passes:
+        nl, nt = dimg.render_pass(tracer, prm, n_samples)
+        if nt == 0:
+            break
+        rays += tracer.last_stats.rays if nl else 0
+        if world > 1:
+            import torch
+            dimg.copy_delta(buf)
+            torch.cuda.synchronize()            # the copy ran on the image's stream, the all-reduce runs on torch's
+            dist.all_reduce(buf)                # disjoint pixel tiles, integer sums: exact, order-independent
+            torch.cuda.synchronize()
+            dimg.set_delta(buf)
+            dimg.end_pass()
+        n_samples += nt
+        n_pass += 1
+    img = dimg.download()
+    dimg.close()
+    return img, n_samples, n_pass, rays
 
 
 def render_image(scene: Scene, tracer: Optional[Tracer] = None, passes: Optional[int] = None,

@@ -324,6 +324,34 @@ uint64_t* acn_dimage_delta( acn_dimage* d, uint64_t* n_words )
     return ( uint64_t* )di->d_delta;
 }
 
+int acn_dimage_read_pass_xy( acn_dimage* d, double* xy )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || ( di->pass_local && !xy ) ) { set_error( "acn_dimage_read_pass_xy: null argument" ); return ACN_ERR_INVALID_ARG; }
+    if( di->pass_local == 0 ) return ACN_OK;
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    ACN_CUDA( cudaMemcpy( xy, di->d_xy, ( size_t )di->pass_local * 2 * sizeof( double ), cudaMemcpyDeviceToHost ) );
+    return ACN_OK;
+}
+
+// delta <-> a caller-owned device buffer of the same size (a torch tensor to all-reduce over NCCL, one process per GPU)
+int acn_dimage_copy_delta( acn_dimage* d, uint64_t* d_dst, void* stream )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || !d_dst ) { set_error( "acn_dimage_copy_delta: null argument" ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    ACN_CUDA( cudaMemcpyAsync( d_dst, di->d_delta, di->words() * 8, cudaMemcpyDeviceToDevice, ( cudaStream_t )stream ) );
+    return ACN_OK;
+}
+int acn_dimage_set_delta( acn_dimage* d, const uint64_t* d_src, void* stream )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di || !d_src ) { set_error( "acn_dimage_set_delta: null argument" ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    ACN_CUDA( cudaMemcpyAsync( di->d_delta, d_src, di->words() * 8, cudaMemcpyDeviceToDevice, ( cudaStream_t )stream ) );
+    return ACN_OK;
+}
+
 int acn_dimage_end_pass( acn_dimage* d, void* stream )
 {
     DImage* di = reinterpret_cast<DImage*>( d );

@@ -379,6 +379,11 @@ int  acn_dimage_begin_pass( acn_dimage* d, const acn_flat_params* prm, const dou
 int  acn_dimage_accumulate( acn_dimage* d, const double* d_xy, const float* d_rgb, uint64_t n, void* stream );
 /* the pass delta: uint64[ width*height*6 ] = pos.x, pos.y, r, g, b (Q20.44), weight — device pointer */
 uint64_t* acn_dimage_delta( acn_dimage* d, uint64_t* n_words );
+/* delta -> / <- a caller-owned device buffer of n_words uint64 (e.g. a torch tensor that is all-reduced over NCCL) */
+int  acn_dimage_copy_delta( acn_dimage* d, uint64_t* d_dst, void* stream );
+int  acn_dimage_set_delta( acn_dimage* d, const uint64_t* d_src, void* stream );
+/* this rank's sample list of the current / last pass, copied to the host (n_local pairs; tests, diagnostics) */
+int  acn_dimage_read_pass_xy( acn_dimage* d, double* xy );
 /* totals += delta, delta = 0, advances the pass counter and the jitter stream */
 int  acn_dimage_end_pass( acn_dimage* d, void* stream );
 /* begin_pass + lum_machine_s_run on the device + accumulate (+ end_pass when the image has one rank) */
