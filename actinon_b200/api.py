@@ -139,6 +139,8 @@ EXPORTED_SYMBOLS = [
     "acn_dimage_create", "acn_dimage_destroy", "acn_dimage_set_shard", "acn_dimage_cycle", "acn_dimage_rval", "acn_dimage_stream",
     "acn_dimage_begin_pass", "acn_dimage_accumulate", "acn_dimage_delta", "acn_dimage_end_pass", "acn_dimage_render_pass",
     "acn_dimage_download", "acn_dimage_upload", "acn_dimage_copy_delta", "acn_dimage_set_delta", "acn_dimage_read_pass_xy",
+    "acn_group_create", "acn_group_destroy", "acn_group_size", "acn_group_uses_peer_access", "acn_group_render_pass",
+    "acn_group_download", "acn_group_upload", "acn_group_image",
 ]
 
 
@@ -208,6 +210,10 @@ def load_library():
         "acn_dimage_download": (I, [V, V]), "acn_dimage_upload": (I, [V, V]),
         "acn_dimage_copy_delta": (I, [V, V, V]), "acn_dimage_set_delta": (I, [V, V, V]),
         "acn_dimage_read_pass_xy": (I, [V, V]),
+        "acn_group_create": (I, [P(FlatSceneStruct), P(Options), P(C.c_int32), C.c_int32, P(V)]), "acn_group_destroy": (None, [V]),
+        "acn_group_size": (I, [V]), "acn_group_uses_peer_access": (I, [V]),
+        "acn_group_render_pass": (I, [V, C.c_uint64, P(C.c_uint64), V, P(Stats)]),
+        "acn_group_download": (I, [V, V]), "acn_group_upload": (I, [V, V]), "acn_group_image": (V, [V, C.c_int32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -658,6 +664,58 @@ class DeviceImage:
 
     def upload(self, image: "Image"):
         _check(self._l.acn_dimage_upload(self._p, image._p))
+
+
+class Group:
+    """One image on several GPUs of one box inside one process (acn_group): a thread, a tracer and a device image per GPU,
+    pixel tiles dealt to the GPUs, per-pass sums exchanged through peer memory."""
+
+    def __init__(self, flat: "FlatScene", devices: Sequence[int], options: Optional[Options] = None):
+        self._l = load_library()
+        self._flat = flat
+        self.options = options or Options()
+        dv = (C.c_int32 * len(devices))(*devices)
+        p = C.c_void_p()
+        _check(self._l.acn_group_create(flat.ptr, C.byref(self.options), dv, len(devices), C.byref(p)))
+        self._p = p
+        self.width, self.height = flat.params.image_width, flat.params.image_height
+        self.last_stats = Stats()
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._l.acn_group_destroy(self._p); self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def uses_peer_access(self) -> bool:
+        return bool(self._l.acn_group_uses_peer_access(self._p))
+
+    def render_pass(self, index_base: int = 0) -> int:
+        n = C.c_uint64(0)
+        st = Stats()
+        _check(self._l.acn_group_render_pass(self._p, index_base, C.byref(n), None, C.byref(st)))
+        self.last_stats = st
+        return n.value
+
+    def render(self, passes: Optional[int] = None):
+        """All passes (or the first `passes`); returns (samples, passes, rays)."""
+        n_samples = n_pass = rays = 0
+        while passes is None or n_pass < passes:
+            n = self.render_pass(n_samples)
+            if n == 0:
+                break
+            n_samples += n; n_pass += 1; rays += self.last_stats.rays
+        return n_samples, n_pass, rays
+
+    def download(self, image: Optional["Image"] = None) -> "Image":
+        image = image or Image(self.width, self.height)
+        _check(self._l.acn_group_download(self._p, image._p))
+        return image
 
 
 def render_image_device(flat: "FlatScene", tracer: "Tracer", passes: Optional[int] = None, dist=None):

@@ -3,6 +3,7 @@
 // tracer entry point fails with ACN_ERR_NO_DEVICE.
 #include "acn_tracer.cuh"
 #include "acn_dimage.cuh"
+#include "acn_group.cuh"
 
 #include <stdarg.h>
 #include <mutex>
@@ -424,6 +425,113 @@ int acn_dimage_upload( acn_dimage* d, const acn_image* im )
     ACN_CUDA( cudaMemcpy( di->d_tot, raw.data(), raw.size() * 8, cudaMemcpyHostToDevice ) );
     di->cycle = acn_image_cycle( im ); di->rval = acn_image_rval( im );
     return ACN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one image on several GPUs in one process (acn_group.cuh)
+// ---------------------------------------------------------------------------------------------
+int acn_group_create( const acn_flat_scene* scene, const acn_options* opt, const int32_t* devices, int32_t n, acn_group** out )
+{
+    if( !scene || !out || n < 1 || n > GROUP_MAX ) { set_error( "acn_group_create: bad arguments (1..%d devices)", ( int )GROUP_MAX ); return ACN_ERR_INVALID_ARG; }
+    *out = nullptr;
+    int nd = acn_device_count();
+    if( nd < 0 ) return nd;
+    acn_options o;
+    if( opt ) o = *opt; else acn_options_default( &o );
+    Group* g = new Group();
+    g->n = n; g->prm = scene->params;
+    g->rc.assign( n, 0 ); g->stats.resize( n ); g->n_local.assign( n, 0 ); g->n_total.assign( n, 0 ); g->err.resize( n );
+    g->bar.n = n;
+    int rc = ACN_OK;
+    for( int r = 0; r < n && !rc; r++ )
+    {
+        const int dev = devices ? devices[ r ] : r;
+        if( dev < 0 || dev >= nd ) { set_error( "acn_group_create: device %d out of range (%d devices)", dev, nd ); rc = ACN_ERR_INVALID_ARG; break; }
+        g->devices.push_back( dev );
+        o.device = dev;
+        acn_tracer* t = nullptr; acn_dimage* d = nullptr;
+        if( ( rc = acn_tracer_create( scene, &o, &t ) ) ) break;
+        g->tracers.push_back( t );
+        if( ( rc = acn_dimage_create( dev, scene->params.image_width, scene->params.image_height, &d ) ) ) break;
+        g->images.push_back( d );
+        if( ( rc = acn_dimage_set_shard( d, n, r, 4 ) ) ) break;
+    }
+    // peer access between every pair of distinct devices
+    for( int r = 0; r < n && !rc; r++ )
+        for( int k = 0; k < n; k++ )
+        {
+            if( g->devices[ k ] == g->devices[ r ] ) continue;
+            int can = 0;
+            cudaSetDevice( g->devices[ r ] );
+            if( cudaDeviceCanAccessPeer( &can, g->devices[ r ], g->devices[ k ] ) != cudaSuccess || !can ) { g->peer = false; continue; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess( g->devices[ k ], 0 );
+            if( e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled ) g->peer = false;
+            cudaGetLastError();
+        }
+    if( !rc && !g->peer )
+    {
+        g->stage.assign( n, nullptr );
+        for( int r = 0; r < n && !rc; r++ ) { cudaSetDevice( g->devices[ r ] ); rc = dev_alloc( &g->stage[ r ], g->img( r )->words() ); }
+    }
+    if( rc ) { delete g; return rc; }
+    for( int r = 0; r < n; r++ ) g->threads.emplace_back( [ g, r ] { g->worker( r ); } );
+    *out = reinterpret_cast<acn_group*>( g );
+    return ACN_OK;
+}
+
+void acn_group_destroy( acn_group* gp ) { if( gp ) delete reinterpret_cast<Group*>( gp ); }
+
+int acn_group_size( const acn_group* gp ) { return gp ? reinterpret_cast<const Group*>( gp )->n : 0; }
+
+int acn_group_uses_peer_access( const acn_group* gp ) { return gp && reinterpret_cast<const Group*>( gp )->peer ? 1 : 0; }
+
+int acn_group_render_pass( acn_group* gp, uint64_t index_base, uint64_t* n_samples, const volatile int* cancel, acn_stats* stats )
+{
+    Group* g = reinterpret_cast<Group*>( gp );
+    if( !g ) { set_error( "acn_group_render_pass: null group" ); return ACN_ERR_INVALID_ARG; }
+    if( n_samples ) *n_samples = 0;
+    if( stats ) memset( stats, 0, sizeof( *stats ) );
+    {
+        std::unique_lock<std::mutex> lk( g->mu );
+        g->index_base = index_base; g->cancel = cancel; g->done = 0; g->cmd = 1; g->seq++;
+        g->cv_cmd.notify_all();
+        g->cv_done.wait( lk, [ & ] { return g->done == g->n; } );
+    }
+    for( int r = 0; r < g->n; r++ )
+        if( g->rc[ r ] ) { set_error( "rank %d (device %d): %s", r, g->devices[ r ], g->err[ r ].c_str() ); return g->rc[ r ]; }
+    if( n_samples ) *n_samples = g->n_total[ 0 ];
+    if( stats )
+        for( int r = 0; r < g->n; r++ )
+        {
+            const acn_stats& s = g->stats[ r ];
+            stats->samples += s.samples; stats->rays_primary += s.rays_primary; stats->rays_reflection += s.rays_reflection;
+            stats->rays_chromatic += s.rays_chromatic; stats->rays_refraction += s.rays_refraction; stats->rays_path += s.rays_path;
+            stats->rays_shadow += s.rays_shadow; stats->rays_light += s.rays_light; stats->diffuse_hits += s.diffuse_hits;
+            stats->kernel_launches += s.kernel_launches; stats->waves = s.waves > stats->waves ? s.waves : stats->waves;
+            stats->device_ms = s.device_ms > stats->device_ms ? s.device_ms : stats->device_ms;
+        }
+    return ACN_OK;
+}
+
+int acn_group_download( acn_group* gp, acn_image* im )
+{
+    Group* g = reinterpret_cast<Group*>( gp );
+    if( !g || !im ) { set_error( "acn_group_download: null argument" ); return ACN_ERR_INVALID_ARG; }
+    return acn_dimage_download( g->images[ 0 ], im );       // every rank holds the whole image
+}
+
+int acn_group_upload( acn_group* gp, const acn_image* im )
+{
+    Group* g = reinterpret_cast<Group*>( gp );
+    if( !g || !im ) { set_error( "acn_group_upload: null argument" ); return ACN_ERR_INVALID_ARG; }
+    for( int r = 0; r < g->n; r++ ) { const int rc = acn_dimage_upload( g->images[ r ], im ); if( rc ) return rc; }
+    return ACN_OK;
+}
+
+acn_dimage* acn_group_image( acn_group* gp, int32_t rank )
+{
+    Group* g = reinterpret_cast<Group*>( gp );
+    return g && rank >= 0 && rank < g->n ? g->images[ rank ] : nullptr;
 }
 
 double acn_measure_fp32_peak_tflops( int device )

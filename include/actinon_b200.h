@@ -393,6 +393,28 @@ int  acn_dimage_render_pass( acn_dimage* d, acn_tracer* t, const acn_flat_params
 int  acn_dimage_download( acn_dimage* d, acn_image* im );
 int  acn_dimage_upload( acn_dimage* d, const acn_image* im );
 
+/* ---------------------------------------------------------------------------------------------
+ * One image on several GPUs of one box, inside one process: what replaces the single call site
+ * lum_machine_s_run( scene, lum_arr ) + lum_image_s_push_arr (scene.c:1141,1156) when more than one device is to work
+ * on an image.  One worker thread, one tracer and one device image per GPU; pixel tiles are dealt to the GPUs, each
+ * pass's per-pixel sums are exchanged straight through peer memory (NVLink / NVSwitch).  devices: n CUDA ordinals
+ * (NULL: 0..n-1; an ordinal may repeat).  The images are bit-identical for every n.
+ *
+ *   acn_group_create( flat, &opt, NULL, 8, &g );
+ *   while( acn_group_render_pass( g, base, &n, cancel, &st ) == 0 && n ) { base += n; acn_group_download( g, image ); ... }
+ * ------------------------------------------------------------------------------------------- */
+typedef struct acn_group acn_group;
+
+int  acn_group_create( const acn_flat_scene* scene, const acn_options* opt, const int32_t* devices, int32_t n, acn_group** out );
+void acn_group_destroy( acn_group* g );
+int  acn_group_size( const acn_group* g );
+int  acn_group_uses_peer_access( const acn_group* g );
+/* one pass of the controller on all GPUs; *n_samples = samples of the pass (0: all passes done); stats summed over the GPUs */
+int  acn_group_render_pass( acn_group* g, uint64_t index_base, uint64_t* n_samples, const volatile int* cancel, acn_stats* stats );
+int  acn_group_download( acn_group* g, acn_image* im );
+int  acn_group_upload( acn_group* g, const acn_image* im );
+acn_dimage* acn_group_image( acn_group* g, int32_t rank );
+
 #ifdef __cplusplus
 }
 #endif

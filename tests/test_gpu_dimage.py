@@ -103,3 +103,36 @@ def test_resume_from_a_host_checkpoint(tmp_path):
         pass
     assert c.download().write_pnm(None) == a.download().write_pnm(None)
     a.close(); c.close(); t.close()
+
+
+def _group_image(flat, devices, options=None):
+    g = acn.Group(flat, devices, options)
+    n_samples, n_pass, rays = g.render()
+    img = g.download()
+    peer = g.uses_peer_access
+    g.close()
+    return img, n_samples, n_pass, rays, peer
+
+
+def test_group_of_three_ranks_on_one_device_is_bit_identical_to_one_rank():
+    """acn_group_* (one process, a worker thread + tracer + device image per rank, deltas exchanged through the owners'
+    memory): three ranks sharing GPU 0 must produce the image of a single rank, to the bit."""
+    flat = acn.scenes.load("wine_glass", image_width=96, image_height=96, direct_samples=10, path_samples=6, gradient_cycles=4)
+    one, n1, p1, r1, _ = _group_image(flat, [0])
+    three, n3, p3, r3, _ = _group_image(flat, [0, 0, 0])
+    assert (n1, p1) == (n3, p3) and p1 == 5
+    assert r1 == r3                                       # the same rays were traced, only by other ranks
+    assert np.array_equal(one.sums(), three.sums())
+    assert one.write_pnm(None) == three.write_pnm(None)
+
+
+def test_group_over_all_gpus_of_the_box_is_bit_identical():
+    n = acn.device_count()
+    if n < 2:
+        pytest.skip("one GPU")
+    flat = acn.scenes.load("diamond", image_width=128, image_height=128, direct_samples=8, path_samples=6, gradient_cycles=3)
+    one, n1, p1, r1, _ = _group_image(flat, [0])
+    many, nn, pn, rn, peer = _group_image(flat, list(range(n)))
+    print(f"{n} GPUs, peer access {peer}")
+    assert (n1, p1, r1) == (nn, pn, rn)
+    assert np.array_equal(one.sums(), many.sums())
