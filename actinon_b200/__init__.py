@@ -16,6 +16,8 @@ from .api import (  # noqa: F401
     Image,
     DeviceImage,
     Group,
+    pixel_owner,
+    PIX_SCALE,
     render_image_device,
     Options,
     Scene,
@@ -42,7 +44,7 @@ from .api import (  # noqa: F401
 from . import scenes  # noqa: F401
 
 __all__ = [
-    "AcnError", "FlatScene", "Image", "DeviceImage", "Group", "render_image_device", "Options", "Scene", "Stats", "Tracer", "device_count",
+    "AcnError", "FlatScene", "Image", "DeviceImage", "Group", "pixel_owner", "PIX_SCALE", "render_image_device", "Options", "Scene", "Stats", "Tracer", "device_count",
     "library_path", "load_library", "lum_machine_run", "measure_fp32_peak_tflops", "render_image",
     "scenes", "SEED_POSITION_HASH", "SEED_INDEX_KEYED", "PRECISION_F32", "PRECISION_F64",
     "CSG_AUTO", "CSG_INTERVALS", "CSG_MARCH", "SPECIALIZE_AUTO", "SPECIALIZE_ON", "SPECIALIZE_OFF", "spec_probe",

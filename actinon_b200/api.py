@@ -136,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "acn_image_create", "acn_image_destroy", "acn_image_size", "acn_image_cycle", "acn_image_rval", "acn_image_next_pass",
     "acn_image_push", "acn_image_average", "acn_image_sums", "acn_image_add_sums", "acn_image_write_pnm",
     "acn_image_save", "acn_image_load", "acn_image_set_state",
-    "acn_dimage_create", "acn_dimage_destroy", "acn_dimage_set_shard", "acn_dimage_cycle", "acn_dimage_rval", "acn_dimage_stream",
+    "acn_pixel_owner", "acn_dimage_create", "acn_dimage_destroy", "acn_dimage_reset", "acn_dimage_set_shard", "acn_dimage_cycle", "acn_dimage_rval", "acn_dimage_stream",
     "acn_dimage_begin_pass", "acn_dimage_accumulate", "acn_dimage_delta", "acn_dimage_end_pass", "acn_dimage_render_pass",
     "acn_dimage_download", "acn_dimage_upload", "acn_dimage_copy_delta", "acn_dimage_set_delta", "acn_dimage_read_pass_xy",
     "acn_group_create", "acn_group_destroy", "acn_group_size", "acn_group_uses_peer_access", "acn_group_render_pass",
@@ -201,7 +201,8 @@ def load_library():
         "acn_image_save": (I, [V, C.c_char_p]), "acn_image_load": (I, [C.c_char_p, P(V)]),
         "acn_image_set_state": (I, [V, C.c_int32, C.c_uint64, V]),
         "acn_dimage_create": (I, [I, C.c_int32, C.c_int32, P(V)]), "acn_dimage_destroy": (None, [V]),
-        "acn_dimage_set_shard": (I, [V, C.c_int32, C.c_int32, C.c_int32]),
+        "acn_dimage_set_shard": (I, [V, C.c_int32, C.c_int32, C.c_int32]), "acn_dimage_reset": (I, [V]),
+        "acn_pixel_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
         "acn_dimage_cycle": (C.c_int32, [V]), "acn_dimage_rval": (C.c_uint64, [V]), "acn_dimage_stream": (V, [V]),
         "acn_dimage_begin_pass": (I, [V, P(FlatParams), P(V), P(C.c_uint64), P(C.c_uint64)]),
         "acn_dimage_accumulate": (I, [V, V, V, C.c_uint64, V]),
@@ -595,6 +596,14 @@ class Image:
         return im
 
 
+def pixel_owner(x: int, y: int, tile: int, n_ranks: int) -> int:
+    """Rank that owns pixel (x, y): tile x tile squares dealt along a Morton curve (acn_dimage_set_shard)."""
+    return load_library().acn_pixel_owner(x, y, tile, n_ranks)
+
+
+PIX_SCALE = float(1 << 44)      # fixed-point scale of the device image's sums (Q20.44)
+
+
 class DeviceImage:
     """lum_image_s + the pass controller resident on the device (acn_dimage): gradient selection, sample list and
     accumulation run as kernels; sums are 64-bit fixed point (bit-identical images for any number of GPUs)."""
@@ -616,6 +625,14 @@ class DeviceImage:
             self.close()
         except Exception:
             pass
+
+    def reset(self):
+        _check(self._l.acn_dimage_reset(self._p))
+
+    def accumulate(self, d_xy, d_rgb, stream=None):
+        """lum_image_s_push_arr of device-resident samples into the pass delta (torch CUDA tensors)."""
+        s = stream.cuda_stream if stream is not None else self._l.acn_dimage_stream(self._p)
+        _check(self._l.acn_dimage_accumulate(self._p, d_xy.data_ptr(), d_rgb.data_ptr(), d_xy.shape[0], s))
 
     def set_shard(self, n_ranks: int, rank: int, tile: int = 4):
         _check(self._l.acn_dimage_set_shard(self._p, n_ranks, rank, tile))

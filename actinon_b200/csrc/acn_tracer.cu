@@ -271,6 +271,24 @@ int acn_dimage_set_shard( acn_dimage* d, int32_t n_ranks, int32_t rank, int32_t 
     return ACN_OK;
 }
 
+int32_t acn_pixel_owner( int32_t x, int32_t y, int32_t tile, int32_t n_ranks )
+{
+    if( x < 0 || y < 0 || tile < 1 || n_ranks < 1 ) return -1;
+    return pixel_owner( x, y, tile, n_ranks );
+}
+
+int acn_dimage_reset( acn_dimage* d )
+{
+    DImage* di = reinterpret_cast<DImage*>( d );
+    if( !di ) { set_error( "acn_dimage_reset: null image" ); return ACN_ERR_INVALID_ARG; }
+    ACN_CUDA( cudaSetDevice( di->device ) );
+    ACN_CUDA( cudaMemsetAsync( di->d_tot, 0, di->words() * 8, di->stream ) );
+    ACN_CUDA( cudaMemsetAsync( di->d_delta, 0, di->words() * 8, di->stream ) );
+    ACN_CUDA( cudaStreamSynchronize( di->stream ) );
+    di->cycle = 0; di->rval = 21943294ull; di->in_pass = false;
+    return ACN_OK;
+}
+
 int32_t  acn_dimage_cycle( const acn_dimage* d ) { return d ? reinterpret_cast<const DImage*>( d )->cycle : -1; }
 uint64_t acn_dimage_rval( const acn_dimage* d ) { return d ? reinterpret_cast<const DImage*>( d )->rval : 0; }
 void*    acn_dimage_stream( acn_dimage* d ) { return d ? ( void* )reinterpret_cast<DImage*>( d )->stream : nullptr; }

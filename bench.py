@@ -1,30 +1,34 @@
 #!/usr/bin/env python
 """bench.py — path samples/s and rays/s of the hot path (lum_machine_s_run, reference src/scene.c:1017) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scene NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scene NAME] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
-One STEP = one sample pass of the hot path over the image of BASELINE.json configs[1]
-(wine_glass.acn exactly as scripted: 400x400, direct_samples 200, path_samples 500, trace_depth 25).
-At N = 1 the pass is pass 0 of the reference's controller (every pixel centre, scene.c:1110-1120:
-160 000 samples).  At N > 1 the step is N such sample passes (pass 0 + N-1 jittered passes: "image
-tiles and sample passes shard across the GPUs") whose samples are dealt to the ranks by 8x8 pixel tiles,
-so every rank traces W*H samples per step (weak scaling) and all samples of a pixel stay on one GPU;
-the per-pixel float4 accumulators are then summed over the ranks with one NCCL all-reduce, inside the
-timed region.
+One STEP = pass 0 of the reference's pass controller (every pixel centre, scene.c:1110-1120) of BASELINE.json configs[1],
+wine_glass.acn exactly as scripted (direct_samples 200, path_samples 500, trace_depth 25), through the product's own pass
+API (acn_dimage_render_pass: sample list built on the device, traced, accumulated per pixel in fixed point).
 
- value    whole-job samples/s with the sample positions already resident in HBM (device-resident C-ABI
-          entry point acn_render_samples_device + acn_accumulate_device [+ all-reduce])
- e2e      the same metric through the reference-facing call with HOST buffers
-          (acn_render_samples = lum_machine_s_run(scene, lum_arr)); H2D of the positions and D2H of the
-          colours are inside the timed region
- roofline FP32-ALU roofline of the dominant kernel: algorithmic FLOPs (oracle counters x SURVEY.md §8d
-          constants, reference traversal order) / CUDA-event time of that kernel's launches in the step
+ N = 1   the scripted 400x400 image: 160 000 samples per step.
+ N > 1   WEAK scaling: the same scene rendered at sqrt(N) x the resolution (566^2, 800^2, 1131^2 for N = 2, 4, 8), i.e.
+         160 000 samples per GPU and step; pixels are dealt to the ranks in 4x4 tiles along a Morton curve, every rank traces
+         its own tiles, and the per-pixel sums of the pass are exchanged with ONE all-reduce (NCCL, uint64 sums, disjoint
+         support) inside the timed region.  `extras.strong` holds the STRONG-scaling figure (the scripted 400x400 pass split
+         over the N ranks), `extras.configs` pass 0 of many_spheres (C3), diamond (C4) and hanging_lamps_in_row 640x360 (C5)
+         split over the N ranks, `extras.video` frames of diamond_video.acn dealt to the ranks (C5).
+
+ value    whole-job samples/s, everything resident in HBM (CUDA events on the image's stream, max over ranks)
+ e2e      N = 1: the reference-facing call with HOST buffers (acn_render_samples = lum_machine_s_run(scene, lum_arr)), H2D of the
+          positions and D2H of the colours inside the timed region.  N > 1: H2D of the rank's positions, trace, accumulate,
+          all-reduce, D2H of the reduced image.
+ roofline FP32-ALU roofline of the dominant kernel: algorithmic FLOPs (oracle counters x SURVEY.md §8d constants, reference
+          traversal order) / CUDA-event time of that kernel's launches in the step
  cpu_baseline   the CPU oracle (FP64, position-hash seeding, all host threads) on the same scene
- --impl reference   the CPU oracle alone (the reference itself cannot be built: beth is absent)
+ --impl reference   the CPU oracle alone (the reference itself cannot be built: its dependency beth is absent)
 
-Inputs are "synthetic" only in the sense of the contract: the geometry is the reference's own scripted
+The kernels are the scene-specialised ones (acn_options.specialize = ON: compiled by NVRTC at acn_tracer_create for the
+scene's structure, same leaf arithmetic as the generic kernels; many_spheres and the lamp scenes do not qualify and run the
+generic kernels).  Inputs are "synthetic" only in the sense of the contract: the geometry is the reference's own scripted
 scene, flattened by our .acn front-end (scenes/*.npz); no dataset is involved.
 """
 from __future__ import annotations
@@ -35,7 +39,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -44,37 +47,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-TILE = 8
 METRIC = "path_samples_per_sec"
 UNIT = "samples/s"
+CPU_FLAGS = "g++ -O3 -march=native -ffp-contract=off (FP64; the reference's makefile adds -march=native to beth's unknown base flags)"
 
 
-# --------------------------------------------------------------------------------------------------
-# workload
-# --------------------------------------------------------------------------------------------------
-def pass_positions(width: int, height: int, p: int) -> np.ndarray:
-    """Sample positions of sample pass p: p = 0 pixel centres (scene.c:1110-1120), p > 0 one jittered
-    position per pixel (the shape of a gradient pass over the full image, scene.c:1124-1138)."""
+def scaled_size(w: int, h: int, n: int):
+    """Image size with n times the pixels of w x h (same aspect)."""
+    if n == 1:
+        return w, h
+    f = np.sqrt(n)
+    return int(round(w * f)), int(round(h * f))
+
+
+def pass0_positions(width: int, height: int) -> np.ndarray:
     ys, xs = np.mgrid[0:height, 0:width]
-    if p == 0:
-        jx = jy = 0.5
-    else:
-        rng = np.random.default_rng(21943294 + p)
-        jx = rng.random((height, width))
-        jy = rng.random((height, width))
-    return np.stack([(xs + jx).ravel(), (ys + jy).ravel()], axis=1).astype(np.float64)
-
-
-def rank_samples(width: int, height: int, n_ranks: int, rank: int) -> np.ndarray:
-    """Samples of one step owned by `rank`: pixels whose 8x8 tile satisfies (tx + ty) % n_ranks == rank,
-    for each of the n_ranks sample passes."""
-    out = []
-    for p in range(n_ranks):
-        xy = pass_positions(width, height, p)
-        tx = (xy[:, 0].astype(np.int64)) // TILE
-        ty = (xy[:, 1].astype(np.int64)) // TILE
-        out.append(xy[(tx + ty) % n_ranks == rank])
-    return np.ascontiguousarray(np.concatenate(out, axis=0))
+    return np.ascontiguousarray(np.stack([(xs + 0.5).ravel(), (ys + 0.5).ravel()], axis=1).astype(np.float64))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -134,12 +122,12 @@ class ClockSampler:
 # CPU arm (oracle): cpu_baseline and --impl reference
 # --------------------------------------------------------------------------------------------------
 def cpu_sample(xy: np.ndarray, stride: int) -> np.ndarray:
-    """Every stride-th sample (stride coprime to the image width keeps the subset spread over the image)."""
     return np.ascontiguousarray(xy[::stride])
 
 
 def cpu_probe_stride(orc, flat, xy, target_s: float, threads: int) -> int:
-    """Chooses the sub-sampling stride so that one CPU pass takes about target_s seconds."""
+    """Sub-sampling stride so that one CPU pass takes about target_s seconds (coprime to the row length: the subset stays
+    spread over the image)."""
     probe = cpu_sample(xy, 97)
     t0 = time.perf_counter()
     orc.render(flat, probe, seed_mode=0, threads=threads)
@@ -148,19 +136,34 @@ def cpu_probe_stride(orc, flat, xy, target_s: float, threads: int) -> int:
     if full <= target_s:
         return 1
     stride = int(np.ceil(full / target_s))
-    while np.gcd(stride, 400) != 1:          # keep it coprime to the row length
+    while np.gcd(stride, flat.params.image_width) != 1:
         stride += 1
     return stride
 
 
-def run_reference_arm(args, flat, scene_name):
+def workload_config(scene_name, prm, n, scripted_wh):
+    W, H = prm.image_width, prm.image_height
+    return {
+        "workload": f"{scene_name}.acn as scripted (direct_samples {prm.direct_samples}, path_samples {prm.path_samples}, trace_depth "
+                    f"{prm.trace_depth}); one step = pass 0 of the pass controller = every pixel centre of the {W}x{H} image "
+                    f"({W * H} samples)" + ("" if n == 1 else f": the scripted {scripted_wh[0]}x{scripted_wh[1]} image at sqrt({n}) x the "
+                    f"resolution, {W * H // n} samples per GPU (weak scaling)") + ", BASELINE.json configs[1]",
+        "samples_per_step": W * H,
+        "sharding": "single GPU" if n == 1 else "4x4 pixel tiles dealt to the ranks along a Morton curve; one NCCL all-reduce (uint64 sums) "
+                    "of the pass's per-pixel sums per step",
+        "kernels": "scene-specialised (NVRTC at acn_tracer_create; acn_options.specialize = ON)",
+        "l2": "ray/task/hit queues (>1 GB per step) exceed the 126 MB L2; a 256 MB buffer is overwritten between timed steps",
+    }
+
+
+def run_reference_arm(args, flat, scene_name, scripted_wh):
     """The reference's CPU implementation of the path (restated: oracle/, FP64, all host threads)."""
     from tests.oracle_lib import Oracle
     orc = Oracle()
     prm = flat.params
     W, H = prm.image_width, prm.image_height
     threads = os.cpu_count() or 1
-    xy_full = pass_positions(W, H, 0)
+    xy_full = pass0_positions(W, H)
     stride = cpu_probe_stride(orc, flat, xy_full, 6.0, threads)
     xy = cpu_sample(xy_full, stride)
     rays = 0
@@ -177,9 +180,9 @@ def run_reference_arm(args, flat, scene_name):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference scene script, flattened)",
-        "config": workload_config(scene_name, prm, args.gpus),
+        "config": workload_config(scene_name, prm, args.gpus, scripted_wh),
         "rays_per_sec": rays / dt,
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "flags": CPU_FLAGS},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference binary unbuildable here (depends on johsteffens/beth, absent); this is the FP64 CPU oracle "
                 "that restates scene.c/compound.c/objects.c, dynamic per-sample scheduling on all host threads",
@@ -187,20 +190,80 @@ def run_reference_arm(args, flat, scene_name):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(scene_name, prm, n):
-    return {
-        "workload": f"{scene_name}.acn as scripted: {prm.image_width}x{prm.image_height}, direct_samples {prm.direct_samples}, "
-                    f"path_samples {prm.path_samples}, trace_depth {prm.trace_depth}; one step = {n} sample pass(es) over the image "
-                    f"({prm.image_width * prm.image_height * n} samples), BASELINE.json configs[1]",
-        "samples_per_step": prm.image_width * prm.image_height * n,
-        "sharding": "8x8 pixel tiles, (tx+ty) % N; one NCCL all-reduce of float4[W*H] per step" if n > 1 else "single GPU",
-        "l2": "ray/task queues (>1 GB per step) exceed the 126 MB L2; a 256 MB buffer is overwritten between timed steps",
-    }
-
-
 # --------------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------------
+class Rig:
+    """One scene on this rank: tracer (scene-specialised kernels when the scene qualifies), sharded device image, and the
+    step = pass 0 through the product's pass API + the exchange of the pass's sums."""
+
+    def __init__(self, acn, torch, dist, flat, local_rank, rank, world):
+        self.acn, self.torch, self.dist = acn, torch, dist
+        self.flat, self.prm = flat, flat.params
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", local_rank)
+        o = dict(seed_mode=acn.SEED_POSITION_HASH, precision=acn.PRECISION_F32, device=local_rank)
+        try:
+            self.tracer = acn.Tracer(flat, acn.Options(specialize=acn.SPECIALIZE_ON, **o))
+            self.specialised = True
+        except acn.AcnError as e:
+            if e.code != -5:
+                raise
+            self.tracer = acn.Tracer(flat, acn.Options(specialize=acn.SPECIALIZE_OFF, **o))      # the scene does not qualify
+            self.specialised = False
+        W, H = self.prm.image_width, self.prm.image_height
+        self.img = acn.DeviceImage(W, H, local_rank)
+        self.img.set_shard(world, rank, 4)
+        self.stream = torch.cuda.ExternalStream(acn.load_library().acn_dimage_stream(self.img._p), device=self.dev)
+        self.buf = torch.zeros(self.img.words, dtype=torch.int64, device=self.dev) if world > 1 else None
+        self.launches = 0
+        self.rays = 0
+        self.n_local = 0
+
+    def step(self):
+        self.img.reset()
+        nl, nt = self.img.render_pass(self.tracer, self.prm)
+        st = self.tracer.last_stats
+        self.launches += (st.kernel_launches if nl else 0) + 4 + (2 if self.world > 1 else 1)      # select, scan, emit, accumulate, commit
+        self.rays += st.rays if nl else 0
+        self.n_local = nl
+        if self.world > 1:
+            with self.torch.cuda.stream(self.stream):
+                self.img.copy_delta(self.buf)
+                self.dist.all_reduce(self.buf)                 # disjoint pixel tiles, integer sums: exact, order-independent
+                self.img.set_delta(self.buf)
+            self.img.end_pass()
+        return st
+
+    def timed(self, steps, warmup, flush=None, barrier=None):
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        if barrier:
+            barrier()
+        ms = []
+        self.launches = 0; self.rays = 0
+        by_class = {}
+        for _ in range(steps):
+            if flush is not None:
+                flush.fill_(1)
+                torch.cuda.synchronize(self.dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            st = self.step()
+            e1.record(self.stream)
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+            for k in ("rays_primary", "rays_reflection", "rays_chromatic", "rays_refraction", "rays_path", "rays_shadow", "diffuse_hits"):
+                by_class[k] = by_class.get(k, 0) + getattr(st, k)
+        if barrier:
+            barrier()
+        return ms, by_class
+
+    def close(self):
+        self.img.close(); self.tracer.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,6 +272,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scene", default="wine_glass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / other-config / video records")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -216,13 +280,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     import actinon_b200 as acn
-    flat = acn.scenes.load(args.scene)
+    scripted = acn.scenes.load(args.scene).params
+    scripted_wh = (scripted.image_width, scripted.image_height)
+    n_for_size = world if args.impl == "b200" else args.gpus
+    W, H = scaled_size(scripted_wh[0], scripted_wh[1], n_for_size)
+    flat = acn.scenes.load(args.scene, image_width=W, image_height=H)
     prm = flat.params
-    W, H = prm.image_width, prm.image_height
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference_arm(args, flat, args.scene)
+            run_reference_arm(args, flat, args.scene, scripted_wh)
         return
 
     import torch
@@ -233,16 +300,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_ranks = world
-
-    xy_np = rank_samples(W, H, n_ranks, rank)
-    n_local = xy_np.shape[0]
-    tracer = acn.Tracer(flat, acn.Options(seed_mode=acn.SEED_POSITION_HASH, precision=acn.PRECISION_F32, device=local_rank))
-    d_xy = torch.from_numpy(xy_np).to(dev)
-    d_rgb = torch.empty((n_local, 3), dtype=torch.float32, device=dev)
-    d_acc = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
     os.environ.pop("ACN_PROFILE_KERNELS", None)
 
     def barrier():
@@ -250,70 +307,68 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def device_step():
-        d_acc.zero_()
-        tracer.render_samples_device(d_xy, d_rgb, stream=stream)
-        tracer.accumulate_device(d_xy, d_rgb, d_acc, stream=stream)
-        if world > 1:
-            dist.all_reduce(d_acc)
-        return tracer.last_stats
+    def over_ranks(vals, op):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return [float(v) for v in t]
 
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
+    rig = Rig(acn, torch, dist, flat, local_rank, rank, world)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    # ---- timed region: exactly K steps; per-step CUDA events on the launching stream, L2 flushed in between
+    # ---- timed region: exactly K steps; per-step CUDA events on the image's stream, L2 flushed in between
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    step_ms = []
-    kernel_cnt = np.zeros(4)
-    launches = 0
-    rays = 0
-    stats_by_class = {}
-    barrier()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        st = device_step()
-        e1.record(stream)
-        e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-        launches += st.kernel_launches + 1 + (1 if world > 1 else 0)
-        rays += st.rays
-        for k in ("rays_primary", "rays_reflection", "rays_chromatic", "rays_refraction", "rays_path", "rays_shadow", "diffuse_hits"):
-            stats_by_class[k] = stats_by_class.get(k, 0) + getattr(st, k)
-    barrier()
+    step_ms, stats_by_class = rig.timed(args.steps, args.warmup, flush, barrier)
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
     total_ms = float(sum(step_ms))
+    launches, rays, n_local = rig.launches, rig.rays, rig.n_local
 
     # ---- one extra, untimed step with an event pair around every tracing-kernel launch (kernel shares for the roofline)
     os.environ["ACN_PROFILE_KERNELS"] = "1"
-    st = device_step()
+    st = rig.step()
     torch.cuda.synchronize(dev)
     os.environ.pop("ACN_PROFILE_KERNELS", None)
     kernel_ms = np.array(list(st.kernel_ms)) * args.steps            # scaled so that the per-step figures below hold
     kernel_cnt = np.array(list(st.kernel_launches_by_class)) * args.steps
     prof_step_ms = st.device_ms
+    xy_np = rig.img.pass_xy(n_local)                                 # this rank's pass-0 samples (for the host legs)
 
-    # ---- end to end through the reference-facing call with host buffers (pinned), same K steps
+    # ---- end to end with host buffers (pinned), same K steps
     h_xy = torch.from_numpy(xy_np).pin_memory()
     h_rgb = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
-    xy_host = h_xy.numpy()
-    rgb_host = h_rgb.numpy()
+    xy_host, rgb_host = h_xy.numpy(), h_rgb.numpy()
     import ctypes as C
     lib = acn.load_library()
+    if world == 1:
+        def host_step():
+            s = acn.Stats()
+            rc = lib.acn_render_samples(rig.tracer._p, xy_host.ctypes.data, n_local, 0, rgb_host.ctypes.data, None, C.byref(s))
+            if rc:
+                raise acn.AcnError(rc, lib.acn_last_error().decode())
+            return float(rgb_host[0, 0])          # the result is read on the host
+        h2d, d2h = n_local * 16, n_local * 12
+    else:
+        d_xy = torch.empty((n_local, 2), dtype=torch.float64, device=dev)
+        d_rgb = torch.empty((n_local, 3), dtype=torch.float32, device=dev)
+        h_img = torch.empty(rig.img.words, dtype=torch.int64).pin_memory()
 
-    def host_step():
-        st = acn.Stats()
-        rc = lib.acn_render_samples(tracer._p, xy_host.ctypes.data, n_local, 0, rgb_host.ctypes.data, None, C.byref(st))
-        if rc:
-            raise acn.AcnError(rc, lib.acn_last_error().decode())
-        return float(rgb_host[0, 0])          # the result is read on the host
-
+        def host_step():
+            rig.img.reset()
+            with torch.cuda.stream(rig.stream):
+                d_xy.copy_(h_xy, non_blocking=True)
+                rig.tracer.render_samples_device(d_xy, d_rgb, stream=rig.stream)
+                rig.img.accumulate(d_xy, d_rgb)
+                rig.img.copy_delta(rig.buf)
+                dist.all_reduce(rig.buf)
+                h_img.copy_(rig.buf, non_blocking=True)
+            rig.stream.synchronize()
+            return int(h_img[5])                  # the reduced image is read on the host
+        h2d, d2h = n_local * 16, rig.img.words * 8
     host_step()
     barrier()
     t0 = time.perf_counter()
@@ -322,17 +377,17 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    # ---- max over ranks
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_s, float(n_local), float(rays), float(launches)], dtype=torch.float64, device=dev)
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_s = float(tmax[0]), float(tmax[1])
-        n_total, rays_total, launches_total = int(tsum[2]), float(tsum[3]), int(tsum[4])
-    else:
-        n_total, rays_total, launches_total = n_local, float(rays), int(launches)
+    # ---- max / sum over ranks
+    total_ms, e2e_s = over_ranks([total_ms, e2e_s], dist.ReduceOp.MAX if world > 1 else None)
+    n_total, rays_total, launches_total, h2d_total, d2h_total = over_ranks([n_local, rays, launches, h2d, d2h], dist.ReduceOp.SUM if world > 1 else None)
+
+    # ---- other configurations and strong scaling (bounded: a few steps each)
+    extras = None
+    if not args.no_extras:
+        extras = run_extras(acn, torch, dist, args, local_rank, rank, world, barrier, over_ranks)
 
     if rank != 0:
+        rig.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -342,23 +397,15 @@ def main():
 
     # ---- roofline of the dominant kernel + CPU baseline (rank 0, N = 1 only for the CPU leg)
     fp32_peak = acn.measure_fp32_peak_tflops(local_rank)
-    class_names = ["k_primary", "k_rays", "k_path", "k_direct", "k_shade", "k_index", "k_sched+k_pop"]
+    class_names = ["k_primary", "k_rays", "k_path", "k_direct", "k_shade", "k_index", "k_sched"]
     dom = int(np.argmax(kernel_ms[:4]))
     roof = {"bound": "fp32", "kernel": class_names[dom], "achieved": None, "peak": fp32_peak, "unit": "TFLOP/s", "frac": None,
-            "traffic": None, "peak_source": "measured live: dependent-free FFMA chains on every SM (acn_measure_fp32_peak_tflops)",
+            "traffic": None, "traffic_note": "not measured live; per-kernel DRAM bytes of an ncu --set full capture are in profiles/r02_*",
+            "peak_source": "measured live: dependent-free FFMA chains on every SM (acn_measure_fp32_peak_tflops)",
             "kernel_ms_per_step": {class_names[i]: kernel_ms[i] / args.steps for i in range(7)},
             "kernel_launches_per_step": {class_names[i]: kernel_cnt[i] / args.steps for i in range(7)},
             "kernel_share_of_step": {class_names[i]: kernel_ms[i] / args.steps / prof_step_ms for i in range(7)},
-            "kernel_timing": "CUDA-event pairs around every launch of the four tracing kernels in one extra untimed step"}
-    # DRAM traffic of the dominant kernel per launch: from the committed ncu capture (dram__bytes_read + write), not live
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        k = tr["kernels"].get(class_names[dom])
-        if k:
-            roof["traffic"] = k["dram_bytes_per_launch"]
-            roof["traffic_source"] = tr["source"] + f"; that launch took {k['launch_us']:.0f} us under ncu"
-    except Exception:
-        pass
+            "kernel_timing": "CUDA-event pairs around every launch of the tracing kernels in one extra untimed step (kernels serialised)"}
     cpu = None
     if not args.no_cpu_baseline:
         # N > 1: the oracle runs a smaller sample on rank 0 only to count the algorithmic FLOPs of rank 0's share (the
@@ -389,27 +436,82 @@ def main():
         roof["queue_gbs"] = roof["queue_bytes_per_step"] / (total_ms / args.steps * 1e-3) / 1e9
         roof["scope"] = "rank 0 (per GPU)"
         if world == 1:
-          cpu = {"value": len(xs) / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                 "sample": f"{len(xs)} of the {n_local} samples of one step (every {stride}th), FP64 oracle, position-hash seeding",
-                 "rays_per_sec": info["rays"] / dt, "oracle_rays_per_sample": info["rays"] / len(xs)}
+            cpu = {"value": len(xs) / dt, "unit": UNIT, "cores": threads, "kind": "port", "flags": CPU_FLAGS,
+                   "sample": f"{len(xs)} of the {n_local} samples of one step (every {stride}th), FP64 oracle, position-hash seeding",
+                   "rays_per_sec": info["rays"] / dt, "oracle_rays_per_sample": info["rays"] / len(xs)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (reference scene script, flattened)",
-        "config": workload_config(args.scene, prm, world),
+        "config": workload_config(args.scene, prm, world, scripted_wh),
         "rays_per_sec": rays_total / (total_ms * 1e-3), "rays_per_step": rays_total / args.steps,
         "rays_by_class_per_step": {k: v / args.steps for k, v in stats_by_class.items()} if world == 1 else None,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_total * 16, "d2h_bytes_per_step": n_total * 12},
-        "gpu_launches": launches_total,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
+                "what": "acn_render_samples with pinned host buffers" if world == 1 else
+                        "per rank: H2D of its positions, trace, accumulate, all-reduce of the pass sums, D2H of the reduced image"},
+        "gpu_launches": int(launches_total),
         "clocks": clk,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "extras": extras,
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
+    rig.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(acn, torch, dist, args, local_rank, rank, world, barrier, over_ranks):
+    """Strong scaling of the headline pass and pass 0 of the other BASELINE.json configs, split over the ranks by pixel tile;
+    frames of the video dealt to the ranks.  Device-resident, CUDA events, max over ranks, 3 steps (1 for the lamps)."""
+    MAX = dist.ReduceOp.MAX if world > 1 else None
+    SUM = dist.ReduceOp.SUM if world > 1 else None
+    out = {"strong": None, "configs": {}, "video": None,
+           "how": "pass 0 (every pixel centre) as scripted, pixel tiles dealt to the ranks, all-reduce of the pass sums inside the timed region; "
+                  "ms = max over ranks of the CUDA-event time, mean of the steps"}
+
+    def one(name, ov, steps, warmup):
+        flat = acn.scenes.load(name, **ov)
+        rig = Rig(acn, torch, dist, flat, local_rank, rank, world)
+        ms, _ = rig.timed(steps, warmup, None, barrier)
+        (t,) = over_ranks([sum(ms)], MAX)
+        n, rays = over_ranks([rig.n_local, rig.rays], SUM)
+        rec = {"width": flat.params.image_width, "height": flat.params.image_height, "direct_samples": flat.params.direct_samples,
+               "path_samples": flat.params.path_samples, "samples_per_step": int(n), "ms_per_step": t / steps,
+               "samples_per_sec": n * steps / (t * 1e-3), "rays_per_sec": rays / (t * 1e-3), "rays_per_step": rays / steps,
+               "specialised_kernels": rig.specialised, "steps": steps}
+        rig.close()
+        return rec
+
+    if world > 1:
+        out["strong"] = one(args.scene, {}, 3, 1)
+    out["configs"]["many_spheres"] = one("many_spheres", {}, 3, 1)
+    out["configs"]["diamond"] = one("diamond", {}, 3, 1)
+    out["configs"]["primitives_320x240_ds10_ps0"] = one("primitives", dict(image_width=320, image_height=240, direct_samples=10, path_samples=0), 3, 1)
+    out["configs"]["hanging_lamps_in_row_640x360"] = one("hanging_lamps_in_row", dict(image_width=640, image_height=360), 1, 0)
+
+    # C5: frames of diamond_video.acn (the ones committed under scenes/), frame i -> rank i mod N, no communication
+    frames = sorted(f[:-4] for f in os.listdir(os.path.join(ROOT, "scenes")) if f.startswith("diamond_video_"))
+    mine = [f for i, f in enumerate(frames) if i % world == rank]
+    rigs = [Rig(acn, torch, None, acn.scenes.load(f), local_rank, 0, 1) for f in mine]      # same structure: one compiled module
+    for r in rigs:
+        r.step()
+    barrier()
+    t0 = time.perf_counter()
+    ms = 0.0
+    for r in rigs:
+        m, _ = r.timed(1, 0)
+        ms += m[0]
+    torch.cuda.synchronize()
+    (t,) = over_ranks([ms], MAX)
+    n, rays = over_ranks([sum(r.n_local for r in rigs), sum(r.rays for r in rigs)], SUM)
+    for r in rigs:
+        r.close()
+    out["video"] = {"frames": len(frames), "what": "pass 0 of every committed frame of diamond_video.acn (400x300, ds 50, ps 50), frame i on rank i mod N",
+                    "ms_total": t, "frames_per_sec": len(frames) / (t * 1e-3), "samples_per_sec": n / (t * 1e-3), "rays_per_sec": rays / (t * 1e-3)}
+    return out
 
 
 if __name__ == "__main__":

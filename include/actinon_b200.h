@@ -369,6 +369,9 @@ int  acn_dimage_create( int device, int32_t width, int32_t height, acn_dimage** 
 void acn_dimage_destroy( acn_dimage* d );
 /* pixels are dealt to the ranks in tile x tile squares along a Morton curve; default: one rank */
 int  acn_dimage_set_shard( acn_dimage* d, int32_t n_ranks, int32_t rank, int32_t tile );
+/* the rank that owns pixel (x, y) under that dealing (pure host function; -1 on bad arguments) */
+int32_t acn_pixel_owner( int32_t x, int32_t y, int32_t tile, int32_t n_ranks );
+int  acn_dimage_reset( acn_dimage* d );                                                    /* lum_image_s_reset, scene.c:790-800 */
 int32_t  acn_dimage_cycle( const acn_dimage* d );
 uint64_t acn_dimage_rval( const acn_dimage* d );
 void*    acn_dimage_stream( acn_dimage* d );                                                /* cudaStream_t of its kernels */

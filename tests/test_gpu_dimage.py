@@ -46,7 +46,12 @@ def test_device_controller_draws_the_same_samples_and_gives_the_same_image(name,
     assert k == len(lists) == prm.gradient_cycles + 1
     img_d = d.download()
     assert img_d.cycle == img_h.cycle and img_d.rval == img_h.rval
-    assert np.array_equal(img_d.sums(), img_h.sums())
+    # the host sums doubles, the device Q20.44 integers: a sample value below 2^-20 (or a jittered position, whose 53-bit
+    # mantissa reaches below 2^-44) is rounded to 2^-45 before it is added; everything else is exact
+    sd, sh = img_d.sums(), img_h.sums()
+    assert np.array_equal(sd[..., 5], sh[..., 5])
+    assert np.abs(sd - sh).max() < 1e-9
+    assert np.array_equal(img_d.average(), img_h.average())
     assert img_d.write_pnm(None) == img_h.write_pnm(None)
     d.close(); t.close()
 
