@@ -551,6 +551,26 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
 // element lists and its CSG programs — as straight-line code over the same leaf functions, and replaces scene_query.
 // ---------------------------------------------------------------------------------------------
 #if defined(ACN_SPEC)
+// the quadric leaf code once per kernel, out of line (everything by value: see dist_hit_ool)
+template <typename R> struct Ev2 { R t0, t1; int c, s0; };
+template <typename R, bool SH> __device__ __noinline__ Ev2<R> squaroid_events_ool_( SceneView<R, SH> sv, int n, Ray<R> ray )
+{
+    Ev2<R> e; e.t0 = e.t1 = R( 0 ); e.s0 = 0;
+    e.c = leaf_events<false>( sv, K_SQUAROID, n, ray, &e.s0, &e.t0, &e.t1 );
+    return e;
+}
+template <typename R, bool SH> __device__ __forceinline__ int squaroid_events_ool( const SceneView<R, SH>& sv, int n, const Ray<R>& ray, int* s0, R* t0, R* t1 )
+{
+    const Ev2<R> e = squaroid_events_ool_( sv, n, ray );
+    *s0 = e.s0; *t0 = e.t0; *t1 = e.t1;
+    return e.c;
+}
+template <typename R, bool SH> __device__ __noinline__ HitN<R> squaroid_hit_ool( SceneView<R, SH> sv, int n, Ray<R> ray, bool want_nor )
+{
+    HitN<R> h; h.n = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    h.a = prim_hit( sv, K_SQUAROID, n, ray, want_nor ? &h.n : ( V3<R>* )nullptr );
+    return h;
+}
 #include "acn_spec_gen.h"
 #endif
 

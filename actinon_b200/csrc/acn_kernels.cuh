@@ -64,7 +64,7 @@ template <typename R> struct DParams
     SceneView<R> sv;
     const DMat<R>*   mats;
     const DLight<R>* lights;
-    int   n_lights;
+    int   n_lights, n_materials;
     int   n_nodes, n_children, n_prog;
     int   width, height;
     R     gamma;
@@ -375,9 +375,9 @@ template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> stage
 }
 
 // obj_color (objects.c:411-422) with txm_plain / txm_chess (textures.c:99-102,142-148)
-template <typename R, bool SH> __device__ __forceinline__ V3<R> obj_color( const DParams<R>& prm, const SceneView<R, SH>& sv0, int node, V3<R> pos )
+template <typename R, bool SH> __device__ __forceinline__ V3<R> obj_color( const DMat<R>* mats, const SceneView<R, SH>& sv0, int node, V3<R> pos )
 {
-    const DMat<R>& m = prm.mats[ sv0.link[ node ].w ];
+    const DMat<R>& m = mats[ sv0.link[ node ].w ];
     if( m.tex_kind == TEX_NONE )  return v3<R>( m.color[ 0 ], m.color[ 1 ], m.color[ 2 ] );
     if( m.tex_kind == TEX_PLAIN ) return v3<R>( m.tex1[ 0 ], m.tex1[ 1 ], m.tex1[ 2 ] );
     R u, v;
@@ -415,9 +415,17 @@ template <typename R> __device__ __forceinline__ void write_ray( const Wave<R>& 
     w.rays_out.o_i[ slot ] = a; w.rays_out.d_[ slot ] = b; w.rays_out.tp[ slot ] = c; w.rays_out.meta[ slot ] = m;
 }
 
+#define ACN_BLOCK 128
+#define ACN_SHADE_MATS 24
+struct ShadeShared
+{
+    unsigned long long n_ab[ ACN_BLOCK / 32 ], base_ab, base_t, c0;
+    unsigned int n_t[ ACN_BLOCK / 32 ];
+};
+
 // ---------------------------------------------------------------------------------------------
 // scene_s_lum (scene.c:420-667) for one hit per lane: emits child rays and at most one diffuse task.
-// WARP-COOPERATIVE: all 32 lanes call it (live = this lane holds a hit).  The surface response is planned first —
+// BLOCK-COOPERATIVE: all threads of the block call it (live = this thread holds a hit).  The surface response is planned first —
 // which of the reflection / chromatic / refraction rays and the diffuse task this hit spawns, with the intensity
 // each stage passes on (scene.c updates `intensity` between the stages) — then the warp reserves the queue slots of
 // ALL its emissions with one atomic for the rays and one for the tasks, then the lanes write.  With an atomic per
@@ -425,18 +433,19 @@ template <typename R> __device__ __forceinline__ void write_ray( const Wave<R>& 
 // latency of those atomics: 2 TB/s, and slower with more resident warps.
 // ---------------------------------------------------------------------------------------------
 template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const Wave<R>& w, const SceneView<R, SH>& sv0, bool live, const Ray<R>& ray, R a, R hit_eps,
-                                                                          const Trans<R>& tr, int depth, R I, V3<R> tp, int sample, u64 key, int lane )
+                                                                          const Trans<R>& tr, int depth, R I, V3<R> tp, int sample, u64 key, int lane,
+                                                                          ShadeShared* sh, const DMat<R>* mats, unsigned long long base_a, unsigned long long base_b )
 {
     const DParams<R>& prm = w.prm;
     live = live && !( depth == 0 || I < prm.min_intensity );                             // scene.c:428
     const V3<R> pos = madd( ray.p, ray.d, a );
     const DMat<R>* me = nullptr;
-    if( live && tr.enter_obj >= 0 ) me = &prm.mats[ sv0.link[ tr.enter_obj ].w ];
+    if( live && tr.enter_obj >= 0 ) me = &mats[ sv0.link[ tr.enter_obj ].w ];
     if( live && me && me->radiance > R( 0 ) )                                            // scene.c:432-437
     {
         R d2 = sqr( pos - xyz( sv0.geo[ tr.enter_obj * GEO_STRIDE ] ) );
         R li = d2 > R( 0 ) ? me->radiance / d2 : Num<R>::mag();
-        add_sample( w, sample, mul( obj_color( prm, sv0, tr.enter_obj, pos ), tp ) * ( li * I ) );
+        add_sample( w, sample, mul( obj_color( mats, sv0, tr.enter_obj, pos ), tp ) * ( li * I ) );
         agg_count( &w.sc->stats[ ST_LIGHT ] );
         live = false;
     }
@@ -455,7 +464,7 @@ template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const
         }
         if( tr.exit_obj >= 0 )                                                           // scene.c:464-470, 656-664
         {
-            const DMat<R>& mx = prm.mats[ sv0.link[ tr.exit_obj ].w ];
+            const DMat<R>& mx = mats[ sv0.link[ tr.exit_obj ].w ];
             nrel /= mx.refr; F = R( 1 ); C = R( 0 ); Dff = R( 0 ); T = true;
             if( a > R( 0 ) )
             {
@@ -480,27 +489,44 @@ template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const
         if( T && I >= prm.min_intensity ) { do_refr = true; I_refr = I; }                // scene.c:633-653
     }
 
-    // ---- reserve: one atomic per warp and end of the ray stack, one for the tasks.  Reflection and chromatic rays go
-    // to end A of the stack, refraction rays to end B: a k_rays warp then traces 32 rays of one kind (reflections leave
-    // the solid they were born on, refractions cross it: different envelope gates, different numbers of crossings)
-    // without a separate partitioning pass over the wave.
+    // ---- reserve: ONE atomic per block for the rays of both ends of the stack (A in the low, B in the high 32 bits of one
+    // word) and one for the tasks.  The L2 atomic unit serialises operations on one address (about one per clock): with
+    // an atomic per warp and 32 hits, k_shade ran at the rate of that one address (4 M atomics, 4 ms per wine_glass
+    // pass) whatever else was done to it.  Reflection and chromatic rays go to end A of the stack, refraction rays to end
+    // B: a k_rays warp then traces 32 rays of one kind (reflections leave the solid they were born on, refractions cross
+    // it: different envelope gates, different numbers of crossings) without a separate partitioning pass over the wave.
     const unsigned int lt = ( 1u << lane ) - 1u;
+    const int wid = threadIdx.x >> 5;
     const unsigned int m_refl = __ballot_sync( ACN_FULL, do_refl ), m_chro = __ballot_sync( ACN_FULL, do_chro );
     const unsigned int m_refr = __ballot_sync( ACN_FULL, do_refr ), tmask = __ballot_sync( ACN_FULL, do_diff );
-    unsigned long long abbase = 0, tbase = 0;
     if( lane == 0 )
     {
-        const unsigned long long nab = ( unsigned long long )( __popc( m_refl ) + __popc( m_chro ) ) | ( ( unsigned long long )__popc( m_refr ) << 32 );
-        if( nab ) abbase = atomicAdd( &w.sc->out_ab, nab );
-        if( tmask ) tbase = atomicAdd( &w.sc->tasks_new, ( unsigned long long )__popc( tmask ) );
+        sh->n_ab[ wid ] = ( unsigned long long )( __popc( m_refl ) + __popc( m_chro ) ) | ( ( unsigned long long )__popc( m_refr ) << 32 );
+        sh->n_t[ wid ] = ( unsigned int )__popc( tmask );
     }
-    abbase = __shfl_sync( ACN_FULL, abbase, 0 ); tbase = __shfl_sync( ACN_FULL, tbase, 0 );
+    __syncthreads();
+    if( threadIdx.x == 0 )
+    {
+        unsigned long long tot_ab = 0; unsigned int tot_t = 0;
+        #pragma unroll
+        for( int k = 0; k < ACN_BLOCK / 32; k++ )
+        {
+            const unsigned long long v = sh->n_ab[ k ]; const unsigned int t = sh->n_t[ k ];
+            sh->n_ab[ k ] = tot_ab; sh->n_t[ k ] = tot_t;            // exclusive prefix over the warps
+            tot_ab += v; tot_t += t;
+        }
+        sh->base_ab = tot_ab ? atomicAdd( &w.sc->out_ab, tot_ab ) : 0ull;
+        sh->base_t = tot_t ? atomicAdd( &w.sc->tasks_new, ( unsigned long long )tot_t ) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long abbase = sh->base_ab + sh->n_ab[ wid ], tbase = sh->base_t + sh->n_t[ wid ];
+    __syncthreads();                                                    // the scratch is rewritten by the next group
     const unsigned long long abase = abbase & 0xFFFFFFFFull, bbase = abbase >> 32;
     if( !live ) return;
     // slots: end A counts up from slot 0, end B down from the last slot; the two ends must not meet (checked again, for
-    // the whole iteration, by k_sched: a lane only sees its own slots)
-    unsigned long long aslot = w.sc->base_a + abase + __popc( m_refl & lt ) + __popc( m_chro & lt );
-    const unsigned long long bidx = w.sc->base_b + bbase + __popc( m_refr & lt );
+    // the whole iteration, by k_sched: a thread only sees its own slots)
+    unsigned long long aslot = base_a + abase + __popc( m_refl & lt ) + __popc( m_chro & lt );
+    const unsigned long long bidx = base_b + bbase + __popc( m_refr & lt );
     if( ( ( do_refl || do_chro ) && aslot + 2 > w.rays_cap ) || ( do_refr && bidx >= w.rays_cap ) ) { w.sc->overflow = 1; return; }
     const unsigned long long bslot = w.rays_cap - 1ull - bidx;
 
@@ -509,7 +535,7 @@ template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const
         write_ray( w, aslot++, pos, reflect( ray.d, tr.exit_nor ), I_refl, depth - 1, tp, RC_REFLECT, sample, mix64( key, KEY_REFLECT ) );
     if( do_chro )
     {
-        V3<R> col = obj_color( prm, sv0, tr.enter_obj, pos );
+        V3<R> col = obj_color( mats, sv0, tr.enter_obj, pos );
         write_ray( w, aslot++, pos, reflect( ray.d, tr.exit_nor ), I_chro, depth - 1, mul( tp, col ), RC_CHROMATIC, sample, mix64( key, KEY_CHROMATIC ) );
     }
     if( do_diff )
@@ -521,7 +547,7 @@ template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const
         u64 rv0 = sv0.seed_mode == SEED_POSITION_HASH
                       ? random_seed( pos, ( u64 )3294479285ull ) + random_seed( nrm, ( u64 )3247146734ull )
                       : mix64( key, KEY_DIFFUSE );
-        V3<R> col = obj_color( prm, sv0, tr.enter_obj, pos );
+        V3<R> col = obj_color( mats, sv0, tr.enter_obj, pos );
         unsigned long long nd = ( unsigned long long )( ( double )prm.direct_samples * ( double )Id );   // scene.c:553
         if( nd == 0 ) nd = 1;
         unsigned long long np = 0;
@@ -634,7 +660,6 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R light_hi
 // ---------------------------------------------------------------------------------------------
 // kernels — all persistent: fixed grid, warps fetch chunks of work through a cursor in Sched
 // ---------------------------------------------------------------------------------------------
-#define ACN_BLOCK 128
 #ifndef ACN_CHUNK
 #define ACN_CHUNK 2        // 32-item groups per cursor fetch when a launch has plenty of work
 #endif
@@ -853,24 +878,38 @@ k_shade( Wave<R> w, HitBuf<R> in )
     if( count > w.hits_cap ) count = w.hits_cap;
     if( count == 0 || w.sc->overflow ) return;
     const int chunk = launch_chunk( count >> 5 );
-    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks
+    if( ( unsigned long long )blockIdx.x * ACN_BLOCK * chunk >= count ) return;                      // more blocks than chunks
+    __shared__ ShadeShared sh;
+    __shared__ DMat<R> s_mats[ ACN_SHADE_MATS ];
+    // the materials next to the staged node table: a hit's surface response starts with two material records
+    const DMat<R>* mats = w.prm.mats;
+    if( w.prm.n_materials <= ACN_SHADE_MATS )
+    {
+        for( int i = threadIdx.x; i < w.prm.n_materials; i += blockDim.x ) s_mats[ i ] = w.prm.mats[ i ];
+        mats = s_mats;
+    }
+    const unsigned long long base_a = w.sc->base_a, base_b = w.sc->base_b;      // fixed for the iteration
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    __syncthreads();
     const int lane = threadIdx.x & 31;
+    // the BLOCK fetches ACN_BLOCK * chunk hits per cursor atomic and reserves the queue slots of ACN_BLOCK hits per atomic
     for( ;; )
     {
-        const unsigned long long c0 = warp_fetch( &w.sc->cur_shade, 32ull * chunk, lane );
+        if( threadIdx.x == 0 ) sh.c0 = atomicAdd( &w.sc->cur_shade, ( unsigned long long )ACN_BLOCK * chunk );
+        __syncthreads();
+        const unsigned long long c0 = sh.c0;
         if( c0 >= count ) break;
         for( int g = 0; g < chunk; g++ )
         {
-            const unsigned long long i = c0 + 32ull * g + lane;
-            if( c0 + 32ull * g >= count ) break;
+            const unsigned long long i = c0 + ( unsigned long long )ACN_BLOCK * g + threadIdx.x;
+            if( c0 + ( unsigned long long )ACN_BLOCK * g >= count ) break;                           // block-uniform
             const bool live = i < count;
-            const unsigned long long il = live ? i : count - 1;          // dead lanes of the last group read a valid record and ignore it
+            const unsigned long long il = live ? i : count - 1;          // dead threads of the last group read a valid record and ignore it
             const R4<R> oa = in.o_a[ il ], di = in.d_i[ il ], ne = in.n_e[ il ], tp = in.tp[ il ];
             const I4 m = in.meta[ il ];
             Ray<R> ray; ray.p = xyz( oa ); ray.d = xyz( di );
             Trans<R> tr; tr.exit_nor = xyz( ne ); tr.exit_obj = m.z; tr.enter_obj = m.w;
-            shade_hits( w, sv0, live, ray, oa.w, ne.w, tr, m.x, di.w, xyz( tp ), m.y, in.key[ il ], lane );
+            shade_hits( w, sv0, live, ray, oa.w, ne.w, tr, m.x, di.w, xyz( tp ), m.y, in.key[ il ], lane, &sh, mats, base_a, base_b );
         }
     }
 }

@@ -33,7 +33,18 @@ struct SpecGen
     int n_elements = 0, n_programs = 0;
 
     static const int MAX_ELEMENTS = 64;              // unrolled element tests per scene query
-    static const int MAX_RUN_UNROLL = 96;
+    // Code size: the instruction caches hold 32 KB (L1.5) = 2 000 instructions; straight-line code that every ray walks
+    // end to end streams from L2, and warps in different places thrash it (diamond_video: 8 000-instruction kernels ran
+    // 2.3x SLOWER than the interpreter).  Long convex runs are therefore LOOPS over their member words (kind literal
+    // when the run is homogeneous), and the quadric leaf code exists once, out of line.
+    int run_unroll = 6;                              // runs of more members than this become loops
+    bool ool_squaroid = true;                        // squaroid leaves / elements through one out-of-line function
+
+    void read_env()
+    {
+        const char* e = getenv( "ACN_SPEC_RUN_UNROLL" ); if( e && e[ 0 ] ) run_unroll = atoi( e );
+        e = getenv( "ACN_SPEC_OOL_SQUAROID" ); if( e && e[ 0 ] ) ool_squaroid = e[ 0 ] != '0';
+    }
 
     void p( const char* fmt, ... )
     {
@@ -117,7 +128,8 @@ struct SpecGen
                 const int k = kind( n );
                 ncross[ v ] = max_crossings( k );
                 p( "    {   // variable %d: leaf %d\n        int s0; R a0 = R( 0 ), a1 = R( 0 );\n", v, n );
-                p( "        const int c = leaf_events<false>( sv, %d, %d, ray, &s0, &a0, &a1 );\n", k, n );
+                if( k == ACN_KIND_SQUAROID && ool_squaroid ) p( "        const int c = squaroid_events_ool( sv, %d, ray, &s0, &a0, &a1 );\n", n );
+                else p( "        const int c = leaf_events<false>( sv, %d, %d, ray, &s0, &a0, &a1 );\n", k, n );
                 p( "        vars |= ( %s )s0 << %d;\n", VT, v );
                 p( "        if( c >= 1 && a0 <= t_far ) { t0_%d = a0; k0_%d = %d; }\n", v, v, id | ( v << 8 ) );
                 if( ncross[ v ] == 2 ) p( "        if( c == 2 && a1 <= t_far ) { t1_%d = a1; k1_%d = %d; }\n", v, v, id | ( v << 8 ) | ( 1 << 16 ) );
@@ -128,17 +140,40 @@ struct SpecGen
             {
                 p( "    {   // variable %d: convex run of %d members, inside-set = [ max entry, min exit ]\n", v, n );
                 p( "        R lo = R( -1 ), hi = inf; int i0 = %d, i1 = %d; bool alive = true;\n", ( int )CSG_VIRTUAL, ( int )CSG_VIRTUAL );
-                int open = 0;
-                for( int m = 1; m <= n; m++ )
+                // consecutive members of one kind (and one sign) form a segment: a long segment is a LOOP over its member words
+                // (they are in the staged program table) with the kind literal, a short one is unrolled
+                for( int m0 = 1; m0 <= n; )
                 {
-                    const int w = ( *prog )[ pc + m ], node = w >> 4;
-                    if( m > 1 && ( m - 1 ) % 8 == 0 ) { p( "        if( __any_sync( __activemask(), alive ) ) {\n" ); open++; }
-                    p( "        if( alive ) { int ms0; R a0 = R( 0 ), a1 = R( 0 ), mlo, mhi; const int mc = leaf_events<false>( sv, %d, %d, ray, &ms0, &a0, &a1 );%s\n",
-                       kind( node ), node, ( w & 15 ) == CSG_MEMBER_NEG ? " ms0 ^= 1;" : "" );
-                    p( "            member_interval( ms0, mc, a0, a1, &mlo, &mhi ); if( mlo > lo ) { lo = mlo; i0 = %d; } if( mhi < hi ) { hi = mhi; i1 = %d; }\n", id + m, id + m );
-                    p( "            if( !( lo < hi ) || lo > t_far ) { lo = inf; alive = false; } }\n" );
+                    const int w0 = ( *prog )[ pc + m0 ], k0 = kind( w0 >> 4 ), neg0 = ( w0 & 15 ) == CSG_MEMBER_NEG;
+                    int m1 = m0;
+                    while( m1 + 1 <= n && kind( ( *prog )[ pc + m1 + 1 ] >> 4 ) == k0 && ( ( ( *prog )[ pc + m1 + 1 ] & 15 ) == CSG_MEMBER_NEG ) == neg0 ) m1++;
+                    const int len = m1 - m0 + 1;
+                    if( len > run_unroll )
+                    {
+                        p( "        if( __any_sync( __activemask(), alive ) )\n        {\n" );
+                        p( "            #pragma unroll 1\n            for( int m = %d; m <= %d; m++ )\n            {\n", m0, m1 );
+                        p( "                const int node = sv.prog[ %d + m ] >> 4;\n", pc );
+                        p( "                if( alive ) { int ms0; R a0 = R( 0 ), a1 = R( 0 ), mlo, mhi;\n" );
+                        if( k0 == ACN_KIND_SQUAROID && ool_squaroid ) p( "                    const int mc = squaroid_events_ool( sv, node, ray, &ms0, &a0, &a1 );%s\n", neg0 ? " ms0 ^= 1;" : "" );
+                        else p( "                    const int mc = leaf_events<false>( sv, %d, node, ray, &ms0, &a0, &a1 );%s\n", k0, neg0 ? " ms0 ^= 1;" : "" );
+                        p( "                    member_interval( ms0, mc, a0, a1, &mlo, &mhi ); if( mlo > lo ) { lo = mlo; i0 = %d + m; } if( mhi < hi ) { hi = mhi; i1 = %d + m; }\n", id, id );
+                        p( "                    if( !( lo < hi ) || lo > t_far ) { lo = inf; alive = false; } }\n" );
+                        p( "                if( ( m & 7 ) == 0 && !__any_sync( __activemask(), alive ) ) break;\n            }\n        }\n" );
+                    }
+                    else
+                    {
+                        for( int m = m0; m <= m1; m++ )
+                        {
+                            const int node = ( *prog )[ pc + m ] >> 4;
+                            p( "        if( alive ) { int ms0; R a0 = R( 0 ), a1 = R( 0 ), mlo, mhi; " );
+                            if( k0 == ACN_KIND_SQUAROID && ool_squaroid ) p( "const int mc = squaroid_events_ool( sv, %d, ray, &ms0, &a0, &a1 );%s\n", node, neg0 ? " ms0 ^= 1;" : "" );
+                            else p( "const int mc = leaf_events<false>( sv, %d, %d, ray, &ms0, &a0, &a1 );%s\n", k0, node, neg0 ? " ms0 ^= 1;" : "" );
+                            p( "            member_interval( ms0, mc, a0, a1, &mlo, &mhi ); if( mlo > lo ) { lo = mlo; i0 = %d; } if( mhi < hi ) { hi = mhi; i1 = %d; }\n", id + m, id + m );
+                            p( "            if( !( lo < hi ) || lo > t_far ) { lo = inf; alive = false; } }\n" );
+                        }
+                    }
+                    m0 = m1 + 1;
                 }
-                for( int k = 0; k < open; k++ ) p( "        }\n" );
                 p( "        if( lo < R( 0 ) ) { vars |= ( %s )1 << %d; if( hi <= t_far ) { t0_%d = hi; k0_%d = i1 | %d; } }\n", VT, v, v, v, v << 8 );
                 p( "        else if( lo < hi ) { t0_%d = lo; k0_%d = i0 | %d; if( hi <= t_far ) { t1_%d = hi; k1_%d = i1 | %d; } }\n",
                    v, v, v << 8, v, v, ( v << 8 ) | ( 1 << 16 ) );
@@ -213,7 +248,8 @@ struct SpecGen
         else               p( "%s    if( !found )\n", ind );
         p( "%s    {\n%s        V3<R> n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); R a;\n", ind, ind );
         bool roughen_here = rough( e );
-        if( simple_leaf( k ) ) p( "%s        a = prim_hit( sv, %d, %d, ray, want_trans ? &n : ( V3<R>* )nullptr );\n", ind, k, e );
+        if( k == ACN_KIND_SQUAROID && ool_squaroid ) p( "%s        { const HitN<R> h = squaroid_hit_ool( sv, %d, ray, want_trans ); a = h.a; n = h.n; }\n", ind, e );
+        else if( simple_leaf( k ) ) p( "%s        a = prim_hit( sv, %d, %d, ray, want_trans ? &n : ( V3<R>* )nullptr );\n", ind, k, e );
         else if( k >= ACN_KIND_PAIR_INSIDE && program_ok( e ) ) p( "%s        a = csg_spec_%d<R, SH>( sv, ray, want_trans ? &n : ( V3<R>* )nullptr, ctx, hor );\n", ind, e );
         else { p( "%s        a = elem_hit<R, MARCH>( sv, sv.link[ %d ], %d, ray, want_trans ? &n : ( V3<R>* )nullptr, ctx, cm, hor );\n", ind, e, e ); roughen_here = false; }
         if( roughen_here ) p( "%s        if( want_trans && a < inf ) roughen( sv, %d, ray, a, &n, ctx );\n", ind, e );
@@ -278,6 +314,7 @@ struct SpecGen
     bool generate()
     {
         out.clear(); n_elements = 0; n_programs = 0;
+        read_env();
         if( !count_elements( fs->light_root, 0 ) || !count_elements( fs->matter_root, 0 ) ) return false;
         p( "// generated by SpecGen (acn_spec.h): structure of one scene, %d nodes, %d element tests\n", fs->n_nodes, n_elements );
         p( "#define ACN_SPEC_SCENE 1\n\n" );

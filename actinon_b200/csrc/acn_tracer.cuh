@@ -656,7 +656,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     prm.sv.prog = d_prog; prm.sv.prog_ref = d_prog_ref; prm.sv.parent = d_parent; prm.n_prog = n_prog;
     prm.sv.eps = ( R )eps; prm.sv.light_root = fs->light_root; prm.sv.matter_root = fs->matter_root;
     prm.sv.seed_mode = opt->seed_mode;
-    prm.mats = d_mats; prm.lights = d_lights; prm.n_lights = lroot.child1;
+    prm.mats = d_mats; prm.lights = d_lights; prm.n_lights = lroot.child1; prm.n_materials = fs->n_materials;
     prm.n_nodes = n; prm.n_children = fs->n_children;
     prm.width = p.image_width; prm.height = p.image_height;
     prm.gamma = ( R )p.gamma;

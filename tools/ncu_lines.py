@@ -7,6 +7,9 @@ skip = sys.argv[5] if len(sys.argv) > 5 else "0"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:" + kre,
                       "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+for k in range(2, len(rows)):                 # some ncu versions print the kernel twice
+    if rows[k] and rows[k][0] == "Kernel Name":
+        rows = rows[:k]; break
 hdr = rows[1]
 col = {k: i for i, k in enumerate(hdr)}
 ins = rows[2:]

@@ -1,25 +1,26 @@
 #!/usr/bin/env python
 """Renders a scene to a .pnm like `actinon <script.acn>` does — on 1..8 B200s.
 
-    python tools/render.py --scene wine_glass --out wine_glass.pnm [--passes K] [--width W --height H]
+    python tools/render.py --scene wine_glass --out wine_glass.pnm [--gpus N] [--passes K] [--width W --height H]
+    python tools/render.py --frames diamond_video_0000{00,10,20} --gpus 8       # frame sequence: frame i -> GPU i mod N
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/render.py --scene diamond --out d.pnm
-    ... --frames diamond_video_0000{00,10,20}     # frame sequence: frame i -> rank i mod N, no communication
 
-Within an image every rank runs the SAME host pass controller (scene.c:1103-1159: pass 0 = pixel centres, then
-gradient_cycles passes of jittered re-sampling where the image gradient exceeds the threshold) on the SAME
-accumulated image, traces only the samples whose 8x8 pixel tile it owns, and the per-pixel sums of the pass
-(position, colour, weight: scene.c:804-813) are all-reduced over NCCL — the one exchange step of the path.
+The pass controller of the reference (scene.c:1103-1159: pass 0 = pixel centres, then gradient_cycles passes of jittered
+re-sampling where the image gradient exceeds the threshold) runs ON THE DEVICE (acn_dimage_*).  Several GPUs:
+ * --gpus N in one process: acn_group_* — a worker thread, a tracer and a device image per GPU, 4x4 pixel tiles dealt to the
+   GPUs along a Morton curve, the per-pass sums exchanged through peer memory (NVLink);
+ * under torchrun (one process per GPU): the same tiles, the per-pass sums all-reduced over NCCL (uint64, exact).
+Either way the image is bit-identical to the single-GPU one.  --host-controller runs the host restatement of the pass
+controller instead (acn_image_*; one GPU), the path the device controller is tested against.
 """
 import argparse
 import os
 import sys
+import threading
 import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-TILE = 8
 
 
 def main():
@@ -27,22 +28,25 @@ def main():
     ap.add_argument("--scene", default="wine_glass")
     ap.add_argument("--frames", nargs="*", default=None, help="scene names of a frame sequence (sharded by frame)")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--gpus", type=int, default=1, help="GPUs of this process (acn_group); under torchrun: one per process")
     ap.add_argument("--passes", type=int, default=None, help="stop after this many passes (default: gradient_cycles + 1)")
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--direct-samples", type=int, default=None)
     ap.add_argument("--path-samples", type=int, default=None)
+    ap.add_argument("--generic", action="store_true", help="generic kernels instead of the scene-specialised ones")
+    ap.add_argument("--host-controller", action="store_true")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
 
-    import torch
-    import torch.distributed as dist
     import actinon_b200 as acn
-    acn.device_count()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    n_dev = acn.device_count()
+    dist = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ov = {}
     for k, v in (("image_width", args.width), ("image_height", args.height), ("direct_samples", args.direct_samples),
@@ -50,52 +54,79 @@ def main():
         if v is not None:
             ov[k] = v
 
-    def render_one(name, out, ranks, my):
-        """ranks/my: how many ranks share this image and which of them I am."""
-        flat = acn.scenes.load(name, **ov)
+    def options(device):
+        return dict(device=device, specialize=acn.SPECIALIZE_OFF if args.generic else acn.SPECIALIZE_ON)
+
+    def tracer_for(flat, device):
+        try:
+            return acn.Tracer(flat, acn.Options(**options(device)))
+        except acn.AcnError as e:
+            if e.code != -5:
+                raise
+            return acn.Tracer(flat, acn.Options(device=device, specialize=acn.SPECIALIZE_OFF))       # the scene does not qualify
+
+    def report(name, flat, img, n_samples, n_pass, rays, dt, gpus, out):
+        h = img.write_pnm(out)
         prm = flat.params
-        W, H = prm.image_width, prm.image_height
-        tracer = acn.Tracer(flat, acn.Options(device=local))
-        img = acn.Image(W, H)
+        print(f"{name}: {prm.image_width}x{prm.image_height}, {n_pass} passes, {n_samples} samples in {dt:.2f} s on {gpus} GPU(s) "
+              f"({n_samples / dt:.0f} samples/s, {rays / dt / 1e9:.2f} G rays/s); image hash {h:016x}" + (f" -> {out}" if out else ""), flush=True)
+
+    def render_one(name, out, device, group_gpus=1, use_dist=None):
+        flat = acn.scenes.load(name, **ov)
+        if group_gpus > 1:
+            try:
+                g = acn.Group(flat, list(range(group_gpus)), acn.Options(**options(-1)))
+            except acn.AcnError as e:
+                if e.code != -5:
+                    raise
+                g = acn.Group(flat, list(range(group_gpus)), acn.Options(specialize=acn.SPECIALIZE_OFF))
+            t0 = time.perf_counter()
+            n_samples, n_pass, rays = g.render(args.passes)
+            dt = time.perf_counter() - t0
+            img = g.download(); g.close()
+            report(name, flat, img, n_samples, n_pass, rays, dt, group_gpus, out)
+            return
+        tracer = tracer_for(flat, device)
         t0 = time.perf_counter()
-        n_pass, n_samples, rays = 0, 0, 0
-        while args.passes is None or n_pass < args.passes:
-            xy = img.next_pass(prm)
-            if xy.shape[0] == 0:
-                break
-            if ranks > 1:
-                tx, ty = xy[:, 0].astype(np.int64) // TILE, xy[:, 1].astype(np.int64) // TILE
-                mine = xy[(tx + ty) % ranks == my]
-            else:
-                mine = xy
-            rgb = tracer.render_samples(mine) if len(mine) else np.empty((0, 3), np.float32)
-            rays += tracer.last_stats.rays if len(mine) else 0
-            if ranks > 1:
-                delta = acn.Image(W, H)
-                delta.push(mine, rgb)
-                d = torch.from_numpy(delta.sums()).to(dev)
-                dist.all_reduce(d)                           # per-pixel sums of the pass, disjoint tiles
-                img.push(np.empty((0, 2)), np.empty((0, 3), np.float32))    # advances cycle + jitter stream like the reference
-                img.add_sums(d.cpu().numpy())
-            else:
-                img.push(mine, rgb)
-            n_samples += len(xy)
-            n_pass += 1
+        if args.host_controller:
+            img = acn.Image(flat.params.image_width, flat.params.image_height)
+            n_samples = n_pass = rays = 0
+            while args.passes is None or n_pass < args.passes:
+                xy = img.next_pass(flat.params)
+                if xy.shape[0] == 0:
+                    break
+                img.push(xy, tracer.render_samples(xy, n_samples))
+                n_samples += xy.shape[0]; n_pass += 1; rays += tracer.last_stats.rays
+        else:
+            img, n_samples, n_pass, rays = acn.render_image_device(flat, tracer, args.passes, use_dist)
         dt = time.perf_counter() - t0
-        h = img.write_pnm(out if (out and my == 0) else None)
-        if my == 0:
-            print(f"{name}: {W}x{H}, {n_pass} passes, {n_samples} samples in {dt:.2f} s on {ranks} GPU(s) "
-                  f"({n_samples / dt:.0f} samples/s, {rays * ranks / dt / 1e9:.2f} G rays/s); image hash {h:016x}"
-                  + (f" -> {out}" if out else ""), flush=True)
         tracer.close()
-        return img
+        if use_dist is not None:
+            import torch
+            t = torch.tensor([float(rays)], dtype=torch.float64, device="cuda"); use_dist.all_reduce(t); rays = float(t[0])
+        if use_dist is None or rank == 0:
+            report(name, flat, img, n_samples, n_pass, rays, dt, world if use_dist is not None else 1, out)
 
     if args.frames:
-        for i, name in enumerate(args.frames):
-            if i % world == rank:
-                render_one(name, (args.out or "frame") + f".{name}.pnm", 1, 0)
+        if world > 1:                                           # one process per GPU: frame i -> rank i mod N
+            for i, name in enumerate(args.frames):
+                if i % world == rank:
+                    render_one(name, (args.out or "frame") + f".{name}.pnm", local)
+        else:                                                   # one process: a thread per GPU, frame i -> GPU i mod N
+            gpus = max(1, min(args.gpus, n_dev))
+            def work(d):
+                for i, name in enumerate(args.frames):
+                    if i % gpus == d:
+                        render_one(name, (args.out or "frame") + f".{name}.pnm", d)
+            th = [threading.Thread(target=work, args=(d,)) for d in range(gpus)]
+            t0 = time.perf_counter()
+            for t in th: t.start()
+            for t in th: t.join()
+            print(f"{len(args.frames)} frames on {gpus} GPU(s) in {time.perf_counter() - t0:.2f} s", flush=True)
+    elif world > 1:
+        render_one(args.scene, args.out, local, 1, dist)
     else:
-        render_one(args.scene, args.out, world, rank)
+        render_one(args.scene, args.out, 0, max(1, min(args.gpus, n_dev)))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
