@@ -130,7 +130,7 @@ EXPORTED_SYMBOLS = [
     "acn_list_create", "acn_list_push", "acn_list_inside_composite", "acn_list_outside_composite", "acn_list_create_compound",
     "acn_move", "acn_rotate", "acn_scale", "acn_set_color", "acn_set_transparency", "acn_set_refractive_index",
     "acn_set_radiance", "acn_set_fresnel_reflectivity", "acn_set_chromatic_reflectivity", "acn_set_diffuse_reflectivity",
-    "acn_set_sigma", "acn_set_surface_roughness", "acn_set_material", "acn_set_envelope", "acn_set_auto_envelope",
+    "acn_set_sigma", "acn_set_surface_roughness", "acn_set_material", "acn_set_envelope", "acn_set_auto_envelope", "acn_set_bounding_envelope",
     "acn_set_texture_plain", "acn_set_texture_chess", "acn_scene_clear", "acn_scene_push",
     "acn_scene_load_acn", "acn_scene_image_name", "acn_scene_select_image", "acn_scene_flatten",
     "acn_image_create", "acn_image_destroy", "acn_image_size", "acn_image_cycle", "acn_image_rval", "acn_image_next_pass",
@@ -185,7 +185,7 @@ def load_library():
         "acn_set_refractive_index": (I, [V, I, D]), "acn_set_radiance": (I, [V, I, D]),
         "acn_set_fresnel_reflectivity": (I, [V, I, D]), "acn_set_chromatic_reflectivity": (I, [V, I, D]),
         "acn_set_diffuse_reflectivity": (I, [V, I, D]), "acn_set_sigma": (I, [V, I, D]), "acn_set_surface_roughness": (I, [V, I, D]),
-        "acn_set_material": (I, [V, I, C.c_char_p]), "acn_set_envelope": (I, [V, I, pd, D]), "acn_set_auto_envelope": (I, [V, I]),
+        "acn_set_material": (I, [V, I, C.c_char_p]), "acn_set_envelope": (I, [V, I, pd, D]), "acn_set_auto_envelope": (I, [V, I]), "acn_set_bounding_envelope": (I, [V, I]),
         "acn_set_texture_plain": (I, [V, I, pd]), "acn_set_texture_chess": (I, [V, I, pd, pd, D]),
         "acn_scene_clear": (I, [V]), "acn_scene_push": (I, [V, I]),
         "acn_scene_load_acn": (I, [V, C.c_char_p, I, P(C.c_char_p), P(I)]),
@@ -335,6 +335,10 @@ class Obj:
 
     def set_envelope(self, pos, radius: float):
         _check(self.scene._l.acn_set_envelope(self.scene._p, self.h, _vec3(pos), float(radius))); return self
+
+    def set_bounding_envelope(self):
+        """Analytic conservative bounding sphere (raises AcnError -5 for unbounded shapes)."""
+        _check(self.scene._l.acn_set_bounding_envelope(self.scene._p, self.h)); return self
 
     def set_auto_envelope(self):
         _check(self.scene._l.acn_set_auto_envelope(self.scene._p, self.h)); return self

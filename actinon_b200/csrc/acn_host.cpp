@@ -185,6 +185,13 @@ int acn_set_auto_envelope( acn_scene* s, acn_obj o )
     return ACN_ERR_INVALID_ARG;
 }
 
+int acn_set_bounding_envelope( acn_scene* s, acn_obj o )
+{
+    Obj* x = get_obj( s, o ); if( !x ) return ACN_ERR_INVALID_ARG;
+    if( !x->set_bounding_envelope() ) { acn::set_error( "set_bounding_envelope: the shape is unbounded (or a scale node): no analytic bound" ); return ACN_ERR_UNSUPPORTED; }
+    return ACN_OK;
+}
+
 int acn_set_texture_plain( acn_scene* s, acn_obj o, const double rgb[ 3 ] )
 {
     Obj* x = get_obj( s, o ); if( !x || !rgb ) return ACN_ERR_INVALID_ARG;

@@ -126,6 +126,52 @@ bool Obj::set_material( const std::string& name )
     return false;
 }
 
+bool analytic_envelope( const Obj& o, Envelope* out )
+{
+    if( o.prp.has_envelope ) { *out = o.prp.envelope; return true; }
+    switch( o.kind )
+    {
+        case ACN_KIND_SPHERE: out->pos = o.prp.pos; out->radius = o.tail[ 0 ]; return true;
+        case ACN_KIND_SQUAROID:
+        {   // a x^2 + b y^2 + c z^2 + r <= 0 with a, b, c > 0 > r: an ellipsoid with half axes sqrt( -r / a ), ...
+            const double a = o.tail[ 0 ], b = o.tail[ 1 ], c = o.tail[ 2 ], r = o.tail[ 3 ];
+            if( !( a > 0 && b > 0 && c > 0 && r < 0 ) ) return false;
+            const double m = a < b ? ( a < c ? a : c ) : ( b < c ? b : c );
+            out->pos = o.prp.pos; out->radius = sqrt( -r / m );
+            return true;
+        }
+        case ACN_KIND_DIST_SPHERE: out->pos = o.prp.pos; out->radius = 1.0 / o.tail[ 0 ]; return true;                     // unit sphere scaled by 1 / inv_scale
+        case ACN_KIND_DIST_TORUS:  out->pos = o.prp.pos; out->radius = ( 1.0 + o.tail[ 1 ] ) / o.tail[ 0 ]; return true;   // major radius 1, tube radius ex_radius
+        case ACN_KIND_PAIR_INSIDE:
+        {
+            Envelope e1, e2;
+            const bool b1 = o.o1 && analytic_envelope( *o.o1, &e1 ), b2 = o.o2 && analytic_envelope( *o.o2, &e2 );
+            if( b1 && b2 ) { *out = e1.radius <= e2.radius ? e1 : e2; return true; }
+            if( b1 ) { *out = e1; return true; }
+            if( b2 ) { *out = e2; return true; }
+            return false;
+        }
+        case ACN_KIND_PAIR_OUTSIDE:
+        {
+            Envelope e1, e2;
+            if( !( o.o1 && o.o2 && analytic_envelope( *o.o1, &e1 ) && analytic_envelope( *o.o2, &e2 ) ) ) return false;
+            *out = envelope_of_pair( e1, e2 );
+            return true;
+        }
+        default: return false;
+    }
+}
+
+bool Obj::set_bounding_envelope()
+{
+    Envelope e;
+    if( !analytic_envelope( *this, &e ) ) return false;
+    e.radius *= 1.0 + 1E-9;          // the shell of thickness eps around the surface stays inside
+    e.radius += 4E-6;
+    prp.has_envelope = true; prp.envelope = e;
+    return true;
+}
+
 void Obj::set_auto_envelope()
 {
     Envelope e = estimate_envelope( *this, 1000, 123, 1.1 );

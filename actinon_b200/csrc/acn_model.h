@@ -62,7 +62,15 @@ struct Obj
     void set_refractive_index( double n );       // objects.c:436-448
     bool set_material( const std::string& name ); // objects.c:1589-1682
     void set_auto_envelope();                    // objects.c:470-476
+    bool set_bounding_envelope();                // analytic bound instead of the Monte-Carlo estimate; false: shape is unbounded
 };
+
+// Conservative bounding sphere of a shape where one follows from its parameters: sphere, ellipsoid,
+// distance-field sphere / torus, A&B (the smaller of the children's bounds: either contains the intersection), A|B
+// (envelope_of_pair of the children's bounds, the reference's own rule, objects.c:113-136).  A shape's own envelope, if
+// set, counts as its bound (obj_side reports "outside" beyond it, objects.c:365-370).  false for unbounded shapes
+// (plane, cylinder, cone, hyperboloids, negations) and for scale nodes.
+bool analytic_envelope( const Obj& o, Envelope* out );
 
 std::unique_ptr<Obj> make_plane();
 std::unique_ptr<Obj> make_sphere( double radius );

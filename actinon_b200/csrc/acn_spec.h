@@ -35,10 +35,12 @@ struct SpecGen
     static const int MAX_ELEMENTS = 64;              // unrolled element tests per scene query
     // Code size: the instruction caches hold 32 KB (L1.5) = 2 000 instructions; straight-line code that every ray walks
     // end to end streams from L2, and warps in different places thrash it (diamond_video: 8 000-instruction kernels ran
-    // 2.3x SLOWER than the interpreter).  Long convex runs are therefore LOOPS over their member words (kind literal
-    // when the run is homogeneous), and the quadric leaf code exists once, out of line.
-    int run_unroll = 6;                              // runs of more members than this become loops
-    bool ool_squaroid = true;                        // squaroid leaves / elements through one out-of-line function
+    // 2.3x SLOWER than the interpreter).  Long convex runs are therefore LOOPS over their member words, one loop per
+    // segment of members of one kind (the kind stays literal); the quadric leaf code can be kept out of line.
+    // Measured (B200, ms per pass 0, profiles/r02_spec_sweep.txt): diamond 12.6 unrolled / 10.6 with segments longer than 3
+    // as loops; diamond_video frame 49: 15.9 / 12.8 (39.9 before any size control); quadrics out of line: no difference.
+    int run_unroll = 3;                              // segments of more members than this become loops
+    bool ool_squaroid = false;                       // squaroid leaves / elements through one out-of-line function
 
     void read_env()
     {

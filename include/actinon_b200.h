@@ -307,6 +307,11 @@ int acn_set_surface_roughness( acn_scene* s, acn_obj o, double v );
 int acn_set_material( acn_scene* s, acn_obj o, const char* name );    /* objects.c:1589-1682 */
 int acn_set_envelope( acn_scene* s, acn_obj o, const double pos[3], double radius );
 int acn_set_auto_envelope( acn_scene* s, acn_obj o );                 /* objects.c:470-476, compound.c:73-107 */
+/* A conservative bounding sphere from the shape's parameters instead of the reference's Monte-Carlo estimate (1000 random
+ * rays, x 1.1): sphere, ellipsoid, torus, A&B, A|B of bounded shapes.  ACN_ERR_UNSUPPORTED for unbounded shapes.  An
+ * envelope is part of a shape's semantics (obj_side reports "outside" beyond it, objects.c:365-370), so a scene built
+ * with this call renders like the reference renders the same scene with the same envelopes set by set_envelope. */
+int acn_set_bounding_envelope( acn_scene* s, acn_obj o );
 int acn_set_texture_plain( acn_scene* s, acn_obj o, const double rgb[3] );
 int acn_set_texture_chess( acn_scene* s, acn_obj o, const double rgb1[3], const double rgb2[3], double scale );
 

@@ -189,3 +189,41 @@ def test_pass_controller_and_image_io(tmp_path):
     assert np.array_equal(img2.next_pass(prm), img.next_pass(prm))
     img.push(img.next_pass(prm), np.zeros((len(img.next_pass(prm)), 3), np.float32))
     assert img.next_pass(prm).shape[0] == 0                 # gradient_cycles + 1 passes in total (scene.c:1103)
+
+
+def test_analytic_bounding_envelopes_contain_the_monte_carlo_ones_extent():
+    """a conservative bound from the shape's parameters instead of the reference's Monte-Carlo estimate
+    (objects.c:312-363): exact for a ball, the largest half axis for an ellipsoid, the smaller child's bound for A&B, the
+    reference's own envelope_of_pair for A|B; unbounded shapes are refused."""
+    import ctypes as C
+    sc = acn.Scene()
+
+    def env_of(o):
+        sc.clear(); sc.push(o)
+        fs = sc.flatten().struct
+        nd = fs.nodes[fs.children[fs.nodes[fs.matter_root].child0]]
+        return np.array(list(nd.env_pos)), nd.env_radius, nd.has_envelope
+
+    ball = sc.create_sphere(0.7) + (1.0, 2.0, 3.0)
+    ball.clone().set_bounding_envelope()
+    c, r, has = env_of(ball.clone().set_bounding_envelope())
+    assert has and np.allclose(c, (1, 2, 3)) and 0.7 <= r < 0.7001
+    egg = sc.create_ellipsoid(0.5, 1.5, 1.0) + (0.0, 1.0, 0.0)
+    c, r, has = env_of(egg.clone().set_bounding_envelope())
+    assert has and 1.5 <= r < 1.5001
+    ring = sc.create_torus(2.0, 0.25)
+    c, r, has = env_of(ring.clone().set_bounding_envelope())
+    assert has and 2.25 <= r <= 2.25 * 1.01 + 1e-4       # create_torus sets (r1 + r2) * 1.01 itself (closures.c:568-591): kept
+    lens = sc.create_sphere(1.0) & (sc.create_sphere(1.0) + (0.5, 0.0, 0.0))
+    c, r, has = env_of(lens.clone().set_bounding_envelope())
+    cm, rm, _ = env_of(lens.clone().set_auto_envelope())
+    assert has and 1.0 <= r < 1.0001
+    assert r < rm                                                   # and tighter than the estimate (1.29 around a sampled centre)
+    pair = sc.create_sphere(1.0) | (sc.create_sphere(0.5) + (2.0, 0.0, 0.0))
+    c, r, has = env_of(pair.clone().set_bounding_envelope())
+    assert has and abs(r - 1.75) < 1e-3 and abs(c[0] - 0.75) < 1e-6     # envelope_of_pair, objects.c:113-136
+    with pytest.raises(acn.AcnError) as e:
+        sc.create_plane().set_bounding_envelope()
+    assert e.value.code == -5
+    with pytest.raises(acn.AcnError):
+        (~sc.create_sphere(1.0)).set_bounding_envelope()
