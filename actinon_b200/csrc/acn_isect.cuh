@@ -41,7 +41,9 @@ namespace acn {
 // that gets that far without a hit falls back to the reference march.
 //
 // Program words (op | arg << 4):  LEAF node | RUN count, then count MEMBER/MEMBER_NEG node words |
-// NEG | AND | OR | ENV node, then (words to skip | variables skipped << 16) | CLIP node.
+// NEG | AND | OR | ENV node, then (words to skip | variables skipped << 16) | CLIP node |
+// XFORM node ... XEND node: the words in between belong to the child of an obj_scale_s (objects.c:1418-1443) and are
+// classified against the ray carried into its frame; their crossings come back as ray parameters of the outer ray.
 // ---------------------------------------------------------------------------------------------
 #ifndef ACN_CSG_INLINE
 #define ACN_CSG_INLINE __forceinline__
@@ -210,6 +212,23 @@ template <typename R> __device__ __forceinline__ void member_interval( int s0, i
     else     { *lo = c >= 1 ? t0 : inf; *hi = c == 2 ? t1 : inf; }
 }
 
+// obj_scale_s (objects.c:1418-1437): the ray in the frame of the scaled child.  The direction is renormalised, so a
+// parameter s of the inner ray is the parameter s * fac of the outer one (fac = 1 / | M d |).
+template <typename R, bool SH> __device__ __forceinline__ Ray<R> scale_ray( const SceneView<R, SH>& sv, int n, const Ray<R>& ray, R* fac )
+{
+    const V3<R> pos = xyz( sv.geo[ n * GEO_STRIDE ] );
+    const M3<R> rax = node_rax( sv, n );
+    const V3<R> inv = v3<R>( sv.geo[ n * GEO_STRIDE ].w, sv.geo[ n * GEO_STRIDE + 1 ].w, sv.geo[ n * GEO_STRIDE + 2 ].w );
+    Ray<R> rl;
+    rl.p = mul( mlv( rax, ray.p - pos ), inv );
+    rl.d = mul( mlv( rax, ray.d ), inv );
+    const R len = r_sqrt( sqr( rl.d ) );
+    const R f = len > R( 0 ) ? R( 1 ) / len : R( 0 );
+    rl.d = rl.d * f;
+    *fac = f;
+    return rl;
+}
+
 // the crossing at tcur of the leaf with program-relative id `id` is the first boundary of the solid `root`: the hit
 // distance (shortened by eps, as every fp_ray_hit reports it) and, if asked for, the normal of the leaf carried up the tree
 template <bool DIST, typename R, bool SH> __device__ __forceinline__ R csg_report_hit( const SceneView<R, SH>& sv, int root, int prog_start, const Ray<R>& ray, R tcur, int id,
@@ -219,15 +238,35 @@ template <bool DIST, typename R, bool SH> __device__ __forceinline__ R csg_repor
     if( nor )
     {
         const int leaf = sv.prog[ prog_start + id ] >> 4;
-        V3<R> nn = leaf_normal<DIST>( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
-        // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations
+        V3<R> nn;
+        int sc = -1;                                // a scale node above the leaf (the builder sweeps at most one level of them)
+        if( DIST && leaf != root ) for( int m = sv.parent[ leaf ]; m >= 0; m = sv.parent[ m ] ) { if( node_kind( sv.link[ m ] ) == K_SCALE ) sc = m; if( m == root ) break; }
+        if( DIST && sc >= 0 )
+        {
+            R fac;
+            const Ray<R> rl = scale_ray( sv, sc, ray, &fac );
+            nn = leaf_normal<DIST>( sv, node_kind( sv.link[ leaf ] ), leaf, rl, fac > R( 0 ) ? tcur / fac : tcur );
+        }
+        else nn = leaf_normal<DIST>( sv, node_kind( sv.link[ leaf ] ), leaf, ray, tcur );
+        // up the tree: roughness at every level that has it (objects.c:266), sign flip at negations, the normal carried
+        // out of a scaled frame (objects.c:1431)
         for( int m = leaf; m != root && m >= 0; m = sv.parent[ m ] )
         {
             const I4 lk = sv.link[ m ];
             if( node_kind( lk ) == K_NEG ) nn = -nn;
+            if( DIST && node_kind( lk ) == K_SCALE )
+            {
+                const V3<R> inv = v3<R>( sv.geo[ m * GEO_STRIDE ].w, sv.geo[ m * GEO_STRIDE + 1 ].w, sv.geo[ m * GEO_STRIDE + 2 ].w );
+                nn = unit( tmlv( node_rax( sv, m ), mul( nn, inv ) ) );
+            }
             if( node_flags( lk ) & F_ROUGH ) roughen( sv, m, ray, a, &nn, ctx );
         }
         if( node_kind( sv.link[ root ] ) == K_NEG ) nn = -nn;
+        if( DIST && node_kind( sv.link[ root ] ) == K_SCALE )
+        {
+            const V3<R> inv = v3<R>( sv.geo[ root * GEO_STRIDE ].w, sv.geo[ root * GEO_STRIDE + 1 ].w, sv.geo[ root * GEO_STRIDE + 2 ].w );
+            nn = unit( tmlv( node_rax( sv, root ), mul( nn, inv ) ) );
+        }
         *nor = nn;
     }
     return a;
@@ -259,6 +298,7 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
         // CLIP variable's events, so the envelope is intersected once, at the ENV word.
         int skip_to = pr.x;                         // this lane idles while pc < skip_to
         R more_from = inf;                          // second crossing of the distance-field leaf just classified (CSG_MORE continues there)
+        Ray<R> rc = ray; R fac = R( 1 );            // the ray in the frame of the words being classified, and what its parameter is worth outside (XFORM)
         #pragma unroll 1
         for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
         {
@@ -269,8 +309,13 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
             if( op == CSG_LEAF )
             {
                 more_from = inf;
-                if( act ) { c = leaf_events<DIST>( sv, node_kind( sv.link[ n ] ), n, ray, &s0, &t0, &t1 ); id0 = id1 = pc - pr.x; if( DIST && c == 2 ) more_from = t1; }
+                if( act ) { c = leaf_events<DIST>( sv, node_kind( sv.link[ n ] ), n, DIST ? rc : ray, &s0, &t0, &t1 ); if( DIST ) { t0 *= fac; t1 *= fac; } id0 = id1 = pc - pr.x; if( DIST && c == 2 ) more_from = t1; }
                 nv++;
+            }
+            else if( DIST && ( op == CSG_XFORM || op == CSG_XEND ) )
+            {   // into / out of the frame of a scaled child (one level: the builder does not sweep nested scale nodes)
+                if( op == CSG_XFORM ) rc = scale_ray( sv, n, ray, &fac ); else { rc = ray; fac = R( 1 ); }
+                continue;
             }
             else if( DIST && op == CSG_MORE )
             {   // crossings 3 and 4 of the distance-field leaf in front (same variable); s0 collects toggles only
@@ -278,7 +323,7 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
                 if( act && more_from < t_far )
                 {
                     int sd;
-                    c = dist_events( sv, node_kind( sv.link[ n ] ), n, ray, more_from + sv.eps, &sd, &t0, &t1 );
+                    c = dist_events( sv, node_kind( sv.link[ n ] ), n, rc, ( more_from + sv.eps ) / fac, &sd, &t0, &t1 ); t0 *= fac; t1 *= fac;
                     id0 = id1 = pc - pr.x;
                 }
                 more_from = inf;
@@ -294,7 +339,8 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
                         const int w = sv.prog[ pc + m ];
                         const int node = w >> 4;
                         R a0 = R( 0 ), a1 = R( 0 ); int ms0;
-                        const int mc = leaf_events<false>( sv, node_kind( sv.link[ node ] ), node, ray, &ms0, &a0, &a1 );
+                        const int mc = leaf_events<false>( sv, node_kind( sv.link[ node ] ), node, DIST ? rc : ray, &ms0, &a0, &a1 );
+                        if( DIST ) { a0 *= fac; a1 *= fac; }
                         if( ( w & 15 ) == CSG_MEMBER_NEG ) ms0 ^= 1;
                         R mlo, mhi;
                         member_interval( ms0, mc, a0, a1, &mlo, &mhi );
@@ -315,7 +361,8 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
                 if( act )
                 {
                     const R4<R> e = sv.env[ n ];
-                    c = sphere_events( xyz( e ), e.w, ray, &s0, &t0, &t1 );
+                    c = sphere_events( xyz( e ), e.w, DIST ? rc : ray, &s0, &t0, &t1 );
+                    if( DIST ) { t0 *= fac; t1 *= fac; }
                     if( c == 0 ) { s0 = 0; skip_to = sub_end; }         // objects.c:264: the ray misses the envelope
                 }
                 if( !__any_sync( __activemask(), pc + 1 >= skip_to ) ) { nv += w2 >> 16; pc = sub_end - 1; }
@@ -429,8 +476,8 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R elem_hit
     if( kind == K_PLANE || kind == K_SPHERE || kind == K_SQUAROID ) a = prim_hit( sv, kind, c, ray, nor );
     else if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval<MARCH>( sv, c, ray, nor, ctx, cm, t_far );
     else if( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) a = dist_hit( sv, kind, c, ray, nor );
-    else if( MARCH ) a = march_hit( sv, c, ray, nor, ctx );
-    else a = Num<R>::inf();                 // unreachable: such scenes run the MARCH instantiation
+    else if( MARCH && sizeof( R ) == 8 ) a = march_hit( sv, c, ray, nor, ctx );     // the reference's recursive march: FP64 validation mode only
+    else a = Num<R>::inf();                 // unreachable: the FP32 tracer refuses scenes the sweep does not cover (Tracer::init)
     if( nor && ( node_flags( lk ) & F_ROUGH ) && a < Num<R>::inf() ) roughen( sv, c, ray, a, nor, ctx );
     return a;
 }
@@ -576,6 +623,7 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
         int end = act ? rec + ( pass == 0 ? sv.wide_light_n : sv.wide_matter_n ) : rec;
         int cur = 0, sp = 0;
         unsigned int todo = 0;                                  // children of record `cur` that passed their envelope and are not handled yet
+        R hor_visit = inf;                                      // the horizon those envelopes were tested against
         R min_a = inf;
         Trans<R> tl; tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
         R el_a = inf; V3<R> el_n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); int el_obj = -1;
@@ -591,6 +639,7 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
                     if( rec < end )
                     {   // visit a record: eight envelope tests, independent of each other
                         cur = rec++;
+                        hor_visit = hor;
                         const WRec<R>* w = sv.wide + cur;
                         unsigned int m = 0;
                         #pragma unroll
@@ -617,10 +666,21 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
                     todo &= todo - 1u;
                     const int i0 = sv.wide[ cur ].info[ 2 * j ], i1 = sv.wide[ cur ].info[ 2 * j + 1 ];
                     const int kind = ( i1 & 15 ) - 1;
+                    // the horizon may have come closer since the record was visited (an earlier sibling was hit): a whole
+                    // subtree is worth a second look at its envelope
+                    bool descend = kind == K_COMPOUND;
+                    if( descend && hor < hor_visit )
+                    {
+                        const R4<R> e = sv.wide[ cur ].env[ j ];
+                        if( !( e.w < R( 0 ) ) && !envelope_hits_before( e, ray, hor ) ) descend = false;
+                    }
                     if( kind == K_COMPOUND )
                     {
+                        if( descend )
+                        {
                         cm.sb[ sp * cm.stride ] = ( int )( ( ( unsigned int )cur << 8 ) | todo ); cm.se[ sp * cm.stride ] = rec; cm.sx[ sp * cm.stride ] = end; sp++;
                         rec = i0; end = i0 + ( int )( ( unsigned int )i1 >> 12 ); todo = 0;
+                        }
                     }
                     else
                     {

@@ -66,11 +66,11 @@ struct SpecGen
     bool program_ok( int root ) const
     {
         const I4 pr = ( *prog_ref )[ root ];
-        if( pr.y <= 0 ) return false;
+        if( pr.y <= 0 || pr.w > 32 ) return false;      // the done-mask of the register sweep holds 2 x 32 crossings
         for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
         {
             const int ins = ( *prog )[ pc ], op = ins & 15, n = ins >> 4;
-            if( op == CSG_MORE ) return false;
+            if( op == CSG_MORE || op == CSG_XFORM || op == CSG_XEND ) return false;
             if( op == CSG_LEAF && !simple_leaf( kind( n ) ) ) return false;
             if( op == CSG_RUN ) { for( int m = 1; m <= n; m++ ) if( !simple_leaf( kind( ( *prog )[ pc + m ] >> 4 ) ) ) return false; pc += n; }
             if( op == CSG_ENV ) pc++;

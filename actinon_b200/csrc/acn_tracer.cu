@@ -178,6 +178,26 @@ int acn_spec_probe( const acn_flat_scene* scene, const acn_options* opt, int com
     const bool f64 = o.precision == ACN_PRECISION_F64;
     CsgBuilder cb;
     cb.build( scene, o.csg_mode == ACN_CSG_INTERVALS || ( o.csg_mode == ACN_CSG_AUTO && !f64 ) );
+    if( getenv( "ACN_VERBOSE" ) )
+    {   // which composite objects the event sweep covers
+        int swept = 0, marched = 0, maxv = 0, maxw = 0;
+        std::function<void( int )> cnt = [ & ]( int c )
+        {
+            const acn_flat_node& cn = scene->nodes[ c ];
+            for( int i = 0; i < cn.child1; i++ )
+            {
+                const int e = scene->children[ cn.child0 + i ];
+                const acn_flat_node& nd = scene->nodes[ e ];
+                if( nd.kind == ACN_KIND_COMPOUND ) { cnt( e ); continue; }
+                if( nd.kind < ACN_KIND_PAIR_INSIDE ) continue;
+                if( cb.prog_ref[ e ].y > 0 ) { swept++; if( cb.prog_ref[ e ].w > maxv ) maxv = cb.prog_ref[ e ].w; if( cb.prog_ref[ e ].y > maxw ) maxw = cb.prog_ref[ e ].y; }
+                else { marched++; fprintf( stderr, "acn: object %d (kind %d) runs the reference march\n", e, nd.kind ); }
+            }
+        };
+        cnt( scene->light_root ); cnt( scene->matter_root );
+        fprintf( stderr, "acn: %d composite objects swept (largest: %d variables, %d words), %d marched; dist leaves %d, coincident %d\n",
+                 swept, maxv, maxw, marched, ( int )cb.has_dist_leaf, ( int )cb.has_coincident );
+    }
     const SpecPlan pl = f64 ? plan_spec<double>( scene, cb ) : plan_spec<float>( scene, cb );
     if( len ) *len = pl.src.size();
     if( seconds ) *seconds = 0;

@@ -210,14 +210,16 @@ struct CsgBuilder
     static bool is_leaf( int k ) { return k == ACN_KIND_PLANE || k == ACN_KIND_SPHERE || k == ACN_KIND_SQUAROID || is_dist( k ); }
     static bool is_pair( int k ) { return k == ACN_KIND_PAIR_INSIDE || k == ACN_KIND_PAIR_OUTSIDE; }
 
-    bool eligible( int n, int guard ) const
+    bool eligible( int n, int guard, bool in_scale = false ) const
     {
         if( guard > 64 ) return false;
         const acn_flat_node& nd = fs->nodes[ n ];
         if( is_dist( nd.kind ) && getenv( "ACN_NO_SWEEP_DIST" ) ) return false;      // diagnostics
         if( is_leaf( nd.kind ) ) return true;
-        if( is_pair( nd.kind ) ) return eligible( nd.child0, guard + 1 ) && eligible( nd.child1, guard + 1 );
-        if( nd.kind == ACN_KIND_NEG ) return eligible( nd.child0, guard + 1 );
+        if( is_pair( nd.kind ) ) return eligible( nd.child0, guard + 1, in_scale ) && eligible( nd.child1, guard + 1, in_scale );
+        if( nd.kind == ACN_KIND_NEG ) return eligible( nd.child0, guard + 1, in_scale );
+        // obj_scale_s: its child is classified against the ray carried into the scaled frame (XFORM .. XEND); one level
+        if( nd.kind == ACN_KIND_SCALE ) return !in_scale && !getenv( "ACN_NO_SWEEP_SCALE" ) && eligible( nd.child0, guard + 1, true );
         return false;
     }
 
@@ -255,6 +257,7 @@ struct CsgBuilder
 
     int n_vars = 0;
     bool has_dist_leaf = false;       // some program has a distance-field leaf: the kernels with that support (MARCH instantiation) are needed
+    bool has_scale = false;           // some program carries the ray into a scaled frame: same kernels
 
     void emit( int n, bool root )
     {
@@ -270,6 +273,11 @@ struct CsgBuilder
             if( is_dist( nd.kind ) ) has_dist_leaf = true;
         }
         else if( nd.kind == ACN_KIND_NEG ) { emit( nd.child0, false ); prog.push_back( CSG_NEG | ( n << 4 ) ); }
+        else if( nd.kind == ACN_KIND_SCALE )
+        {
+            prog.push_back( CSG_XFORM | ( n << 4 ) ); emit( nd.child0, false ); prog.push_back( CSG_XEND | ( n << 4 ) );
+            has_scale = true;
+        }
         else
         {
             std::vector<int> ops; operands( n, nd.kind, true, ops );
@@ -358,7 +366,7 @@ struct CsgBuilder
         if( guard > 64 ) return 64;
         const acn_flat_node& nd = fs->nodes[ n ];
         if( is_pair( nd.kind ) ) { int a = depth( nd.child0, guard + 1 ), b = depth( nd.child1, guard + 1 ); return 1 + ( a > b ? a : b ); }
-        if( nd.kind == ACN_KIND_NEG ) return 1 + depth( nd.child0, guard + 1 );
+        if( nd.kind == ACN_KIND_NEG || nd.kind == ACN_KIND_SCALE ) return 1 + depth( nd.child0, guard + 1 );
         return 1;
     }
 
@@ -383,7 +391,7 @@ struct CsgBuilder
             // the bit stack of the interpreter holds 32 levels; a left-deep chain needs 2 however long it is
             const char* skip = getenv( "ACN_NO_SWEEP_NODE" );       // diagnostics: keep one object on the reference march
             if( skip && atoi( skip ) == n ) continue;
-            if( enable && ( is_pair( nd.kind ) || nd.kind == ACN_KIND_NEG ) && eligible( n, 0 ) && depth( n, 0 ) < 30 && prog_ref[ n ].y == 0 )
+            if( enable && ( is_pair( nd.kind ) || nd.kind == ACN_KIND_NEG || nd.kind == ACN_KIND_SCALE ) && eligible( n, 0 ) && depth( n, 0 ) < 30 && prog_ref[ n ].y == 0 )
             {
                 const size_t mark = prog.size();
                 n_vars = 0;
@@ -403,7 +411,11 @@ struct CsgBuilder
                     prog_ref[ n ] = r;
                     if( coincident_leaves( n ) ) has_coincident = true;
                 }
-                else prog.resize( mark );
+                else
+                {
+                    if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: object %d: program of %d words, %d variables exceeds the sweep's limits\n", n, ( int )len, n_vars );
+                    prog.resize( mark );
+                }
             }
         }
     }
@@ -441,7 +453,27 @@ static bool needs_march( const acn_flat_scene* fs, const CsgBuilder& cb )
         }
     };
     walk( fs->light_root ); walk( fs->matter_root );
-    return march || cb.has_dist_leaf || cb.has_coincident;
+    return march || cb.has_dist_leaf || cb.has_coincident || cb.has_scale;
+}
+
+// composite objects the event sweep does not cover (programs of more than CSG_MAX_VARS variables or 254 words, nested
+// scale nodes): the FP64 validation mode runs the reference's recursive march on them, the FP32 tracer refuses the scene
+static int first_unswept( const acn_flat_scene* fs, const CsgBuilder& cb )
+{
+    int bad = -1;
+    std::function<void( int )> walk = [ & ]( int c )
+    {
+        const acn_flat_node& cn = fs->nodes[ c ];
+        for( int i = 0; i < cn.child1 && bad < 0; i++ )
+        {
+            const int e = fs->children[ cn.child0 + i ];
+            const acn_flat_node& nd = fs->nodes[ e ];
+            if( nd.kind == ACN_KIND_COMPOUND ) { walk( e ); continue; }
+            if( nd.kind >= ACN_KIND_PAIR_INSIDE && cb.prog_ref[ e ].y == 0 ) bad = e;
+        }
+    };
+    walk( fs->light_root ); if( bad < 0 ) walk( fs->matter_root );
+    return bad;
 }
 
 // bytes of the node table as staged into shared memory (layout in Tracer::init)
@@ -576,7 +608,8 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         };
         build( fs->light_root, &wide_root[ 0 ], &wide_root[ 1 ] );
         build( fs->matter_root, &wide_root[ 2 ], &wide_root[ 3 ] );
-        if( wide.size() < ( size_t )( 1 << 23 ) && !getenv( "ACN_NO_WIDE" ) )
+        const char* we = getenv( "ACN_WIDE" );
+        if( wide.size() < ( size_t )( 1 << 23 ) && we && we[ 0 ] == '1' )     // experimental: measured slower than the list walk so far (profiles/r02_wide_walk.txt)
         {
             if( wide.empty() ) { WRec<R> e; memset( &e, 0, sizeof( e ) ); wide.push_back( e ); wgeo.resize( 8 ); }
             if( ( rc = dev_alloc( &d_wide, wide.size() ) ) ) return rc;
@@ -599,6 +632,18 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         ACN_CUDA( cudaMemcpy( d_prog_ref, cb.prog_ref.data(), cb.prog_ref.size() * sizeof( I4 ), cudaMemcpyHostToDevice ) );
         ACN_CUDA( cudaMemcpy( d_parent, cb.parent.data(), cb.parent.size() * sizeof( int ), cudaMemcpyHostToDevice ) );
         march = needs_march( fs, cb );
+        if( sizeof( R ) == 4 )
+        {   // the FP32 product path has no recursive march: every composite object is swept, or the scene is refused
+            const int bad = first_unswept( fs, cb );
+            if( bad >= 0 )
+            {
+                set_error( fast ? "object %d (kind %d) exceeds what the CSG event sweep covers (%d variables, 254 program words, one level of scale nodes); "
+                                  "the reference's recursive march runs in the FP64 validation mode only"
+                                : "csg_mode MARCH (object %d, kind %d): the reference's recursive march runs in the FP64 validation mode only (limit %d)",
+                           bad, fs->nodes[ bad ].kind, ( int )CSG_MAX_VARS );
+                return ACN_ERR_UNSUPPORTED;
+            }
+        }
         if( getenv( "ACN_VERBOSE" ) )
         {
             int swept = 0, marched = 0;
@@ -616,8 +661,8 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
                 }
             };
             cnt( fs->light_root ); cnt( fs->matter_root );
-            fprintf( stderr, "acn: %d composite objects swept, %d marched; program words %d; dist leaves %d, coincident surfaces %d -> %s kernels\n",
-                     swept, marched, n_prog, ( int )cb.has_dist_leaf, ( int )cb.has_coincident, march ? "full-featured (MARCH)" : "lean" );
+            fprintf( stderr, "acn: %d composite objects swept, %d marched; program words %d; dist leaves %d, coincident surfaces %d, scale nodes %d -> %s kernels\n",
+                     swept, marched, n_prog, ( int )cb.has_dist_leaf, ( int )cb.has_coincident, ( int )cb.has_scale, march ? "full-featured" : "lean" );
         }
     }
 
