@@ -24,14 +24,6 @@ struct alignas( 16 ) I4 { int x, y, z, w; };
 // one child of a compound, packed for the traversal: its envelope and its link word with the node index in .w
 // (the material, which the traversal does not need, stays in link[n].w)
 template <typename R> struct CRec { R4<R> env; I4 link; };
-// Eight children of a compound in one record (scenes whose tables stay in global memory: deep trees of compounds).  A ray
-// tests the eight envelopes in ONE visit — eight independent sphere tests from one contiguous record instead of eight
-// trips round a loop with a dependent record load each — and then handles the survivors one by one.
-//   env[ j ].w    radius; -1: the child has no envelope (always passes); -2: empty slot
-//   info[ 2j ]    leaf: node index; compound: its first record
-//   info[ 2j+1 ]  ( kind + 1 ) | flags << 4 | ( number of records of a compound child ) << 12
-// wide_geo[ 8 * record + j ] holds ( centre, radius ) of a sphere child, so its test needs no second dependent load.
-template <typename R> struct WRec { R4<R> env[ 8 ]; int info[ 16 ]; };
 
 enum
 {
@@ -77,9 +69,6 @@ template <typename R, bool SH = false> struct SceneView
     Tab<int, SH>     prog;      // postfix CSG programs (interval evaluator), see acn_isect.cuh: csg_eval
     Tab<I4, SH>      prog_ref;  // per node: program start, length (0: none -> reference march), truth table offset (-1: none), variables
     Tab<int, SH>     parent;    // per node: CSG parent (-1 at the top of an object)
-    const WRec<R>*   wide;      // eight-children records of all compounds (global memory; null: none)
-    const R4<R>*     wide_geo;
-    int wide_light, wide_light_n, wide_matter, wide_matter_n;   // records of the two root compounds
     R   eps;            // shell thickness (f3_eps, vectors.h:33)
     int light_root;
     int matter_root;

@@ -63,13 +63,13 @@ template <typename T> struct SPtr
 template <typename R> struct CsgMem
 {
     SPtr<R> t; SPtr<unsigned short> iv;         // CSG_E events: crossing, leaf id | variable << 8
-    SPtr<int> sb, se, sx;                       // per nesting level of compounds: where the walk of the parent list resumes, its end (+ the wide walk's third word)
+    SPtr<int> sb, se;                           // per nesting level of compounds: where the walk of the parent list resumes, its end
     int stride;
 };
 
 template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthreads, int levels )
 {
-    return ( size_t )( sizeof( R ) + 2 ) * CSG_E * nthreads + ( size_t )12 * levels * nthreads;
+    return ( size_t )( sizeof( R ) + 2 ) * CSG_E * nthreads + ( size_t )8 * levels * nthreads;
 }
 
 template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned char* base, int nthreads, int tid, int levels )
@@ -80,7 +80,6 @@ template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned cha
     m.iv.a = b + ( unsigned int )( sizeof( R ) * CSG_E * nthreads + tid * 2 );
     const unsigned int stk = b + ( unsigned int )( ( sizeof( R ) + 2 ) * CSG_E * nthreads );
     m.sb.a = stk + ( unsigned int )( tid * 4 ); m.se.a = stk + ( unsigned int )( ( levels * nthreads + tid ) * 4 );
-    m.sx.a = stk + ( unsigned int )( ( 2 * levels * nthreads + tid ) * 4 );
     m.stride = nthreads;
     return m;
 }
@@ -595,122 +594,6 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
 }
 
 // ---------------------------------------------------------------------------------------------
-// scene_query over eight-children records (WRec, acn_geom.h) — the walk of the kernels whose tables stay in global memory
-// (many_spheres: an 8-ary tree of 4 681 compounds over 32 768 spheres; the lamp scenes; the FP64 validation mode).
-// Semantics as scene_query: children are handled in list order (depth first), so ties fall as in compound.c:215-299; the
-// envelopes of a record are tested when it is visited, against the horizon of that moment (a later, tighter horizon
-// would only cull more: nothing that can matter is lost), a leaf's own test sees the current horizon.
-// State per lane: the record being handled + the mask of its children still to do; per nesting level on the stack
-// ( record << 8 | mask, next record, end ).  Lockstep over the lanes that entered together, as in scene_query.
-// ---------------------------------------------------------------------------------------------
-template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_query_wide( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,
-                                                                                 Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
-{
-    const R inf = Num<R>::inf();
-    const bool want_trans = ( flags & Q_TRANS ) != 0;
-    const R slack = R( 2 ) * sv.eps;
-    const unsigned int mask = __activemask();
-    R best = inf;
-    bool found = false;
-    #pragma unroll 1
-    for( int pass = 0; pass < 2; pass++ )
-    {
-        bool act = !found && ( flags & ( pass == 0 ? Q_LIGHT : Q_MATTER ) ) != 0;
-        const int root = pass == 0 ? sv.light_root : sv.matter_root;
-        const R far0 = r_min( t_far, best );
-        if( act && ( node_flags( sv.link[ root ] ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + slack ) ) act = false;
-        int rec = pass == 0 ? sv.wide_light : sv.wide_matter;
-        int end = act ? rec + ( pass == 0 ? sv.wide_light_n : sv.wide_matter_n ) : rec;
-        int cur = 0, sp = 0;
-        unsigned int todo = 0;                                  // children of record `cur` that passed their envelope and are not handled yet
-        R hor_visit = inf;                                      // the horizon those envelopes were tested against
-        R min_a = inf;
-        Trans<R> tl; tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
-        R el_a = inf; V3<R> el_n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); int el_obj = -1;
-        for( ;; )
-        {
-            const bool more = !found && ( todo != 0 || rec < end || sp > 0 );
-            if( !__any_sync( mask, more ) ) break;
-            if( more )
-            {
-                const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;
-                if( todo == 0 )
-                {
-                    if( rec < end )
-                    {   // visit a record: eight envelope tests, independent of each other
-                        cur = rec++;
-                        hor_visit = hor;
-                        const WRec<R>* w = sv.wide + cur;
-                        unsigned int m = 0;
-                        #pragma unroll
-                        for( int j = 0; j < 8; j++ )
-                        {
-                            const R4<R> e = w->env[ j ];
-                            const bool in = e.w < R( 0 ) ? e.w > R( -1.5 ) : envelope_hits_before( e, ray, hor );
-                            m |= ( in ? 1u : 0u ) << j;
-                        }
-                        todo = m;
-                    }
-                    else
-                    {   // the records of a nested compound are through: back to its parent's record
-                        sp--;
-                        const int pk = cm.sb[ sp * cm.stride ];
-                        cur = ( int )( ( unsigned int )pk >> 8 ); todo = ( unsigned int )pk & 255u;
-                        rec = cm.se[ sp * cm.stride ]; end = cm.sx[ sp * cm.stride ];
-                        if( sp == 0 && want_trans ) { trans_commit( sv, ray, el_a, el_n, el_obj, &min_a, &tl ); el_a = inf; el_obj = -1; }
-                    }
-                }
-                else
-                {
-                    const int j = __ffs( ( int )todo ) - 1;
-                    todo &= todo - 1u;
-                    const int i0 = sv.wide[ cur ].info[ 2 * j ], i1 = sv.wide[ cur ].info[ 2 * j + 1 ];
-                    const int kind = ( i1 & 15 ) - 1;
-                    // the horizon may have come closer since the record was visited (an earlier sibling was hit): a whole
-                    // subtree is worth a second look at its envelope
-                    bool descend = kind == K_COMPOUND;
-                    if( descend && hor < hor_visit )
-                    {
-                        const R4<R> e = sv.wide[ cur ].env[ j ];
-                        if( !( e.w < R( 0 ) ) && !envelope_hits_before( e, ray, hor ) ) descend = false;
-                    }
-                    if( kind == K_COMPOUND )
-                    {
-                        if( descend )
-                        {
-                        cm.sb[ sp * cm.stride ] = ( int )( ( ( unsigned int )cur << 8 ) | todo ); cm.se[ sp * cm.stride ] = rec; cm.sx[ sp * cm.stride ] = end; sp++;
-                        rec = i0; end = i0 + ( int )( ( unsigned int )i1 >> 12 ); todo = 0;
-                        }
-                    }
-                    else
-                    {
-                        V3<R> n = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
-                        R a;
-                        if( kind == K_SPHERE && !( ( i1 >> 4 ) & F_ROUGH ) )
-                        {
-                            const R4<R> g = sv.wide_geo[ cur * 8 + j ];
-                            a = sphere_hit<R>( xyz( g ), g.w, ray, sv.eps, want_trans ? &n : ( V3<R>* )nullptr );
-                        }
-                        else a = elem_hit<R, MARCH>( sv, sv.link[ i0 ], i0, ray, want_trans ? &n : ( V3<R>* )nullptr, ctx, cm, hor );
-                        if( !want_trans )
-                        {
-                            if( a < min_a ) { min_a = a; if( a <= t_far ) found = true; }
-                        }
-                        else if( sp > 0 )
-                        {
-                            if( a < el_a ) { el_a = a; el_n = n; el_obj = i0; }
-                        }
-                        else trans_commit( sv, ray, a, n, i0, &min_a, &tl );
-                    }
-                }
-            }
-        }
-        if( min_a < best ) { best = min_a; if( want_trans ) *trans = tl; }
-    }
-    return best;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Scene-specialised build (NVRTC, acn_spec.h): the generated header restates the structure of ONE scene — its top-level
 // element lists and its CSG programs — as straight-line code over the same leaf functions, and replaces scene_query.
 // ---------------------------------------------------------------------------------------------
@@ -744,7 +627,6 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R query( c
 #if defined(ACN_SPEC_SCENE)
     return spec_scene_query<R, MARCH, SH>( sv, ray, flags, t_far, trans, ctx, cm );
 #else
-    if constexpr( !SH ) { if( sv.wide ) return scene_query_wide<R, MARCH, SH>( sv, ray, flags, t_far, trans, ctx, cm ); }
     return scene_query<R, MARCH, SH>( sv, ray, flags, t_far, trans, ctx, cm );
 #endif
 }

@@ -369,7 +369,6 @@ template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> stage
         sv.parent.a   = base + prm.off_par;
         sv.prog.a     = base + prm.off_prog;
         sv.children.a = 0;                       // march / host only
-        sv.wide = nullptr; sv.wide_geo = nullptr; sv.wide_light = sv.wide_light_n = sv.wide_matter = sv.wide_matter_n = 0;   // staged tables are walked as lists
         sv.eps = prm.sv.eps; sv.light_root = prm.sv.light_root; sv.matter_root = prm.sv.matter_root; sv.seed_mode = prm.sv.seed_mode;
         return sv;
     }

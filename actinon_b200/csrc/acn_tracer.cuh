@@ -103,7 +103,6 @@ template <typename R> struct Tracer : TracerBase
     // device copies of the scene tables
     R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr; CRec<R>* d_crec = nullptr;
     int* d_prog = nullptr; I4* d_prog_ref = nullptr; int* d_parent = nullptr; int n_prog = 0;
-    WRec<R>* d_wide = nullptr; R4<R>* d_wide_geo = nullptr;
     DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
     // queues
@@ -136,7 +135,7 @@ template <typename R> struct Tracer : TracerBase
     {
         cudaSetDevice( device );
         cudaFree( d_env ); cudaFree( d_link ); cudaFree( d_geo ); cudaFree( d_children ); cudaFree( d_crec );
-        cudaFree( d_prog ); cudaFree( d_prog_ref ); cudaFree( d_parent ); cudaFree( d_wide ); cudaFree( d_wide_geo );
+        cudaFree( d_prog ); cudaFree( d_prog_ref ); cudaFree( d_parent );
         cudaFree( d_mats ); cudaFree( d_lights ); cudaFree( d_skipA ); cudaFree( d_skipC );
         free_rays( ray_stack );
         free_tasks( task_stack ); free_tasks( task_new ); free_hits( hit_q );
@@ -572,53 +571,6 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         ACN_CUDA( cudaMemcpy( d_crec, crec.data(), crec.size() * sizeof( CRec<R> ), cudaMemcpyHostToDevice ) );
     }
 
-    // ---- eight-children records of the compounds (WRec, acn_geom.h): the walk of the kernels that read the tables from
-    // global memory (scenes too large for shared memory, FP64 validation)
-    int wide_root[ 4 ] = { 0, 0, 0, 0 };
-    {
-        std::vector<WRec<R>> wide;
-        std::vector<R4<R>> wgeo;
-        std::function<void( int, int*, int* )> build = [ & ]( int c, int* first_out, int* n_out )
-        {
-            const acn_flat_node& cn = fs->nodes[ c ];
-            const int m = cn.child1, nrec = ( m + 7 ) / 8;
-            const size_t first = wide.size();
-            WRec<R> empty;
-            for( int j = 0; j < 8; j++ ) { empty.env[ j ].x = empty.env[ j ].y = empty.env[ j ].z = ( R )0; empty.env[ j ].w = ( R )-2; empty.info[ 2 * j ] = empty.info[ 2 * j + 1 ] = 0; }
-            wide.resize( first + nrec, empty );
-            R4<R> zero; zero.x = zero.y = zero.z = zero.w = ( R )0;
-            wgeo.resize( ( first + nrec ) * 8, zero );
-            for( int i = 0; i < m; i++ )
-            {
-                const int e = fs->children[ cn.child0 + i ];
-                const acn_flat_node& nd = fs->nodes[ e ];
-                int i0 = e, i1 = ( nd.kind + 1 ) | ( ( link[ e ].x >> 8 ) << 4 );
-                if( nd.kind == ACN_KIND_COMPOUND ) { int cf = 0, cnr = 0; build( e, &cf, &cnr ); i0 = cf; i1 |= cnr << 12; }     // may reallocate `wide`
-                WRec<R>& r = wide[ first + i / 8 ];
-                const int j = i % 8;
-                r.env[ j ] = env[ e ];                      // .w = -1 without envelope
-                r.info[ 2 * j ] = i0; r.info[ 2 * j + 1 ] = i1;
-                if( nd.kind == ACN_KIND_SPHERE )
-                {
-                    R4<R>& g = wgeo[ ( first + i / 8 ) * 8 + j ];
-                    g.x = ( R )nd.pos[ 0 ]; g.y = ( R )nd.pos[ 1 ]; g.z = ( R )nd.pos[ 2 ]; g.w = ( R )nd.tail[ 0 ];
-                }
-            }
-            *first_out = ( int )first; *n_out = nrec;
-        };
-        build( fs->light_root, &wide_root[ 0 ], &wide_root[ 1 ] );
-        build( fs->matter_root, &wide_root[ 2 ], &wide_root[ 3 ] );
-        const char* we = getenv( "ACN_WIDE" );
-        if( wide.size() < ( size_t )( 1 << 23 ) && we && we[ 0 ] == '1' )     // experimental: measured slower than the list walk so far (profiles/r02_wide_walk.txt)
-        {
-            if( wide.empty() ) { WRec<R> e; memset( &e, 0, sizeof( e ) ); wide.push_back( e ); wgeo.resize( 8 ); }
-            if( ( rc = dev_alloc( &d_wide, wide.size() ) ) ) return rc;
-            if( ( rc = dev_alloc( &d_wide_geo, wgeo.size() ) ) ) return rc;
-            ACN_CUDA( cudaMemcpy( d_wide, wide.data(), wide.size() * sizeof( WRec<R> ), cudaMemcpyHostToDevice ) );
-            ACN_CUDA( cudaMemcpy( d_wide_geo, wgeo.data(), wgeo.size() * sizeof( R4<R> ), cudaMemcpyHostToDevice ) );
-        }
-    }
-
     // ---- CSG interval programs
     CsgBuilder cb;
     {
@@ -701,7 +653,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             }
         }
         SceneView<double> hv; hv.env = henv.data(); hv.geo = hgeo.data(); hv.link = link.data(); hv.children = fs->children;
-        hv.prog = nullptr; hv.prog_ref = nullptr; hv.parent = nullptr; hv.wide = nullptr; hv.wide_geo = nullptr;
+        hv.prog = nullptr; hv.prog_ref = nullptr; hv.parent = nullptr;
         hv.eps = eps; hv.light_root = fs->light_root; hv.matter_root = fs->matter_root; hv.seed_mode = 0;
         for( int i = 0; i < lroot.child1; i++ )
         {
@@ -746,8 +698,6 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     // ---- params
     prm.sv.env = d_env; prm.sv.link = d_link; prm.sv.geo = d_geo; prm.sv.children = d_children; prm.sv.crec = d_crec;
     prm.sv.prog = d_prog; prm.sv.prog_ref = d_prog_ref; prm.sv.parent = d_parent; prm.n_prog = n_prog;
-    prm.sv.wide = d_wide; prm.sv.wide_geo = d_wide_geo;
-    prm.sv.wide_light = wide_root[ 0 ]; prm.sv.wide_light_n = wide_root[ 1 ]; prm.sv.wide_matter = wide_root[ 2 ]; prm.sv.wide_matter_n = wide_root[ 3 ];
     prm.sv.eps = ( R )eps; prm.sv.light_root = fs->light_root; prm.sv.matter_root = fs->matter_root;
     prm.sv.seed_mode = opt->seed_mode;
     prm.mats = d_mats; prm.lights = d_lights; prm.n_lights = lroot.child1; prm.n_materials = fs->n_materials;

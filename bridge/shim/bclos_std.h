@@ -1,0 +1,1 @@
+#include "bcore_std.h"

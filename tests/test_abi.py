@@ -79,3 +79,12 @@ def test_product_does_not_reference_the_oracle():
     assert not bad, bad
     sh = open(os.path.join(ROOT, "build.sh")).read()
     assert "oracle" not in sh
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree absent (GPU box)")
+def test_reference_side_bridge_parses_against_the_reference_headers():
+    """bridge/acn_bridge.c (the flattener + the replaced call site a maintainer adds) must parse against the
+    reference's own objects.h / compound.h / distance.h / scene.h where they lie, with bridge/shim standing in for beth."""
+    import subprocess
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "bridge"), "check"], capture_output=True, text=True)
+    assert r.returncode == 0 and "syntax OK" in r.stdout, r.stdout + r.stderr
