@@ -669,11 +669,14 @@ class DeviceImage:
         _check(self._l.acn_dimage_read_pass_xy(self._p, xy.ctypes.data))
         return xy
 
-    def copy_delta(self, d_tensor):
-        _check(self._l.acn_dimage_copy_delta(self._p, d_tensor.data_ptr(), self._l.acn_dimage_stream(self._p)))
+    def copy_delta(self, d_tensor, stream=None):
+        """The pass delta -> a caller-owned int64 CUDA tensor (stream: a torch stream; default the image's own stream)."""
+        s = stream.cuda_stream if stream is not None else self._l.acn_dimage_stream(self._p)
+        _check(self._l.acn_dimage_copy_delta(self._p, d_tensor.data_ptr(), s))
 
-    def set_delta(self, d_tensor):
-        _check(self._l.acn_dimage_set_delta(self._p, d_tensor.data_ptr(), self._l.acn_dimage_stream(self._p)))
+    def set_delta(self, d_tensor, stream=None):
+        s = stream.cuda_stream if stream is not None else self._l.acn_dimage_stream(self._p)
+        _check(self._l.acn_dimage_set_delta(self._p, d_tensor.data_ptr(), s))
 
     def end_pass(self):
         _check(self._l.acn_dimage_end_pass(self._p, self._l.acn_dimage_stream(self._p)))
@@ -739,9 +742,11 @@ class Group:
         return image
 
 
-def render_image_device(flat: "FlatScene", tracer: "Tracer", passes: Optional[int] = None, dist=None):
+def render_image_device(flat: "FlatScene", tracer: "Tracer", passes: Optional[int] = None, dist=None, log=None):
     """scene_s_create_image_file with the image on the device; `dist` = torch.distributed (initialised, NCCL) shards the pixel
-    tiles over the ranks and all-reduces the per-pass deltas.  Returns (Image, samples, passes, rays of this rank)."""
+    tiles over the ranks and all-reduces the per-pass deltas.  Returns (Image, samples, passes, rays of this rank).
+    log: optional callable(pass index, n_total, n_local, Stats, wall seconds of the pass)."""
+    import time
     prm = flat.params
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
@@ -754,6 +759,7 @@ def render_image_device(flat: "FlatScene", tracer: "Tracer", passes: Optional[in
         buf = torch.zeros(dimg.words, dtype=torch.int64, device=dev)
     n_samples = n_pass = rays = 0
     while passes is None or n_pass < passes:
+        t0 = time.perf_counter()
         nl, nt = dimg.render_pass(tracer, prm, n_samples)
         if nt == 0:
             break
@@ -766,6 +772,8 @@ def render_image_device(flat: "FlatScene", tracer: "Tracer", passes: Optional[in
             torch.cuda.synchronize()
             dimg.set_delta(buf)
             dimg.end_pass()
+        if log is not None:
+            log(n_pass, nt, nl, tracer.last_stats, time.perf_counter() - t0)
         n_samples += nt
         n_pass += 1
     img = dimg.download()

@@ -214,7 +214,10 @@ class Rig:
         W, H = self.prm.image_width, self.prm.image_height
         self.img = acn.DeviceImage(W, H, local_rank)
         self.img.set_shard(world, rank, 4)
-        self.stream = torch.cuda.ExternalStream(acn.load_library().acn_dimage_stream(self.img._p), device=self.dev)
+        # The pass runs on the image's own stream and returns synchronised; the exchange of the pass sums (NCCL) and the
+        # timing events use torch's current stream.  Every step ends with a host synchronisation of both, so an event pair
+        # on torch's stream around a step brackets all of its device work.
+        self.stream = torch.cuda.current_stream(self.dev)
         self.buf = torch.zeros(self.img.words, dtype=torch.int64, device=self.dev) if world > 1 else None
         self.launches = 0
         self.rays = 0
@@ -228,10 +231,10 @@ class Rig:
         self.rays += st.rays if nl else 0
         self.n_local = nl
         if self.world > 1:
-            with self.torch.cuda.stream(self.stream):
-                self.img.copy_delta(self.buf)
-                self.dist.all_reduce(self.buf)                 # disjoint pixel tiles, integer sums: exact, order-independent
-                self.img.set_delta(self.buf)
+            self.img.copy_delta(self.buf, self.stream)
+            self.dist.all_reduce(self.buf)                 # disjoint pixel tiles, integer sums: exact, order-independent
+            self.img.set_delta(self.buf, self.stream)
+            self.stream.synchronize()
             self.img.end_pass()
         return st
 
@@ -359,14 +362,14 @@ def main():
 
         def host_step():
             rig.img.reset()
-            with torch.cuda.stream(rig.stream):
-                d_xy.copy_(h_xy, non_blocking=True)
-                rig.tracer.render_samples_device(d_xy, d_rgb, stream=rig.stream)
-                rig.img.accumulate(d_xy, d_rgb)
-                rig.img.copy_delta(rig.buf)
-                dist.all_reduce(rig.buf)
-                h_img.copy_(rig.buf, non_blocking=True)
+            d_xy.copy_(h_xy, non_blocking=True)
+            rig.tracer.render_samples_device(d_xy, d_rgb, stream=rig.stream)      # returns when the samples are traced
+            rig.img.accumulate(d_xy, d_rgb, rig.stream)
+            rig.img.copy_delta(rig.buf, rig.stream)
+            dist.all_reduce(rig.buf)
+            h_img.copy_(rig.buf, non_blocking=True)
             rig.stream.synchronize()
+            rig.img.reset()                       # the delta of this pass is dropped again
             return int(h_img[5])                  # the reduced image is read on the host
         h2d, d2h = n_local * 16, rig.img.words * 8
     host_step()

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--path-samples", type=int, default=None)
     ap.add_argument("--generic", action="store_true", help="generic kernels instead of the scene-specialised ones")
     ap.add_argument("--host-controller", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="per-pass samples, rays, waves, device and wall time (one GPU, device controller)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
 
@@ -98,7 +99,12 @@ def main():
                 img.push(xy, tracer.render_samples(xy, n_samples))
                 n_samples += xy.shape[0]; n_pass += 1; rays += tracer.last_stats.rays
         else:
-            img, n_samples, n_pass, rays = acn.render_image_device(flat, tracer, args.passes, use_dist)
+            log = None
+            if args.verbose and rank == 0:
+                def log(k, nt, nl, st, wall):
+                    print(f"  pass {k:3d}: {nt:7d} samples ({nl} here), {st.rays / 1e6:7.1f} M rays, {st.waves:3d} waves, {st.kernel_launches:4d} launches, "
+                          f"device {st.device_ms:7.2f} ms, wall {wall * 1e3:7.2f} ms", flush=True)
+            img, n_samples, n_pass, rays = acn.render_image_device(flat, tracer, args.passes, use_dist, log)
         dt = time.perf_counter() - t0
         tracer.close()
         if use_dist is not None:
