@@ -315,20 +315,6 @@ template <typename R> __device__ __forceinline__ AccV<R> seg_sum_acc( AccV<R> v,
     return v;
 }
 
-// Keys are non-decreasing over the lanes (-1: idle lane): the lane that starts my run of equal keys.  What all children of
-// one (task, light) share — the cone to the light, the sampling basis — is computed by that lane alone and handed round
-// with shuffles: 7 instructions per lane instead of ~80 (two normalisations, a canonical orthonormal, a square root).
-__device__ __forceinline__ int run_leader( int key, int lane )
-{
-    const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
-    const unsigned int starts = __ballot_sync( ACN_FULL, lane == 0 || kprev != key );
-    return 31 - __clz( ( int )( starts & ( 0xFFFFFFFFu >> ( 31 - lane ) ) ) );
-}
-template <typename R> __device__ __forceinline__ V3<R> shfl_v3( V3<R> v, int src )
-{
-    return v3<R>( __shfl_sync( ACN_FULL, v.x, src ), __shfl_sync( ACN_FULL, v.y, src ), __shfl_sync( ACN_FULL, v.z, src ) );
-}
-
 template <typename R> __device__ __forceinline__ void add_sample_acc( const Wave<R>& w, int sample, const AccV<R>& c )
 {
     typename Acc<R>::T* a = w.accum + 4ull * ( unsigned long long )sample;
@@ -967,65 +953,31 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     {
         const unsigned long long b0 = warp_fetch( &w.sc->cur_direct, chunk, lane );
         if( b0 >= n_blocks ) break;
-        // the windows of both blocks of the chunk are requested at once (two dependent loads each: directory, running
-        // counts), and every lane brings the task slot of "its" window entry along: the owner's slot is then a shuffle away
-        // instead of a third dependent load
-        ListWindow lws[ ACN_CHUNK ]; unsigned int slots[ ACN_CHUNK ];
-        #pragma unroll
-        for( int c = 0; c < ACN_CHUNK; c++ )
+        for( unsigned long long blk = b0; blk < b0 + chunk && blk < n_blocks; blk++ )
         {
-            const unsigned long long blk = b0 + c < n_blocks ? b0 + c : n_blocks - 1;
-            lws[ c ] = list_window( dl_cum, dl_dir, blk, n_entries, lane );
-            const unsigned long long e = ( unsigned long long )lws[ c ].e0 + lane;
-            slots[ c ] = e < n_entries ? dl_slot[ e ] : 0u;
-        }
-        #pragma unroll
-        for( int c = 0; c < ACN_CHUNK; c++ )
-        {
-            const unsigned long long blk = b0 + c;
-            if( c >= chunk || blk >= n_blocks ) break;
-            const ListWindow lw = lws[ c ];
+            const ListWindow lw = list_window( dl_cum, dl_dir, blk, n_entries, lane );
             const unsigned long long idx = ( blk << 5 ) + lane;
             const bool live = idx < total;
             const int j = window_find( lw.incl, live ? idx : ( blk << 5 ) );
             const unsigned long long prev = __shfl_sync( ACN_FULL, lw.incl, ( j + 31 ) & 31 );
-            const unsigned int t_owner = __shfl_sync( ACN_FULL, slots[ c ], j );
             AccV<R> sum = acc_zero<R>();
             int sample = -1;
-            // ---- the child: task t, light li, sample jj
-            unsigned int t = 0, nd = 1, li = 0, jj = 0;
-            I4 m; m.x = m.y = m.z = m.w = 0;
-            R4<R> pi, nc, pa, tb;
-            pi.x = pi.y = pi.z = pi.w = nc.x = nc.y = nc.z = nc.w = pa.x = pa.y = pa.z = pa.w = tb.x = tb.y = tb.z = tb.w = R( 0 );
             if( live )
             {
                 const unsigned long long r = idx - ( j ? prev : lw.excl0 );
-                t = t_owner;
-                m = in.meta[ t ];
-                nd = ( unsigned int )m.z;
-                li = ( unsigned int )( r / nd ); jj = ( unsigned int )( r - ( unsigned long long )li * nd );
-                pi = in.pos_id[ t ]; nc = in.nrm_ci[ t ]; pa = in.prj_a[ t ]; tb = in.tpc_b[ t ];
-            }
-            // ---- what the children of one (task, light) share, computed by the first lane of the run (obj_fov +
-            // m3d_s_con_z, scene.c:546-552)
-            const int leader = run_leader( live ? j * prm.n_lights + ( int )li : -1, lane );
-            V3<R> bZ = v3<R>( R( 0 ), R( 0 ), R( 1 ) ), bX = v3<R>( R( 1 ), R( 0 ), R( 0 ) ); R cos_rs = R( 0 );
-            if( live && lane == leader )
-            {
-                const SceneView<R, SH> svl = ray_view( prm, sv0, xyz( pi ) );
-                V3<R> axis;
-                obj_fov( svl, prm.lights[ li ].node, xyz( pi ), &axis, &cos_rs );
-                const Basis<R> b0 = basis_con_z( axis );
-                bZ = b0.Z; bX = b0.X;
-            }
-            bZ = shfl_v3( bZ, leader ); bX = shfl_v3( bX, leader ); cos_rs = __shfl_sync( ACN_FULL, cos_rs, leader );
-            if( live )
-            {
+                const unsigned int t = dl_slot[ lw.e0 + j ];
+                const I4 m = in.meta[ t ];
                 sample = m.x;
+                const unsigned int nd = ( unsigned int )m.z;
+                const unsigned int li = ( unsigned int )( r / nd ), jj = ( unsigned int )( r - ( unsigned long long )li * nd );
+                const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
                 const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
                 const DLight<R>& lg = prm.lights[ li ];
+
                 const SceneView<R, SH> sv = ray_view( prm, sv0, pos );
-                Basis<R> bs; bs.Z = bZ; bs.X = bX; bs.Y = cross( bZ, bX );
+                V3<R> axis; R cos_rs;
+                obj_fov( sv, lg.node, pos, &axis, &cos_rs );
+                const Basis<R> bs = basis_con_z( axis );
                 const R h = R( 1 ) - cos_rs;                                                 // areal_coverage, vectors.h:362
                 u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )li * nd + jj );
                 Ray<R> out; out.p = pos;
@@ -1125,22 +1077,14 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
         V3<R> tpm = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
         int sample = -1, key = -1;
         bool defer = false;
-        // the sampling basis around the task's normal (m3d_s_con_z, scene.c:588) is the same for all children of a task:
-        // the first lane of a run of equal tasks computes it (items are in non-decreasing task order in both kinds of group)
-        R4<R> nc; nc.x = nc.y = nc.w = R( 0 ); nc.z = R( 1 );
-        if( item != ACN_NONE64 ) nc = in.nrm_ci[ item >> 32 ];
-        const int leader = run_leader( item != ACN_NONE64 ? ( int )( ( item >> 32 ) & 0x7FFFFFFFull ) : -1, lane );
-        V3<R> bX = v3<R>( R( 1 ), R( 0 ), R( 0 ) ), bZ = v3<R>( R( 0 ), R( 0 ), R( 1 ) );
-        if( item != ACN_NONE64 && lane == leader ) { const Basis<R> b0 = basis_con_z( xyz( nc ) ); bX = b0.X; bZ = b0.Z; }
-        bX = shfl_v3( bX, leader ); bZ = shfl_v3( bZ, leader );
         if( item != ACN_NONE64 )
         {
             const unsigned long long t = item >> 32;
             const unsigned int i = ( unsigned int )item;
             const I4 m = in.meta[ t ];
-            const R4<R> pi = in.pos_id[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+            const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
             const V3<R> nrm = xyz( nc );
-            Basis<R> bs; bs.Z = bZ; bs.X = bX; bs.Y = cross( bZ, bX );
+            const Basis<R> bs = basis_con_z( nrm );
             u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )L * ( unsigned int )m.z + i );
             Ray<R> out; out.p = xyz( pi );
             out.d = from_basis( bs, sphere_cap<R>( &rv, R( 1 ) ) );
