@@ -30,7 +30,7 @@ enum
     K_COMPOUND = 0, K_PLANE = 1, K_SPHERE = 2, K_SQUAROID = 3, K_DIST_SPHERE = 4, K_DIST_TORUS = 5,
     K_PAIR_INSIDE = 6, K_PAIR_OUTSIDE = 7, K_NEG = 8, K_SCALE = 9
 };
-enum { F_ENV = 1, F_ROUGH = 2 };
+enum { F_ENV = 1, F_ROUGH = 2, F_SELF = 4, F_ENV2 = 8 };     // traversal records only (acn_tracer.cuh: CullBounds) — F_SELF: the record's ball IS the sphere; F_ENV2: test env[node] as well
 enum { GEO_STRIDE = 5 };
 enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
 enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };

@@ -564,7 +564,11 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
                     // horizon: an element must come within eps of the root's minimum to matter (merge rule);
                     // inside a nested element it must also beat that element's own minimum
                     const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;
-                    if( !( node_flags( lk ) & F_ENV ) || envelope_hits_before( rec.env, ray, hor ) )
+                    // rec.env: the element's cull bound — a tight ball round the contents (CullBounds; F_SELF: the sphere itself;
+                    // F_ENV2: the reference's envelope must be met as well) or the reference's envelope
+                    bool pass = !( node_flags( lk ) & ( F_ENV | F_SELF ) ) || envelope_hits_before( rec.env, ray, hor );
+                    if( pass && ( node_flags( lk ) & F_ENV2 ) ) pass = envelope_hits_before( sv.env[ c ], ray, hor );   // the ball sticks out of the envelope
+                    if( pass )
                     {
                         if( node_kind( lk ) == K_COMPOUND )
                         {
@@ -573,7 +577,13 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
                         else
                         {
                             V3<R> n;
-                            const R a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm, hor );
+                            R a;
+                            if( node_flags( lk ) & F_SELF )
+                            {
+                                a = sphere_hit<R>( xyz( rec.env ), rec.env.w, ray, sv.eps, want_trans ? &n : nullptr );
+                                if( want_trans && ( node_flags( lk ) & F_ROUGH ) && a < inf ) roughen( sv, c, ray, a, &n, ctx );
+                            }
+                            else a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm, hor );
                             if( !want_trans )
                             {
                                 if( a < min_a ) { min_a = a; if( a <= t_far ) found = true; }
