@@ -21,8 +21,11 @@ namespace acn {
 
 template <typename R> struct alignas( sizeof( R ) * 4 ) R4 { R x, y, z, w; };
 struct alignas( 16 ) I4 { int x, y, z, w; };
-// one child of a compound, packed for the traversal: its envelope and its link word with the node index in .w
-// (the material, which the traversal does not need, stays in link[n].w)
+// one element of a child list, packed for the traversal: its cull bound (envelope or tighter ball) and
+// link = ( kind | flags << 8, first record of the element's own list (compounds), skip record, node index );
+// skip = the record a ray goes to when it is through with this element: the next sibling or, behind the last one of
+// a list, the skip record of the list's compound (-1: end of the root list).  The records of a scene form a tree
+// laid out depth-first (acn_tracer.cuh), so a traversal is one index: no stack.
 template <typename R> struct CRec { R4<R> env; I4 link; };
 
 enum
@@ -30,7 +33,9 @@ enum
     K_COMPOUND = 0, K_PLANE = 1, K_SPHERE = 2, K_SQUAROID = 3, K_DIST_SPHERE = 4, K_DIST_TORUS = 5,
     K_PAIR_INSIDE = 6, K_PAIR_OUTSIDE = 7, K_NEG = 8, K_SCALE = 9
 };
-enum { F_ENV = 1, F_ROUGH = 2, F_SELF = 4, F_ENV2 = 8 };     // traversal records only (acn_tracer.cuh: CullBounds) — F_SELF: the record's ball IS the sphere; F_ENV2: test env[node] as well
+// flags of a node; the last three occur in traversal records only (acn_tracer.cuh: CullBounds, threaded records) —
+// F_SELF: the record's ball IS the sphere; F_ENV2: test env[node] as well; F_TOP: element of a root compound
+enum { F_ENV = 1, F_ROUGH = 2, F_SELF = 4, F_ENV2 = 8, F_TOP = 16 };
 enum { GEO_STRIDE = 5 };
 enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
 enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
@@ -72,6 +77,8 @@ template <typename R, bool SH = false> struct SceneView
     R   eps;            // shell thickness (f3_eps, vectors.h:33)
     int light_root;
     int matter_root;
+    int rec_light;      // first traversal record of each root list (-1: empty)
+    int rec_matter;
     int seed_mode;
 };
 

@@ -49,7 +49,7 @@ namespace acn {
 #define ACN_CSG_INLINE __forceinline__
 #endif
 
-// per-thread scratch of a scene query in shared memory, [slot][thread]: the CSG events and the traversal stack
+// per-thread scratch of a scene query in shared memory, [slot][thread]: the CSG events
 // element i of an array in shared memory, addressed by its 32-bit shared-window byte address (LDS/STS, no 64-bit pointer registers)
 template <typename T> struct SPtr
 {
@@ -63,23 +63,20 @@ template <typename T> struct SPtr
 template <typename R> struct CsgMem
 {
     SPtr<R> t; SPtr<unsigned short> iv;         // CSG_E events: crossing, leaf id | variable << 8
-    SPtr<int> sb, se;                           // per nesting level of compounds: where the walk of the parent list resumes, its end
     int stride;
 };
 
-template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthreads, int levels )
+template <typename R> __host__ __device__ inline size_t csg_mem_bytes( int nthreads )
 {
-    return ( size_t )( sizeof( R ) + 2 ) * CSG_E * nthreads + ( size_t )8 * levels * nthreads;
+    return ( size_t )( sizeof( R ) + 2 ) * CSG_E * nthreads;
 }
 
-template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned char* base, int nthreads, int tid, int levels )
+template <typename R> __device__ __forceinline__ CsgMem<R> csg_mem( unsigned char* base, int nthreads, int tid )
 {
     CsgMem<R> m;
     const unsigned int b = ( unsigned int )__cvta_generic_to_shared( base );
     m.t.a  = b + ( unsigned int )( tid * sizeof( R ) );
     m.iv.a = b + ( unsigned int )( sizeof( R ) * CSG_E * nthreads + tid * 2 );
-    const unsigned int stk = b + ( unsigned int )( ( sizeof( R ) + 2 ) * CSG_E * nthreads );
-    m.sb.a = stk + ( unsigned int )( tid * 4 ); m.se.a = stk + ( unsigned int )( ( levels * nthreads + tid ) * 4 );
     m.stride = nthreads;
     return m;
 }
@@ -467,15 +464,19 @@ template <typename R, bool SH> __device__ __noinline__ R march_hit( const SceneV
 }
 
 // obj_ray_hit after the envelope test (objects.c:261-284): fp_ray_hit + roughness
-template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R elem_hit( const SceneView<R, SH>& sv, const I4& lk, int c, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
+// MARCH selects what the kernel instantiation carries: 0 the event sweep over planes, spheres and quadrics; 1 the
+// full-featured sweep (distance-field leaves, coincident crossings, scale nodes; FP64: the reference's recursive march
+// too); 2 no composite objects at all — a scene of planes, spheres and quadrics (many_spheres.acn) gets kernels whose
+// register count and code size are set by the walk, not by the event sweep they never run.
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ R elem_hit( const SceneView<R, SH>& sv, const I4& lk, int c, const Ray<R>& ray, V3<R>* nor, HitCtx ctx,
                                                                          const CsgMem<R>& cm, const R t_far )
 {
     const int kind = node_kind( lk );
     R a;
     if( kind == K_PLANE || kind == K_SPHERE || kind == K_SQUAROID ) a = prim_hit( sv, kind, c, ray, nor );
-    else if( kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval<MARCH>( sv, c, ray, nor, ctx, cm, t_far );
-    else if( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) a = dist_hit( sv, kind, c, ray, nor );
-    else if( MARCH && sizeof( R ) == 8 ) a = march_hit( sv, c, ray, nor, ctx );     // the reference's recursive march: FP64 validation mode only
+    else if( MARCH != 2 && kind >= K_PAIR_INSIDE && sv.prog_ref[ c ].y > 0 ) a = csg_eval<MARCH == 1>( sv, c, ray, nor, ctx, cm, t_far );
+    else if( MARCH != 2 && ( kind == K_DIST_SPHERE || kind == K_DIST_TORUS ) ) a = dist_hit( sv, kind, c, ray, nor );
+    else if( MARCH == 1 && sizeof( R ) == 8 ) a = march_hit( sv, c, ray, nor, ctx );     // the reference's recursive march: FP64 validation mode only
     else a = Num<R>::inf();                 // unreachable: the FP32 tracer refuses scenes the sweep does not cover (Tracer::init)
     if( nor && ( node_flags( lk ) & F_ROUGH ) && a < Num<R>::inf() ) roughen( sv, c, ray, a, nor, ctx );
     return a;
@@ -512,20 +513,19 @@ template <typename R, bool SH> __device__ __forceinline__ void trans_commit( con
     }
 }
 
-template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ R scene_query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,
                                                                             Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
 {
     // t_far: hits at a >= t_far are of no interest to the caller (the shadow test's light distance, a path
     // ray's max_path_length, +inf otherwise).  Without Q_TRANS a hit with a <= t_far ends the search at once.
-    // Envelopes are culled against the best candidate so far: nothing inside an envelope that the ray enters
+    // Bounds are culled against the best candidate so far: nothing inside a ball that the ray enters
     // at t_env can be reported closer than t_env - eps, so skipping it when t_env > horizon + 2 eps changes nothing.
     //
-    // The walk is LOCKSTEP over the lanes that enter the query together: one child record (or one pop of the
-    // range stack) per iteration and lane, a vote keeps everybody in the loop until the last lane is through.
-    // Written as a plain while-loop with `continue`s the lanes drifted apart for good — a lane whose ray misses an
-    // envelope went round the loop on its own while its neighbours tested a sphere, and from then on each drift
-    // group ran the same instructions at different times (many_spheres: 4-8 of 32 lanes active per instruction
-    // even on the loop head).
+    // The walk follows the threaded traversal records (CRec): one record per iteration and lane, the position is one
+    // index.  It is LOCKSTEP over the lanes that enter the query together: a vote keeps everybody in the loop until the
+    // last lane is through.  (Written as a plain while-loop with `continue`s the lanes drifted apart for good — a lane
+    // whose ray misses a bound went round the loop on its own while its neighbours tested a sphere, and from then on
+    // each drift group ran the same instructions at different times.)
     const R inf = Num<R>::inf();
     const bool want_trans = ( flags & Q_TRANS ) != 0;
     const R slack = R( 2 ) * sv.eps;
@@ -540,67 +540,227 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R scene_qu
         const I4 rl = sv.link[ root ];
         const R far0 = r_min( t_far, best );                 // strict '<' between the roots: matter must beat the lights
         if( act && ( node_flags( rl ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + slack ) ) act = false;
-        int sp = 0;
-        int beg = rl.y, end = act ? rl.y + rl.z : rl.y;
+        int cur = act ? ( pass == 0 ? sv.rec_light : sv.rec_matter ) : -1;
         R min_a = inf;
         Trans<R> tl; tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
-        R el_a = inf; V3<R> el_n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); int el_obj = -1;     // closest hit inside the current nested element
+        // closest hit inside the current nested element of the root (a compound among the root's elements counts as ONE
+        // element whose hit is the plain closest hit of its contents, compound.c:215-244)
+        R el_a = inf; V3<R> el_n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); int el_obj = -1;
+        bool nested = false;
         for( ;; )
         {
-            const bool more = !found && ( beg < end || sp > 0 );
+            const bool more = !found && cur >= 0;
             if( !__any_sync( mask, more ) ) break;
             if( more )
             {
-                if( beg >= end )
-                {   // a nested list is through: back to its parent list
-                    sp--; beg = cm.sb[ sp * cm.stride ]; end = cm.se[ sp * cm.stride ];
-                    if( sp == 0 && want_trans ) { trans_commit( sv, ray, el_a, el_n, el_obj, &min_a, &tl ); el_a = inf; el_obj = -1; }
+                const CRec<R> rec = sv.crec[ cur ];
+                const I4 lk = rec.link;
+                const int c = lk.w, fl = node_flags( lk );
+                cur = lk.z;
+                if( want_trans && nested && ( fl & F_TOP ) )
+                {   // back among the root's elements: the nested element is through
+                    trans_commit( sv, ray, el_a, el_n, el_obj, &min_a, &tl ); el_a = inf; el_obj = -1; nested = false;
                 }
-                else
+                // horizon: an element must come within eps of the root's minimum to matter (merge rule);
+                // inside a nested element it must also beat that element's own minimum
+                const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;
+                // rec.env: the element's cull bound — a tight ball round the contents (CullBounds; F_SELF: the sphere itself;
+                // F_ENV2: the reference's envelope must be met as well) or the reference's envelope
+                bool ok = !( fl & ( F_ENV | F_SELF ) ) || envelope_hits_before( rec.env, ray, hor );
+                if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits_before( sv.env[ c ], ray, hor );   // the ball sticks out of the envelope
+                if( ok )
                 {
-                    const CRec<R> rec = sv.crec[ beg++ ];
-                    const I4 lk = rec.link;
-                    const int c = lk.w;
-                    // horizon: an element must come within eps of the root's minimum to matter (merge rule);
-                    // inside a nested element it must also beat that element's own minimum
-                    const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;
-                    // rec.env: the element's cull bound — a tight ball round the contents (CullBounds; F_SELF: the sphere itself;
-                    // F_ENV2: the reference's envelope must be met as well) or the reference's envelope
-                    bool pass = !( node_flags( lk ) & ( F_ENV | F_SELF ) ) || envelope_hits_before( rec.env, ray, hor );
-                    if( pass && ( node_flags( lk ) & F_ENV2 ) ) pass = envelope_hits_before( sv.env[ c ], ray, hor );   // the ball sticks out of the envelope
-                    if( pass )
+                    if( node_kind( lk ) == K_COMPOUND )
                     {
-                        if( node_kind( lk ) == K_COMPOUND )
+                        cur = lk.y;                          // first record of its list (its skip record when the list is empty)
+                        if( fl & F_TOP ) nested = true;
+                    }
+                    else
+                    {
+                        V3<R> n;
+                        R a;
+                        if( fl & F_SELF )
                         {
-                            cm.sb[ sp * cm.stride ] = beg; cm.se[ sp * cm.stride ] = end; sp++; beg = lk.y; end = lk.y + lk.z;     // depth checked at upload
+                            a = sphere_hit<R>( xyz( rec.env ), rec.env.w, ray, sv.eps, want_trans ? &n : nullptr );
+                            if( want_trans && ( fl & F_ROUGH ) && a < inf ) roughen( sv, c, ray, a, &n, ctx );
                         }
-                        else
+                        else a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm, hor );
+                        if( !want_trans )
                         {
-                            V3<R> n;
-                            R a;
-                            if( node_flags( lk ) & F_SELF )
-                            {
-                                a = sphere_hit<R>( xyz( rec.env ), rec.env.w, ray, sv.eps, want_trans ? &n : nullptr );
-                                if( want_trans && ( node_flags( lk ) & F_ROUGH ) && a < inf ) roughen( sv, c, ray, a, &n, ctx );
-                            }
-                            else a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : nullptr, ctx, cm, hor );
-                            if( !want_trans )
-                            {
-                                if( a < min_a ) { min_a = a; if( a <= t_far ) found = true; }
-                            }
-                            else if( sp > 0 )
-                            {
-                                if( a < el_a ) { el_a = a; el_n = n; el_obj = c; }
-                            }
-                            else trans_commit( sv, ray, a, n, c, &min_a, &tl );
+                            if( a < min_a ) { min_a = a; if( a <= t_far ) found = true; }
                         }
+                        else if( nested )
+                        {
+                            if( a < el_a ) { el_a = a; el_n = n; el_obj = c; }
+                        }
+                        else trans_commit( sv, ray, a, n, c, &min_a, &tl );
                     }
                 }
             }
         }
+        if( want_trans && nested ) trans_commit( sv, ray, el_a, el_n, el_obj, &min_a, &tl );      // the root list ended inside a nested element
         if( min_a < best ) { best = min_a; if( want_trans ) *trans = tl; }
     }
     return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same walk one record at a time, for the kernels that keep 32 traversals going per warp and hand a lane a new ray
+// the moment its old one is through (acn_kernels.cuh: refill loops).  The position of a traversal is `cur`; a lane can
+// be interrupted between any two records.
+//   walk_any_step     "is anything at a <= t_far?" (shadow rays, probes): returns the next record, WALK_END when the
+//                     list is through without a find, WALK_FOUND at the first element hit at a <= t_far
+//   WalkT, walk_step  closest hit with the eps-merge of the root's elements (Q_TRANS), or a probe: returns the next record,
+//                     WALK_END or WALK_FOUND; walk_trans_finish closes a nested element that reached the end of the root list
+// Same tests in the same order as scene_query, which the specialised builds and k_primary keep using.
+// ---------------------------------------------------------------------------------------------
+enum { WALK_END = -1, WALK_FOUND = -2 };
+
+// In a refill loop 28 of 32 lanes test a record in every iteration, and whatever only the lanes do whose ray PASSED the
+// bound runs at two or three lanes: thirty instructions of "compute the sphere hit and its normal" for one record in ten
+// cost more issue slots than the bound tests of all of them (ncu, many_spheres).  The steps below therefore keep the
+// common cases free of divergent branches: the ray / ball arithmetic is done once per record (RayBall), bound test,
+// descent into a compound and a sphere held in its record (F_SELF) are selects on it, and the normal of a sphere inside
+// a nested element is not computed when it becomes the element's closest hit but when the element is committed
+// (WalkT::el_rec).  Everything else — planes, quadrics, composite objects, rough spheres, spheres among the root's own
+// elements — takes the general path.
+template <typename R> struct RayBall
+{
+    R s, q, disc, eps;                      // p.d, |p|^2 - r^2, r^2 - |p - (p.d) d|^2 (gmath.h:64-97, rejection-vector form)
+    V3<R> p;
+    __device__ __forceinline__ RayBall( const R4<R>& b, const Ray<R>& ray, R eps_ ) : eps( eps_ )
+    {
+        p = ray.p - xyz( b );
+        s = dot( p, ray.d );
+        q = sqr( p ) - b.w * b.w;
+        const V3<R> l = p - ray.d * s;
+        disc = b.w * b.w - sqr( l );
+    }
+    // envelope_hits_before
+    __device__ __forceinline__ bool before( R t_far ) const
+    {
+        const R g = -s - t_far;
+        return disc >= R( 0 ) && ( q < R( 0 ) || ( s < R( 0 ) && !( g > R( 0 ) && g * g > disc ) ) );
+    }
+    // sphere_hit without the normal
+    __device__ __forceinline__ R hit() const
+    {
+        const R sq = r_sqrt( r_max( disc, R( 0 ) ) );
+        const R a = ( s < R( 0 ) && q > R( 0 ) ) ? -s - sq - eps : -s + sq - eps;
+        return ( disc >= R( 0 ) && ( s < R( 0 ) || q < R( 0 ) ) ) ? a : Num<R>::inf();
+    }
+    // is the sphere's hit distance <= x (STRICT: < x)?  No square root: entry -s - sq <= x + eps  <=>  g <= 0 or g^2 <= disc
+    // with g = -s - x - eps; exit -s + sq <= x + eps  <=>  h >= 0 and disc <= h^2 with h = x + eps + s
+    template <bool STRICT> __device__ __forceinline__ bool hit_within( R x ) const
+    {
+        const R h = x + eps + s;            // = -g
+        const bool entry = s < R( 0 ) && q > R( 0 );
+        const bool any = disc >= R( 0 ) && ( s < R( 0 ) || q < R( 0 ) );
+        const bool e_in = STRICT ? ( h > R( 0 ) || h * h < disc ) : ( h >= R( 0 ) || h * h <= disc );
+        const bool x_in = STRICT ? ( h > R( 0 ) && disc < h * h ) : ( h >= R( 0 ) && disc <= h * h );
+        return any && ( entry ? e_in : x_in );
+    }
+};
+
+// STRICT: a find needs a < t_far (probes, whose callers test a < t_lim) instead of a <= t_far (shadow rays: scene.c:569 min > a)
+template <typename R, int MARCH, bool SH, bool STRICT> __device__ __forceinline__ int walk_any_step( const SceneView<R, SH>& sv, const Ray<R>& ray, const R t_far, const int cur,
+                                                                                               HitCtx ctx, const CsgMem<R>& cm )
+{
+    const CRec<R> rec = sv.crec[ cur ];
+    const I4 lk = rec.link;
+    const int c = lk.w, fl = node_flags( lk );
+    const R hor = t_far + R( 2 ) * sv.eps;
+    const RayBall<R> rb( rec.env, ray, sv.eps );
+    bool ok = !( fl & ( F_ENV | F_SELF ) ) || rb.before( hor );
+    if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits_before( sv.env[ c ], ray, hor );
+    const bool comp = node_kind( lk ) == K_COMPOUND, self = ( fl & F_SELF ) != 0;
+    int next = ( ok && comp ) ? lk.y : lk.z;
+    if( ok && self && rb.template hit_within<STRICT>( t_far ) ) next = WALK_FOUND;
+    if( ok && !comp && !self )
+    {
+        const R a = elem_hit<R, MARCH>( sv, lk, c, ray, ( V3<R>* )nullptr, ctx, cm, hor );
+        if( STRICT ? a < t_far : ( a <= t_far && a < Num<R>::inf() ) ) next = WALK_FOUND;
+    }
+    return next;
+}
+
+template <typename R> struct WalkT
+{
+    R min_a, el_a; V3<R> el_n; int el_obj, el_rec; Trans<R> tl; bool nested;
+    __device__ __forceinline__ void reset()
+    {
+        min_a = el_a = Num<R>::inf(); el_n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); el_obj = el_rec = -1; nested = false;
+        tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    }
+};
+
+// the nested element of the root is through: its closest hit becomes one candidate of the root (compound.c:246-299).
+// el_rec >= 0: that hit is a sphere held in its record, whose normal was left for now (sphere_ray_hit, gmath.h:64-97).
+template <typename R, bool SH> __device__ __forceinline__ void walk_commit_nested( const SceneView<R, SH>& sv, const Ray<R>& ray, WalkT<R>& s )
+{
+    if( s.el_rec >= 0 && s.el_a < Num<R>::inf() )
+    {
+        const CRec<R> rec = sv.crec[ s.el_rec ];
+        s.el_n = unit( madd( ray.p - xyz( rec.env ), ray.d, s.el_a ) );
+        s.el_obj = rec.link.w;
+    }
+    trans_commit( sv, ray, s.el_a, s.el_n, s.el_obj, &s.min_a, &s.tl );
+    s.el_a = Num<R>::inf(); s.el_obj = s.el_rec = -1; s.nested = false;
+}
+
+// one record of a walk that is a probe (STRICT any-hit) in some lanes and a closest-hit search with transitions in others.
+// far0: min( the caller's t_far, the closest light hit ) — matter must beat the lights (scene.c:362-382)
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ int walk_step( const SceneView<R, SH>& sv, const Ray<R>& ray, const R far0, const bool want_trans, const int cur,
+                                                                               WalkT<R>& s, HitCtx ctx, const CsgMem<R>& cm )
+{
+    const CRec<R> rec = sv.crec[ cur ];
+    const I4 lk = rec.link;
+    const int c = lk.w, fl = node_flags( lk );
+    if( want_trans && s.nested && ( fl & F_TOP ) ) walk_commit_nested( sv, ray, s );         // back among the root's elements
+    const R hor = ( want_trans ? r_min( r_min( s.min_a + sv.eps, s.el_a ), far0 ) : far0 ) + R( 2 ) * sv.eps;
+    const RayBall<R> rb( rec.env, ray, sv.eps );
+    bool ok = !( fl & ( F_ENV | F_SELF ) ) || rb.before( hor );
+    if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits_before( sv.env[ c ], ray, hor );
+    const bool comp = node_kind( lk ) == K_COMPOUND;
+    // a sphere held in its record whose hit needs no normal now: a probe, or inside a nested element
+    const bool leaf = ( fl & ( F_SELF | F_ROUGH ) ) == F_SELF && ( !want_trans || s.nested );
+    int next = ( ok && comp ) ? lk.y : lk.z;
+    if( ok && comp && ( fl & F_TOP ) ) s.nested = true;
+    const R a_leaf = rb.hit();
+    if( ok && leaf )
+    {
+        if( !want_trans ) { if( a_leaf < far0 ) next = WALK_FOUND; }
+        else if( a_leaf < s.el_a ) { s.el_a = a_leaf; s.el_rec = cur; }
+    }
+    if( ok && !comp && !leaf )
+    {
+        V3<R> n = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+        R a;
+        if( fl & F_SELF )
+        {
+            a = sphere_hit<R>( xyz( rec.env ), rec.env.w, ray, sv.eps, &n );
+            if( want_trans && ( fl & F_ROUGH ) && a < Num<R>::inf() ) roughen( sv, c, ray, a, &n, ctx );
+        }
+        else a = elem_hit<R, MARCH>( sv, lk, c, ray, want_trans ? &n : ( V3<R>* )nullptr, ctx, cm, hor );
+        if( !want_trans ) { if( a < far0 ) next = WALK_FOUND; }
+        else if( s.nested ) { if( a < s.el_a ) { s.el_a = a; s.el_n = n; s.el_obj = c; s.el_rec = -1; } }
+        else trans_commit( sv, ray, a, n, c, &s.min_a, &s.tl );
+    }
+    return next;
+}
+
+template <typename R, bool SH> __device__ __forceinline__ void walk_trans_finish( const SceneView<R, SH>& sv, const Ray<R>& ray, WalkT<R>& s )
+{
+    if( s.nested ) walk_commit_nested( sv, ray, s );        // the root list ended inside a nested element
+}
+
+// may the walk of a root compound start at all?  (the root's own envelope, culled against the horizon)
+template <typename R, bool SH> __device__ __forceinline__ int walk_root( const SceneView<R, SH>& sv, const Ray<R>& ray, const bool light, const R far0 )
+{
+    const int root = light ? sv.light_root : sv.matter_root;
+    const I4 rl = sv.link[ root ];
+    if( ( node_flags( rl ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + R( 2 ) * sv.eps ) ) return WALK_END;
+    return light ? sv.rec_light : sv.rec_matter;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -631,7 +791,7 @@ template <typename R, bool SH> __device__ __noinline__ HitN<R> squaroid_hit_ool(
 #include "acn_spec_gen.h"
 #endif
 
-template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ R query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,
                                                                       Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )
 {
 #if defined(ACN_SPEC_SCENE)

@@ -78,7 +78,6 @@ template <typename R> struct DParams
     R     eps_rel;                            // per-ray shell thickness = max( sv.eps, eps_rel * |origin|_inf ); 0: constant
     int   stage_bytes;                        // node table bytes staged into shared memory (0: none)
     unsigned int off_geo, off_link, off_pref, off_crec, off_par, off_prog;   // byte offsets of the staged tables (env at 0)
-    int   stk_levels;                         // levels of the traversal stack in shared memory (deepest compound nesting + 1)
     int   n_heavy;                            // envelopes of the expensive top-level objects (CSG, distance fields); -1: no split
     int   heavy[ 8 ];
     const u64* skipA;                         // LCG skip table: state after 2k steps = s*A[k] + C[k]
@@ -317,6 +316,9 @@ template <typename R> __device__ __forceinline__ AccV<R> seg_sum_acc( AccV<R> v,
 
 template <typename R> __device__ __forceinline__ void add_sample_acc( const Wave<R>& w, int sample, const AccV<R>& c )
 {
+#ifdef ACN_TEST_NO_ACC
+    if( sample >= 0 ) return;       // timing experiment only
+#endif
     typename Acc<R>::T* a = w.accum + 4ull * ( unsigned long long )sample;
     atomic_add_acc( a + 0, c.x );
     atomic_add_acc( a + 1, c.y );
@@ -370,6 +372,7 @@ template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> stage
         sv.prog.a     = base + prm.off_prog;
         sv.children.a = 0;                       // march / host only
         sv.eps = prm.sv.eps; sv.light_root = prm.sv.light_root; sv.matter_root = prm.sv.matter_root; sv.seed_mode = prm.sv.seed_mode;
+        sv.rec_light = prm.sv.rec_light; sv.rec_matter = prm.sv.rec_matter;
         return sv;
     }
 }
@@ -577,12 +580,30 @@ template <typename R, bool SH> __device__ __forceinline__ void shade_hits( const
                    RC_REFRACT, sample, mix64( key, KEY_REFRACT ) );
 }
 
+// a hit of a ray of the tree goes to the hit queue: the surface response (scene_s_lum) runs in its own kernel (k_shade)
+// over the compacted hits.  eps: the shell thickness the ray was traced with.
+template <typename R> __device__ __forceinline__ void emit_hit( const Wave<R>& w, const Ray<R>& ray, R a, R eps, const Trans<R>& tr, R I, int depth, V3<R> tp, int sample, u64 key )
+{
+    // the hit distance itself is only good to a few ulp of its magnitude: keep the shading point that far in front
+    const R hit_eps = r_max( eps, w.prm.eps_rel * a );
+    a -= hit_eps - eps;
+    const unsigned long long slot = agg_inc( &w.sc->hits );
+    if( slot >= w.hits_cap ) { w.sc->overflow = 5; return; }
+    R4<R> q;
+    q.x = ray.p.x; q.y = ray.p.y; q.z = ray.p.z; q.w = a;                          w.hits_out.o_a[ slot ] = q;
+    q.x = ray.d.x; q.y = ray.d.y; q.z = ray.d.z; q.w = I;                          w.hits_out.d_i[ slot ] = q;
+    q.x = tr.exit_nor.x; q.y = tr.exit_nor.y; q.z = tr.exit_nor.z; q.w = hit_eps;  w.hits_out.n_e[ slot ] = q;
+    q.x = tp.x; q.y = tp.y; q.z = tp.z; q.w = R( 0 );                              w.hits_out.tp[ slot ] = q;
+    I4 m; m.x = depth; m.y = sample; m.z = tr.exit_obj; m.w = tr.enter_obj;        w.hits_out.meta[ slot ] = m;
+    w.hits_out.key[ slot ] = key;
+}
+
 // trace one ray of the tree and shade its hit; returns true when the ray leaves the scene, in which
 // case the caller owes the sample  background * tp * I  (scene.c:484-491, 613-616)
 //   cls != RC_PATH: scene_s_trans_hit (lights + matter)
 //   cls == RC_PATH: matter only; "leaves" = nothing closer than max_path_length        (scene.c:606-616)
 //   probe: the hit's shading would return 0 (depth 0 or I < Imin) — only "anything hit?" matters
-template <typename R, bool MARCH, bool SH> __device__ __forceinline__ bool trace_ray( const Wave<R>& w, const SceneView<R, SH>& sv0, const CsgMem<R>& cm, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ bool trace_ray( const Wave<R>& w, const SceneView<R, SH>& sv0, const CsgMem<R>& cm, const Ray<R>& ray, R I, int depth, V3<R> tp, int cls,
                                                                 bool probe, int sample, u64 key )
 {
     const DParams<R>& prm = w.prm;
@@ -598,19 +619,7 @@ template <typename R, bool MARCH, bool SH> __device__ __forceinline__ bool trace
     R a = query<R, MARCH>( sv, ray, flags, t_lim, &tr, ctx, cm );     // nothing at or beyond t_lim matters
     if( !( a < t_lim ) ) return true;
     if( probe ) return false;
-    // the hit distance itself is only good to a few ulp of its magnitude: keep the shading point that far in front
-    const R hit_eps = r_max( sv.eps, prm.eps_rel * a );
-    a -= hit_eps - sv.eps;
-    // the surface response (scene_s_lum) runs in its own kernel over the compacted hits
-    const unsigned long long slot = agg_inc( &w.sc->hits );
-    if( slot >= w.hits_cap ) { w.sc->overflow = 5; return false; }
-    R4<R> q;
-    q.x = ray.p.x; q.y = ray.p.y; q.z = ray.p.z; q.w = a;                          w.hits_out.o_a[ slot ] = q;
-    q.x = ray.d.x; q.y = ray.d.y; q.z = ray.d.z; q.w = I;                          w.hits_out.d_i[ slot ] = q;
-    q.x = tr.exit_nor.x; q.y = tr.exit_nor.y; q.z = tr.exit_nor.z; q.w = hit_eps;  w.hits_out.n_e[ slot ] = q;
-    q.x = tp.x; q.y = tp.y; q.z = tp.z; q.w = R( 0 );                              w.hits_out.tp[ slot ] = q;
-    I4 m; m.x = depth; m.y = sample; m.z = tr.exit_obj; m.w = tr.enter_obj;        w.hits_out.meta[ slot ] = m;
-    w.hits_out.key[ slot ] = key;
+    emit_hit( w, ray, a, sv.eps, tr, I, depth, tp, sample, key );
     return false;
 }
 
@@ -638,14 +647,14 @@ __device__ __forceinline__ void pend_push( unsigned long long* ring, int head, i
 }
 
 // obj_ray_hit of a light for a direct sample (scene.c:564): spheres in line, any other shape out of line
-template <typename R, bool MARCH, bool SH> __device__ __noinline__ R light_hit_cold( SceneView<R, SH> sv, int node, Ray<R> ray, HitCtx ctx, CsgMem<R> cm )
+template <typename R, int MARCH, bool SH> __device__ __noinline__ R light_hit_cold( SceneView<R, SH> sv, int node, Ray<R> ray, HitCtx ctx, CsgMem<R> cm )
 {
     const I4 lk = sv.link[ node ];
     if( ( node_flags( lk ) & F_ENV ) && !envelope_hits( sv.env[ node ], ray ) ) return Num<R>::inf();
     return elem_hit<R, MARCH>( sv, lk, node, ray, ( V3<R>* )nullptr, ctx, cm, Num<R>::inf() );
 }
 
-template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R light_hit( const SceneView<R, SH>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ R light_hit( const SceneView<R, SH>& sv, int node, const Ray<R>& ray, HitCtx ctx, const CsgMem<R>& cm )
 {
     const I4 lk = sv.link[ node ];
     if( node_kind( lk ) == K_SPHERE )
@@ -751,7 +760,7 @@ __global__ void k_sched( Sched* s, const u64* cum, const unsigned int* pdir, uns
 }
 
 // camera rays (scene.c:976-990) fused with their first trace + shade
-template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK )
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK )
 k_primary( Wave<R> w, const double* __restrict__ xy )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -760,7 +769,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
     const int chunk = launch_chunk( count >> 5 );
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks: no need to stage the scene
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     unsigned long long n_rays = 0;
@@ -794,7 +803,8 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
 // explicit rays, read in place from the tops of the two ends of the ray stack: items [0, pad_a) are the take_a newest
 // rays of end A (reflection / chromatic), padded to a whole number of 32-ray groups so that no warp mixes the kinds,
 // items [pad_a, pad_a + take_b) the take_b newest of end B (refraction).  What k_shade spawns afterwards overwrites them.
-template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
+#if defined(ACN_SPEC_SCENE)
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
 k_rays( Wave<R> w, RayBuf<R> in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -806,7 +816,7 @@ k_rays( Wave<R> w, RayBuf<R> in )
     const int chunk = launch_chunk( count >> 5 );
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x );
     const int lane = threadIdx.x & 31;
     unsigned long long* ring = ring_all[ threadIdx.x >> 5 ];
     int pend_head = 0, pend_n = 0;
@@ -865,6 +875,161 @@ k_rays( Wave<R> w, RayBuf<R> in )
     warp_count( &w.sc->stats[ ST_CHROMATIC ], n_chro, lane );
     warp_count( &w.sc->stats[ ST_REFRACT ], n_refr, lane );
 }
+
+#else
+// ---------------------------------------------------------------------------------------------
+// The kernels that WALK the scene (no specialised code for its structure): refill loops.
+// A ray's walk through the threaded traversal records takes anything between one record (it misses the first bound)
+// and hundreds (many_spheres: a ray grazing five levels of clusters), and the children of a diffuse hit point in
+// all directions.  Traced a group of 32 at a time, a warp waited for its longest walk with a third of its lanes
+// busy (ncu, many_spheres: 11.7 of the 21.7 lanes that had a ray at all were inside the walk on average; the other
+// ten had drawn a direction below the horizon).  Here a warp keeps 32 walks going: a lane whose ray is through takes
+// the next LIVE ray at once.  Rays that have to be generated first (shadow and path children: window search,
+// sampling, light test — warp-collective work at 32 lanes) go through a ring in shared memory; the walk of a lane is
+// one record index (acn_isect.cuh: walk_*_step) and survives the refill in registers.
+// Results are added per ray with integer (fixed-point) atomics: the sums do not depend on the order.
+// ---------------------------------------------------------------------------------------------
+#ifndef ACN_REFILL_MIN
+#define ACN_REFILL_MIN 8          // idle lanes that trigger a refill (all 32 at the latest)
+#endif
+
+// per-ray shell thickness (ray_view) without copying the scene view
+template <typename R> __device__ __forceinline__ R ray_eps( const DParams<R>& prm, R eps0, V3<R> o )
+{
+    return prm.eps_rel > R( 0 ) ? r_max( eps0, prm.eps_rel * r_max( r_max( r_abs( o.x ), r_abs( o.y ) ), r_abs( o.z ) ) ) : eps0;
+}
+
+// lights of a ray of the tree (first pass of scene_s_trans_hit, scene.c:362-382): the few records of the light root, walked
+// at once by the lanes that have just been given a ray.  Returns the closest light hit; its transition goes to *tl.
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ R walk_lights( const SceneView<R, SH>& sv, const Ray<R>& ray, const bool want_trans, Trans<R>* tl,
+                                                                               HitCtx ctx, const CsgMem<R>& cm )
+{
+    const R inf = Num<R>::inf();
+    WalkT<R> s; s.reset();
+    int c = walk_root( sv, ray, true, inf );
+    while( c >= 0 ) c = walk_step<R, MARCH>( sv, ray, inf, want_trans, c, s, ctx, cm );
+    if( !want_trans ) return c == WALK_FOUND ? R( 0 ) : inf;            // a probe only asks "anything?"
+    walk_trans_finish( sv, ray, s );
+    *tl = s.tl;
+    return s.min_a;
+}
+
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
+k_rays( Wave<R> w, RayBuf<R> in )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    __shared__ R   s_ln[ 3 ][ ACN_BLOCK ];          // transition of the closest light hit of the lane's ray
+    __shared__ int s_lo[ 2 ][ ACN_BLOCK ];
+    const unsigned long long take_a = w.sc->take_a, take_b = w.sc->take_b, pad_a = ( take_a + 31ull ) & ~31ull;
+    const unsigned long long base_a = w.sc->base_a, top_b = w.rays_cap - 1ull - w.sc->base_b;      // slot of B's item j: top_b - j
+    const unsigned long long count = pad_a + take_b;
+    if( count == 0 || w.sc->overflow ) return;
+    const int chunk = launch_chunk( count >> 5 );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= count ) return;     // more warps than chunks
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x );
+    const DParams<R>& prm = w.prm;
+    const R inf = Num<R>::inf();
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = ( 1u << lane ) - 1u;
+    bool input_done = false;
+    unsigned long long c_cur = 0, c_end = 0;
+    unsigned int n_refl = 0, n_chro = 0, n_refr = 0;
+    // the lane's walk
+    int cur = WALK_END;
+    unsigned long long slot = 0;
+    Ray<R> ray; ray.p = ray.d = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    R eps = sv0.eps, best_l = inf;
+    bool probe = false, pend = false;
+    HitCtx ctx; ctx.key = 0;
+    WalkT<R> ws; ws.reset();
+    for( ;; )
+    {
+        const unsigned int idle = __ballot_sync( ACN_FULL, cur < 0 );
+        if( idle == ACN_FULL || ( !input_done && __popc( idle ) >= ACN_REFILL_MIN ) )
+        {
+            if( pend )
+            {   // ---- the rays that came to their end since the last refill, together: hit record or background
+                pend = false;
+                SceneView<R, SH> sv = sv0; sv.eps = eps;
+                const R4<R> a = in.o_i[ slot ], c = in.tp[ slot ];
+                const I4 m = in.meta[ slot ];
+                if( !probe ) walk_trans_finish( sv, ray, ws );
+                if( !probe && ws.min_a < best_l ) emit_hit( w, ray, ws.min_a, eps, ws.tl, a.w, m.x & 0xFF, xyz( c ), m.y, ctx.key );
+                else if( !probe && best_l < inf )
+                {
+                    Trans<R> tl;
+                    tl.exit_nor = v3<R>( s_ln[ 0 ][ threadIdx.x ], s_ln[ 1 ][ threadIdx.x ], s_ln[ 2 ][ threadIdx.x ] );
+                    tl.exit_obj = s_lo[ 0 ][ threadIdx.x ]; tl.enter_obj = s_lo[ 1 ][ threadIdx.x ];
+                    emit_hit( w, ray, best_l, eps, tl, a.w, m.x & 0xFF, xyz( c ), m.y, ctx.key );
+                }
+                else add_sample( w, m.y, mul( prm.background, xyz( c ) ) * a.w );          // scene.c:484-491: the ray leaves the scene
+            }
+            if( c_cur >= c_end && !input_done )
+            {
+                c_cur = warp_fetch( &w.sc->cur_rays, 32ull * chunk, lane );
+                c_end = c_cur + 32ull * chunk;
+                if( c_cur >= count ) input_done = true;
+            }
+            if( input_done ) { if( idle == ACN_FULL ) break; }
+            else
+            {   // the r-th idle lane takes item c_cur + r
+                const int n_idle = __popc( idle );
+                const unsigned long long avail = c_end - c_cur;
+                const int n_take = ( unsigned long long )n_idle < avail ? n_idle : ( int )avail;
+                const int r = __popc( idle & lt );
+                if( cur < 0 && r < n_take )
+                {
+                    unsigned long long i = c_cur + r;
+                    if( i < pad_a ) i = i < take_a ? base_a + i : ACN_NONE64;
+                    else            i = i < count ? top_b - ( i - pad_a ) : ACN_NONE64;
+                    if( i != ACN_NONE64 )
+                    {
+                        const R4<R> a = in.o_i[ i ], b = in.d_[ i ];
+                        const I4 m = in.meta[ i ];
+                        slot = i;
+                        ray.p = xyz( a ); ray.d = xyz( b );
+                        const int cls = ( m.x >> 8 ) & 0xFF;
+                        n_refl += cls == RC_REFLECT; n_chro += cls == RC_CHROMATIC; n_refr += cls == RC_REFRACT;
+                        probe = ( m.x & RAYF_PROBE ) != 0;
+                        ctx.key = ( u64 )( unsigned )m.z | ( ( u64 )( unsigned )m.w << 32 );
+                        eps = ray_eps( prm, sv0.eps, ray.p );
+                        SceneView<R, SH> sv = sv0; sv.eps = eps;
+                        Trans<R> tl; tl.exit_obj = tl.enter_obj = -1; tl.exit_nor = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+                        best_l = walk_lights<R, MARCH>( sv, ray, !probe, &tl, ctx, cm );
+                        if( !probe && best_l < inf )
+                        {
+                            s_ln[ 0 ][ threadIdx.x ] = tl.exit_nor.x; s_ln[ 1 ][ threadIdx.x ] = tl.exit_nor.y; s_ln[ 2 ][ threadIdx.x ] = tl.exit_nor.z;
+                            s_lo[ 0 ][ threadIdx.x ] = tl.exit_obj; s_lo[ 1 ][ threadIdx.x ] = tl.enter_obj;
+                        }
+                        ws.reset();
+                        cur = ( probe && best_l < inf ) ? WALK_FOUND : walk_root( sv, ray, false, best_l );
+                        if( cur == WALK_END )
+                        {   // no matter in the way: a light hit, or the ray leaves the scene
+                            if( !probe && best_l < inf ) emit_hit( w, ray, best_l, eps, tl, a.w, m.x & 0xFF, xyz( in.tp[ i ] ), m.y, ctx.key );
+                            else add_sample( w, m.y, mul( prm.background, xyz( in.tp[ i ] ) ) * a.w );
+                        }
+                    }
+                }
+                c_cur += n_take;
+            }
+        }
+        if( cur >= 0 )
+        {
+            SceneView<R, SH> sv = sv0; sv.eps = eps;
+            const int nx = walk_step<R, MARCH>( sv, ray, best_l, !probe, cur, ws, ctx, cm );
+            // what a finished ray owes (a hit record, the background) is a hundred instructions of its own: done one ray at
+            // a time they cost more issue slots than the whole walk.  The lane waits with it for the next refill, where the
+            // lanes that finished since the last one do it together.
+            pend = nx == WALK_END;
+            cur = nx;
+        }
+    }
+    warp_count( &w.sc->stats[ ST_REFLECT ], n_refl, lane );
+    warp_count( &w.sc->stats[ ST_CHROMATIC ], n_chro, lane );
+    warp_count( &w.sc->stats[ ST_REFRACT ], n_refr, lane );
+}
+#endif
 
 // scene_s_lum (scene.c:420-667) over the hits of the iteration: emits child rays and diffuse tasks
 template <typename R, bool SH> __global__ void __launch_bounds__( ACN_BLOCK )
@@ -934,7 +1099,8 @@ __device__ __forceinline__ ListWindow list_window( const u64* __restrict__ cum, 
 
 // direct lighting (scene.c:542-581): one lane per (task, light, sample); the shadow rays exist only
 // as (entry, child index) and are regenerated from the task with an O(1) LCG skip-ahead
-template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
+#if defined(ACN_SPEC_SCENE)
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
 k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
           const unsigned int* __restrict__ dl_dir )
 {
@@ -944,7 +1110,7 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     const int chunk = launch_chunk( total >> 5 );
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= total ) return;     // more warps than chunks
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const unsigned long long n_blocks = ( total + 31 ) >> 5;
@@ -1018,9 +1184,149 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     warp_count( &w.sc->stats[ ST_SHADOW ], n_shadow, lane );
 }
 
+#else
+// refill loop (see k_rays): blocks of 32 children are GENERATED by the whole warp (owner search, cone sampling, light test,
+// contribution) and the live ones — direction above the horizon, light met — queue in a ring; idle lanes take them
+// from there and walk the matter root for an occluder.  An unoccluded ray adds its contribution at once.
+#define ACN_RING 64
+template <typename R> struct ShadowRing { R ox[ ACN_RING ], oy[ ACN_RING ], oz[ ACN_RING ], dx[ ACN_RING ], dy[ ACN_RING ], dz[ ACN_RING ], tf[ ACN_RING ], cr[ ACN_RING ], cg[ ACN_RING ], cb[ ACN_RING ]; int smp[ ACN_RING ]; };
+
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
+k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
+          const unsigned int* __restrict__ dl_dir )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    __shared__ ShadowRing<R> rings[ ACN_BLOCK / 32 ];
+    const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
+    if( total == 0 || w.sc->overflow ) return;
+    const int chunk = launch_chunk( total >> 5 );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * 32ull * chunk >= total ) return;     // more warps than chunks
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x );
+    const DParams<R>& prm = w.prm;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = ( 1u << lane ) - 1u;
+    const unsigned long long n_blocks = ( total + 31 ) >> 5;
+    ShadowRing<R>& rg = rings[ threadIdx.x >> 5 ];
+    int head = 0, ring_n = 0;
+    bool input_done = false;
+    unsigned long long b_cur = 0, b_end = 0;
+    unsigned long long n_shadow = 0;
+    HitCtx ctx; ctx.key = 0;
+    // the lane's walk
+    int cur = WALK_END, smp = 0;
+    bool pend = false;
+    Ray<R> ray; ray.p = ray.d = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    R eps = sv0.eps, tfar = R( 0 );
+    V3<R> con = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    for( ;; )
+    {
+        const unsigned int idle = __ballot_sync( ACN_FULL, cur < 0 );
+        if( idle == ACN_FULL || ( __popc( idle ) >= ACN_REFILL_MIN && !( input_done && ring_n == 0 ) ) )
+        {
+            const int n_idle = __popc( idle );
+            if( pend ) { pend = false; add_sample( w, smp, con ); }          // the unoccluded rays since the last refill, together (see k_rays)
+            while( !input_done && ring_n < n_idle )
+            {   // ---- generate the next block of 32 children
+                if( b_cur >= b_end )
+                {
+                    b_cur = warp_fetch( &w.sc->cur_direct, chunk, lane );
+                    b_end = b_cur + chunk < n_blocks ? b_cur + chunk : n_blocks;
+                    if( b_cur >= n_blocks ) { input_done = true; break; }
+                }
+                const unsigned long long blk = b_cur++;
+                const ListWindow lw = list_window( dl_cum, dl_dir, blk, n_entries, lane );
+                const unsigned long long idx = ( blk << 5 ) + lane;
+                const bool live = idx < total;
+                const int j = window_find( lw.incl, live ? idx : ( blk << 5 ) );
+                const unsigned long long prev = __shfl_sync( ACN_FULL, lw.incl, ( j + 31 ) & 31 );
+                bool want = false;
+                Ray<R> out; out.p = out.d = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+                R a = R( 0 ); V3<R> c3 = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); int sample = 0;
+                if( live )
+                {
+                    const unsigned long long r = idx - ( j ? prev : lw.excl0 );
+                    const unsigned int t = dl_slot[ lw.e0 + j ];
+                    const I4 m = in.meta[ t ];
+                    sample = m.x;
+                    const unsigned int nd = ( unsigned int )m.z;
+                    const unsigned int li = ( unsigned int )( r / nd ), jj = ( unsigned int )( r - ( unsigned long long )li * nd );
+                    const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+                    const V3<R> pos = xyz( pi ), nrm = xyz( nc ), prj = xyz( pa );
+                    const DLight<R>& lg = prm.lights[ li ];
+                    const SceneView<R, SH> sv = ray_view( prm, sv0, pos );
+                    V3<R> axis; R cos_rs;
+                    obj_fov( sv, lg.node, pos, &axis, &cos_rs );
+                    const Basis<R> bs = basis_con_z( axis );
+                    const R h = R( 1 ) - cos_rs;                                                 // areal_coverage, vectors.h:362
+                    u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )li * nd + jj );
+                    out.p = pos;
+                    out.d = from_basis( bs, sphere_cap<R>( &rv, h ) );
+                    R wgt = dot( out.d, nrm );
+                    if( wgt > R( 0 ) )
+                    {
+                        n_shadow++;
+                        a = light_hit<R, MARCH>( sv, lg.node, out, ctx, cm );                  // scene.c:564
+                        if( a < Num<R>::inf() )
+                        {
+                            if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, prj );
+                            n_shadow++;
+                            const V3<R> hp = madd( out.p, out.d, a );
+                            const R d2 = sqr( hp - v3<R>( lg.pos[ 0 ], lg.pos[ 1 ], lg.pos[ 2 ] ) );
+                            const R lint = d2 > R( 0 ) ? lg.radiance / d2 : Num<R>::mag();
+                            const R f = lint * wgt * pi.w * ( R( 2 ) * h / ( R )nd );           // scene.c:574,579
+                            c3 = v3<R>( lg.color[ 0 ] * f * tb.x, lg.color[ 1 ] * f * tb.y, lg.color[ 2 ] * f * tb.z );
+                            want = true;
+                        }
+                    }
+                }
+                const unsigned int wm = __ballot_sync( ACN_FULL, want );
+                if( want )
+                {
+                    const int q = ( head + ring_n + __popc( wm & lt ) ) & ( ACN_RING - 1 );
+                    rg.ox[ q ] = out.p.x; rg.oy[ q ] = out.p.y; rg.oz[ q ] = out.p.z;
+                    rg.dx[ q ] = out.d.x; rg.dy[ q ] = out.d.y; rg.dz[ q ] = out.d.z;
+                    rg.tf[ q ] = a; rg.cr[ q ] = c3.x; rg.cg[ q ] = c3.y; rg.cb[ q ] = c3.z; rg.smp[ q ] = sample;
+                }
+                ring_n += __popc( wm );
+                __syncwarp();
+            }
+            // ---- hand out: the r-th idle lane takes the r-th ray of the ring
+            const int n_take = n_idle < ring_n ? n_idle : ring_n;
+            if( n_take > 0 )
+            {
+                const int r = __popc( idle & lt );
+                if( cur < 0 && r < n_take )
+                {
+                    const int q = ( head + r ) & ( ACN_RING - 1 );
+                    ray.p = v3<R>( rg.ox[ q ], rg.oy[ q ], rg.oz[ q ] ); ray.d = v3<R>( rg.dx[ q ], rg.dy[ q ], rg.dz[ q ] );
+                    tfar = rg.tf[ q ]; con = v3<R>( rg.cr[ q ], rg.cg[ q ], rg.cb[ q ] ); smp = rg.smp[ q ];
+                    eps = ray_eps( prm, sv0.eps, ray.p );
+                    SceneView<R, SH> sv = sv0; sv.eps = eps;
+                    cur = walk_root( sv, ray, false, tfar );
+                    if( cur == WALK_END ) add_sample( w, smp, con );
+                }
+                head = ( head + n_take ) & ( ACN_RING - 1 ); ring_n -= n_take;
+                __syncwarp();
+            }
+            else if( idle == ACN_FULL ) break;           // nothing left to generate, nothing queued, nothing in flight
+        }
+        if( cur >= 0 )
+        {   // ---- one record of the shadow test (scene.c:569: the light is seen when nothing lies at or before it)
+            SceneView<R, SH> sv = sv0; sv.eps = eps;
+            const int nx = walk_any_step<R, MARCH, SH, false>( sv, ray, tfar, cur, ctx, cm );
+            pend = nx == WALK_END;
+            cur = nx;
+        }
+    }
+    warp_count( &w.sc->stats[ ST_SHADOW ], n_shadow, lane );
+}
+#endif
+
 // indirect rays (scene.c:584-621): one lane per (task, path sample); the child ray is generated,
 // traced and shaded in place, never stored.
-template <typename R, bool MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_PATH : ACN_MINB_PATH_G )
+#if defined(ACN_SPEC_SCENE)
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_PATH : ACN_MINB_PATH_G )
 k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -1031,7 +1337,7 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     const int chunk = launch_chunk( blk_hi - blk_lo );
     if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * chunk >= blk_hi - blk_lo ) return;   // more warps than chunks
     const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
-    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x, w.prm.stk_levels );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x );
     const DParams<R>& prm = w.prm;
     const int lane = threadIdx.x & 31;
     const int L = prm.n_lights;
@@ -1121,6 +1427,146 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     }
     warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
 }
+
+#else
+// refill loop (see k_rays, k_direct): generated children above the horizon queue in a ring as ( ray, intensity, task, child );
+// what a finished walk needs beyond that (throughput, sample, depth, key of the task) is read again from the task.
+template <typename R> struct PathRing { R ox[ ACN_RING ], oy[ ACN_RING ], oz[ ACN_RING ], dx[ ACN_RING ], dy[ ACN_RING ], dz[ ACN_RING ], ci[ ACN_RING ]; unsigned int t[ ACN_RING ], i[ ACN_RING ]; };
+
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_PATH : ACN_MINB_PATH_G )
+k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
+{
+    extern __shared__ __align__( 32 ) unsigned char smem[];
+    __shared__ PathRing<R> rings[ ACN_BLOCK / 32 ];
+    const unsigned long long blk_lo = w.sc->path_blk_lo, blk_hi = w.sc->path_blk_hi;
+    if( blk_hi <= blk_lo || w.sc->overflow ) return;
+    const unsigned long long c_hi = w.sc->path_c_hi, n_entries = w.sc->path_nt;
+    const int chunk = launch_chunk( blk_hi - blk_lo );
+    if( ( unsigned long long )blockIdx.x * ( ACN_BLOCK / 32 ) * chunk >= blk_hi - blk_lo ) return;   // more warps than chunks
+    const SceneView<R, SH> sv0 = stage_scene<R, SH>( w.prm, smem );
+    const CsgMem<R> cm = csg_mem<R>( smem + ( SH ? w.prm.stage_bytes : 0 ), ACN_BLOCK, threadIdx.x );
+    const DParams<R>& prm = w.prm;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = ( 1u << lane ) - 1u;
+    const int L = prm.n_lights;
+    const unsigned long long n_blocks = blk_hi - blk_lo;
+    const R t_lim = prm.max_path_length;
+    PathRing<R>& rg = rings[ threadIdx.x >> 5 ];
+    int head = 0, ring_n = 0;
+    bool input_done = false;
+    unsigned long long b_cur = 0, b_end = 0;
+    unsigned long long n_path = 0;
+    // the lane's walk
+    int cur = WALK_END;
+    unsigned int tsk = 0, chi = 0;               // task entry, child (bit 31: probe)
+    Ray<R> ray; ray.p = ray.d = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+    R eps = sv0.eps, ci = R( 0 );
+    bool pend = false;
+    HitCtx ctx; ctx.key = 0;
+    WalkT<R> ws; ws.reset();
+    for( ;; )
+    {
+        const unsigned int idle = __ballot_sync( ACN_FULL, cur < 0 );
+        if( idle == ACN_FULL || ( __popc( idle ) >= ACN_REFILL_MIN && !( input_done && ring_n == 0 ) ) )
+        {
+            const int n_idle = __popc( idle );
+            if( pend )
+            {   // ---- the rays that came to their end since the last refill, together (see k_rays)
+                pend = false;
+                const bool probe = ( chi & 0x80000000u ) != 0;
+                SceneView<R, SH> sv = sv0; sv.eps = eps;
+                const I4 m = in.meta[ tsk ];
+                const V3<R> tpm = xyz( in.tpc_b[ tsk ] ) * ( R( 2 ) / ( R )( unsigned int )m.w );   // scene.c:620
+                if( !probe ) walk_trans_finish( sv, ray, ws );
+                if( !probe && ws.min_a < t_lim ) emit_hit( w, ray, ws.min_a, eps, ws.tl, ci, m.y - 10, tpm, m.x, ctx.key );
+                else add_sample( w, m.x, mul( prm.background, tpm ) * ci );                       // scene.c:613-616
+            }
+            while( !input_done && ring_n < n_idle )
+            {   // ---- generate the next block of 32 children
+                if( b_cur >= b_end )
+                {
+                    b_cur = warp_fetch( &w.sc->cur_path, chunk, lane );
+                    b_end = b_cur + chunk < n_blocks ? b_cur + chunk : n_blocks;
+                    if( b_cur >= n_blocks ) { input_done = true; break; }
+                }
+                const unsigned long long blk = blk_lo + b_cur; b_cur++;
+                const ListWindow lw = list_window( in.cum, pdir, blk, n_entries, lane );
+                const unsigned long long idx = ( blk << 5 ) + lane;
+                const bool live = idx < c_hi;
+                const int j = window_find( lw.incl, live ? idx : ( blk << 5 ) );
+                const unsigned long long prev = __shfl_sync( ACN_FULL, lw.incl, ( j + 31 ) & 31 );
+                bool want = false;
+                Ray<R> out; out.p = out.d = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
+                R cint = R( 0 ); unsigned int t = 0, i = 0;
+                if( live )
+                {
+                    t = lw.e0 + j;
+                    i = ( unsigned int )( idx - ( j ? prev : lw.excl0 ) );
+                    const I4 m = in.meta[ t ];
+                    const R4<R> pi = in.pos_id[ t ], nc = in.nrm_ci[ t ], pa = in.prj_a[ t ], tb = in.tpc_b[ t ];
+                    const V3<R> nrm = xyz( nc );
+                    const Basis<R> bs = basis_con_z( nrm );
+                    u64 rv = skip2( prm, in.rv0[ t ], ( unsigned long long )L * ( unsigned int )m.z + i );
+                    out.p = xyz( pi );
+                    out.d = from_basis( bs, sphere_cap<R>( &rv, R( 1 ) ) );
+                    R wgt = dot( out.d, nrm );
+                    if( wgt > R( 0 ) )                                                           // scene.c:600
+                    {
+                        if( tb.w > R( 0 ) ) wgt = oren_nayar( wgt, nc.w, pa.w, tb.w, out.d, nrm, xyz( pa ) );
+                        n_path++;
+                        cint = wgt * pi.w;
+                        if( ( m.y - 10 ) == 0 || cint < prm.min_intensity ) i |= 0x80000000u;    // probe: its shading would return 0
+                        want = true;
+                    }
+                }
+                const unsigned int wm = __ballot_sync( ACN_FULL, want );
+                if( want )
+                {
+                    const int q = ( head + ring_n + __popc( wm & lt ) ) & ( ACN_RING - 1 );
+                    rg.ox[ q ] = out.p.x; rg.oy[ q ] = out.p.y; rg.oz[ q ] = out.p.z;
+                    rg.dx[ q ] = out.d.x; rg.dy[ q ] = out.d.y; rg.dz[ q ] = out.d.z;
+                    rg.ci[ q ] = cint; rg.t[ q ] = t; rg.i[ q ] = i;
+                }
+                ring_n += __popc( wm );
+                __syncwarp();
+            }
+            const int n_take = n_idle < ring_n ? n_idle : ring_n;
+            if( n_take > 0 )
+            {
+                const int r = __popc( idle & lt );
+                if( cur < 0 && r < n_take )
+                {
+                    const int q = ( head + r ) & ( ACN_RING - 1 );
+                    ray.p = v3<R>( rg.ox[ q ], rg.oy[ q ], rg.oz[ q ] ); ray.d = v3<R>( rg.dx[ q ], rg.dy[ q ], rg.dz[ q ] );
+                    ci = rg.ci[ q ]; tsk = rg.t[ q ]; chi = rg.i[ q ];
+                    eps = ray_eps( prm, sv0.eps, ray.p );
+                    ctx.key = mix64( in.key[ tsk ], KEY_PATH0 + ( chi & 0x7FFFFFFFu ) );
+                    ws.reset();
+                    SceneView<R, SH> sv = sv0; sv.eps = eps;
+                    cur = walk_root( sv, ray, false, t_lim );
+                    if( cur == WALK_END )
+                    {   // scene.c:613-616: nothing within max_path_length: background
+                        const I4 m = in.meta[ tsk ];
+                        add_sample( w, m.x, mul( prm.background, xyz( in.tpc_b[ tsk ] ) * ( R( 2 ) / ( R )( unsigned int )m.w ) ) * ci );
+                    }
+                }
+                head = ( head + n_take ) & ( ACN_RING - 1 ); ring_n -= n_take;
+                __syncwarp();
+            }
+            else if( idle == ACN_FULL ) break;
+        }
+        if( cur >= 0 )
+        {
+            const bool probe = ( chi & 0x80000000u ) != 0;
+            SceneView<R, SH> sv = sv0; sv.eps = eps;
+            const int nx = walk_step<R, MARCH>( sv, ray, t_lim, !probe, cur, ws, ctx, cm );
+            pend = nx == WALK_END;
+            cur = nx;
+        }
+    }
+    warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
+}
+#endif
 
 // New tasks of the iteration -> (a) the direct list: one entry per task with >= 1 shadow child,
 // (b) the task stack: tasks that still have path children.  A warp allocates its entries and their

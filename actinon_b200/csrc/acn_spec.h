@@ -337,7 +337,7 @@ struct SpecGen
         for( int e : todo ) emit_program( e );
         p( "// scene_s_trans_hit / compound_s_ray_trans_hit / compound_s_ray_hit (scene.c:362-382, compound.c:215-299) with the element\n"
            "// lists of this scene unrolled; semantics as scene_query (acn_isect.cuh)\n" );
-        p( "template <typename R, bool MARCH, bool SH> __device__ __forceinline__ R spec_scene_query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,\n"
+        p( "template <typename R, int MARCH, bool SH> __device__ __forceinline__ R spec_scene_query( const SceneView<R, SH>& sv, const Ray<R>& ray, const int flags, const R t_far,\n"
            "                                                                                 Trans<R>* trans, HitCtx ctx, const CsgMem<R>& cm )\n{\n" );
         p( "    const R inf = Num<R>::inf();\n    const bool want_trans = ( flags & Q_TRANS ) != 0;\n    const R slack = R( 2 ) * sv.eps;\n" );
         p( "    R best = inf;\n    bool found = false;\n" );

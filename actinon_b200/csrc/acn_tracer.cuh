@@ -103,6 +103,7 @@ template <typename R> struct Tracer : TracerBase
     // device copies of the scene tables
     R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr; CRec<R>* d_crec = nullptr;
     int* d_prog = nullptr; I4* d_prog_ref = nullptr; int* d_parent = nullptr; int n_prog = 0;
+    size_t n_rec = 0; int rec_light = -1, rec_matter = -1;     // traversal records: count, first record of each root list (-1: empty)
     DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
     // queues
@@ -125,7 +126,7 @@ template <typename R> struct Tracer : TracerBase
     void ( *kp_path )( Wave<R>, TaskBuf<R>, const unsigned int* ) = nullptr;
     void ( *kp_direct )( Wave<R>, TaskBuf<R>, const u64*, const unsigned int*, const unsigned int* ) = nullptr;
     void ( *kp_shade )( Wave<R>, HitBuf<R> ) = nullptr;
-    template <bool MARCH, bool SH> void select_kernels()
+    template <int MARCH, bool SH> void select_kernels()
     {
         kp_primary = k_primary<R, MARCH, SH>; kp_rays = k_rays<R, MARCH, SH>; kp_path = k_path<R, MARCH, SH>;
         kp_direct = k_direct<R, MARCH, SH>; kp_shade = k_shade<R, SH>;
@@ -475,11 +476,31 @@ static int first_unswept( const acn_flat_scene* fs, const CsgBuilder& cb )
     return bad;
 }
 
+// number of traversal records: one per element of every child list reached from the two roots (a compound that two
+// lists share is laid out once per reference — the records form a TREE, see ThreadedRecords); capped
+static size_t threaded_record_count( const acn_flat_scene* fs, size_t cap = ( size_t )1 << 26 )
+{
+    size_t n = 0;
+    std::function<void( int, int )> walk = [ & ]( int c, int guard )
+    {
+        const acn_flat_node& cn = fs->nodes[ c ];
+        n += ( size_t )cn.child1;
+        if( n > cap || guard > 64 ) return;
+        for( int i = 0; i < cn.child1; i++ )
+        {
+            const int e = fs->children[ cn.child0 + i ];
+            if( fs->nodes[ e ].kind == ACN_KIND_COMPOUND ) walk( e, guard + 1 );
+        }
+    };
+    walk( fs->light_root, 0 ); walk( fs->matter_root, 0 );
+    return n;
+}
+
 // bytes of the node table as staged into shared memory (layout in Tracer::init)
 template <typename R> static size_t staged_table_bytes( const acn_flat_scene* fs, size_t n_prog )
 {
     const size_t n = ( size_t )fs->n_nodes;
-    return n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + ( size_t )fs->n_children * sizeof( CRec<R> ) + n_prog * sizeof( int );
+    return n * ( sizeof( R4<R> ) * ( 1 + GEO_STRIDE ) + 2 * sizeof( I4 ) + sizeof( int ) ) + threaded_record_count( fs ) * sizeof( CRec<R> ) + n_prog * sizeof( int );
 }
 template <typename R> static bool stages_table( const acn_flat_scene* fs, size_t n_prog )
 {
@@ -654,22 +675,53 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     ACN_CUDA( cudaMemcpy( d_link, link.data(), n * sizeof( I4 ), cudaMemcpyHostToDevice ) );
     ACN_CUDA( cudaMemcpy( d_geo, geo.data(), ( size_t )n * GEO_STRIDE * sizeof( R4<R> ), cudaMemcpyHostToDevice ) );
     if( fs->n_children > 0 ) ACN_CUDA( cudaMemcpy( d_children, fs->children, fs->n_children * sizeof( int ), cudaMemcpyHostToDevice ) );
-    {   // the child lists once more as packed records (cull bound + link word, node index in .w)
-        std::vector<CRec<R>> crec( fs->n_children > 0 ? fs->n_children : 1 );
+    {   // ---- traversal records.  The child lists of the two root compounds as ONE array of packed records
+        // ( cull bound | kind + flags, first record of the child list, SKIP record, node ), threaded: a ray that fails an
+        // element's bound (or is through with a leaf) goes to the element's skip record — its next sibling, or, behind
+        // the last element of a list, whatever follows the list's compound — and a ray that passes a compound's bound goes
+        // to the first record of its list.  The walk is a single index per ray: no stack, no "back to the parent list"
+        // steps, and a traversal can be parked and resumed with four bytes of state (acn_kernels.cuh: refill loops).
+        // Lists are laid out depth-first; a compound referenced from two lists gets two copies of its list.
+        n_rec = threaded_record_count( fs );
+        if( n_rec > ( ( size_t )1 << 26 ) ) { set_error( "flat scene: more than 2^26 traversal records (shared compounds expand into a tree)" ); return ACN_ERR_UNSUPPORTED; }
+        std::vector<CRec<R>> crec( n_rec > 0 ? n_rec : 1 );
         const CullBounds cbnd( fs, !getenv( "ACN_NO_TIGHT_BOUNDS" ) );
-        for( int i = 0; i < fs->n_children; i++ )
+        size_t next_free = 0;
+        std::function<int( int, int, bool )> emit = [ & ]( int compound, int escape, bool top ) -> int
         {
-            const int c = fs->children[ i ];
-            crec[ i ].env = env[ c ]; crec[ i ].link = link[ c ]; crec[ i ].link.w = c;
-            const CullBounds::Rec& b = cbnd.rec[ c ];
-            if( b.mode == CullBounds::KEEP ) continue;
-            crec[ i ].env.x = ( R )b.c[ 0 ]; crec[ i ].env.y = ( R )b.c[ 1 ]; crec[ i ].env.z = ( R )b.c[ 2 ]; crec[ i ].env.w = ( R )b.r;
-            int flags = node_flags( link[ c ] ) & ~F_ENV;
-            flags |= b.mode == CullBounds::SELF ? F_SELF : F_ENV;
-            if( b.env_too ) flags |= F_ENV2;
-            crec[ i ].link.x = node_kind( link[ c ] ) | ( flags << 8 );
-        }
-        if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: traversal records: %d of %d with a tight cull bound, %d spheres held in their record, %d of them test the reference's envelope as well\n", cbnd.n_tight, fs->n_children, cbnd.n_self, cbnd.n_both );
+            const acn_flat_node& cn = fs->nodes[ compound ];
+            if( cn.child1 <= 0 ) return escape;
+            const int base = ( int )next_free;
+            next_free += ( size_t )cn.child1;
+            for( int i = 0; i < cn.child1; i++ )
+            {
+                const int c = fs->children[ cn.child0 + i ];
+                CRec<R>& r = crec[ base + i ];
+                r.env = env[ c ];
+                int flags = node_flags( link[ c ] );
+                const CullBounds::Rec& b = cbnd.rec[ c ];
+                if( b.mode != CullBounds::KEEP )
+                {
+                    r.env.x = ( R )b.c[ 0 ]; r.env.y = ( R )b.c[ 1 ]; r.env.z = ( R )b.c[ 2 ]; r.env.w = ( R )b.r;
+                    flags = ( flags & ~F_ENV ) | ( b.mode == CullBounds::SELF ? F_SELF : F_ENV );
+                    if( b.env_too ) flags |= F_ENV2;
+                }
+                if( top ) flags |= F_TOP;
+                r.link.x = node_kind( link[ c ] ) | ( flags << 8 );
+                r.link.z = i + 1 < cn.child1 ? base + i + 1 : escape;
+                r.link.y = -1;
+                r.link.w = c;
+            }
+            for( int i = 0; i < cn.child1; i++ )
+            {
+                const int c = fs->children[ cn.child0 + i ];
+                if( fs->nodes[ c ].kind == ACN_KIND_COMPOUND ) crec[ base + i ].link.y = emit( c, crec[ base + i ].link.z, false );
+            }
+            return base;
+        };
+        rec_light = emit( fs->light_root, -1, true );
+        rec_matter = emit( fs->matter_root, -1, true );
+        if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: %zu traversal records: %d compounds with a tight cull bound, %d spheres held in their record, %d of both test the reference's envelope as well\n", n_rec, cbnd.n_tight, cbnd.n_self, cbnd.n_both );
         if( ( rc = dev_alloc( &d_crec, crec.size() ) ) ) return rc;
         ACN_CUDA( cudaMemcpy( d_crec, crec.data(), crec.size() * sizeof( CRec<R> ), cudaMemcpyHostToDevice ) );
     }
@@ -757,7 +809,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         }
         SceneView<double> hv; hv.env = henv.data(); hv.geo = hgeo.data(); hv.link = link.data(); hv.children = fs->children;
         hv.prog = nullptr; hv.prog_ref = nullptr; hv.parent = nullptr;
-        hv.eps = eps; hv.light_root = fs->light_root; hv.matter_root = fs->matter_root; hv.seed_mode = 0;
+        hv.eps = eps; hv.light_root = fs->light_root; hv.matter_root = fs->matter_root; hv.seed_mode = 0; hv.rec_light = hv.rec_matter = -1;
         for( int i = 0; i < lroot.child1; i++ )
         {
             const int ln = fs->children[ lroot.child0 + i ];
@@ -802,9 +854,10 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     prm.sv.env = d_env; prm.sv.link = d_link; prm.sv.geo = d_geo; prm.sv.children = d_children; prm.sv.crec = d_crec;
     prm.sv.prog = d_prog; prm.sv.prog_ref = d_prog_ref; prm.sv.parent = d_parent; prm.n_prog = n_prog;
     prm.sv.eps = ( R )eps; prm.sv.light_root = fs->light_root; prm.sv.matter_root = fs->matter_root;
+    prm.sv.rec_light = rec_light; prm.sv.rec_matter = rec_matter;
     prm.sv.seed_mode = opt->seed_mode;
     prm.mats = d_mats; prm.lights = d_lights; prm.n_lights = lroot.child1; prm.n_materials = fs->n_materials;
-    prm.n_nodes = n; prm.n_children = fs->n_children;
+    prm.n_nodes = n; prm.n_children = ( int )n_rec;
     prm.width = p.image_width; prm.height = p.image_height;
     prm.gamma = ( R )p.gamma;
     prm.background = v3<R>( ( R )p.background_color[ 0 ], ( R )p.background_color[ 1 ], ( R )p.background_color[ 2 ] );
@@ -859,24 +912,27 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         prm.off_geo  = ( unsigned int )o; o += ( size_t )n * GEO_STRIDE * sizeof( R4<R> );
         prm.off_link = ( unsigned int )o; o += ( size_t )n * sizeof( I4 );
         prm.off_pref = ( unsigned int )o; o += ( size_t )n * sizeof( I4 );
-        prm.off_crec = ( unsigned int )o; o += ( size_t )fs->n_children * sizeof( CRec<R> );
+        prm.off_crec = ( unsigned int )o; o += n_rec * sizeof( CRec<R> );
         prm.off_par  = ( unsigned int )o; o += ( size_t )n * sizeof( int );
         prm.off_prog = ( unsigned int )o;
     }
     // (f32 only: the FP64 validation instantiations read the tables from global memory)
     prm.stage_bytes = stages_table<R>( fs, ( size_t )n_prog ) ? ( int )( ( table + 31 ) & ~( size_t )31 ) : 0;
+    // kernel instantiation (acn_isect.cuh: elem_hit): 2 = planes, spheres and quadrics only, 1 = full-featured, 0 = lean sweep
+    bool prims_only = !march;
+    for( int i = 0; i < n && prims_only; i++ ) prims_only = fs->nodes[ i ].kind <= ACN_KIND_SQUAROID;
     if constexpr( sizeof( R ) == 4 )
     {
-        if( prm.stage_bytes > 0 ) { if( march ) select_kernels<true, true>(); else select_kernels<false, true>(); }
-        else                      { if( march ) select_kernels<true, false>(); else select_kernels<false, false>(); }
+        if( prm.stage_bytes > 0 ) { if( march ) select_kernels<1, true>(); else if( prims_only ) select_kernels<2, true>(); else select_kernels<0, true>(); }
+        else                      { if( march ) select_kernels<1, false>(); else if( prims_only ) select_kernels<2, false>(); else select_kernels<0, false>(); }
     }
-    else { if( march ) select_kernels<true, false>(); else select_kernels<false, false>(); }
-    {
-        const int dl = compound_depth( fs, fs->light_root, 0 ), dm = compound_depth( fs, fs->matter_root, 0 );
-        prm.stk_levels = ( dl > dm ? dl : dm ) + 1;
+    else { if( march ) select_kernels<1, false>(); else if( prims_only ) select_kernels<2, false>(); else select_kernels<0, false>(); }
+    {   // staged tables, then the per-thread scratch of the CSG event sweep (none for a scene without composite objects)
+        bool any_prog = false;
+        for( size_t i = 0; i < cb.prog_ref.size(); i++ ) any_prog = any_prog || cb.prog_ref[ i ].y > 0;
+        smem_bytes = prm.stage_bytes + ( any_prog ? ( int )csg_mem_bytes<R>( ACN_BLOCK ) : 0 );
     }
-    smem_bytes = prm.stage_bytes + ( int )csg_mem_bytes<R>( ACN_BLOCK, prm.stk_levels );      // staged tables, then the per-thread query scratch
-    if( smem_bytes > 40 * 1024 )
+    if( smem_bytes > 30 * 1024 )
     {
         ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
         ACN_CUDA( cudaFuncSetAttribute( ( const void* )kp_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes ) );
@@ -905,7 +961,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
                 {
                     ok = true;
                     DriverApi& drv = DriverApi::get();
-                    if( smem_bytes > 40 * 1024 )
+                    if( smem_bytes > 30 * 1024 )
                         for( int k = 0; k < SPEC_K_COUNT; k++ )
                             if( drv.FuncSetAttribute( spec->fn[ k ], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_bytes ) != CUDA_SUCCESS ) ok = false;
                     if( !ok ) { spec.reset(); set_error( "scene specialisation: cannot set the shared-memory size of the compiled kernels" ); }
