@@ -521,9 +521,9 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ R scene_que
     // Bounds are culled against the best candidate so far: nothing inside a ball that the ray enters
     // at t_env can be reported closer than t_env - eps, so skipping it when t_env > horizon + 2 eps changes nothing.
     //
-    // The walk follows the threaded traversal records (CRec): one record per iteration and lane, the position is one
-    // index.  It is LOCKSTEP over the lanes that enter the query together: a vote keeps everybody in the loop until the
-    // last lane is through.  (Written as a plain while-loop with `continue`s the lanes drifted apart for good — a lane
+    // The walk follows the threaded traversal records (CRec): one record per iteration, the position of a lane is one
+    // index.  It is LOCKSTEP over the lanes that enter the query together: a warp reduction keeps everybody in the loop
+    // until the last lane is through.  (Written as a plain while-loop with `continue`s the lanes drifted apart for good — a lane
     // whose ray misses a bound went round the loop on its own while its neighbours tested a sphere, and from then on
     // each drift group ran the same instructions at different times.)
     const R inf = Num<R>::inf();
@@ -550,8 +550,18 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ R scene_que
         for( ;; )
         {
             const bool more = !found && cur >= 0;
+            // the records are laid out in pre-order (links point forward): the lanes at the LOWEST record take a step, a lane
+            // that skipped a subtree waits at its next record until the others arrive or pass.  Lanes that meet the same
+            // composite object then run its event sweep side by side (hanging_lamps_in_row: the sweep ran at 2.3 lanes
+            // of 32 when every lane stepped in every iteration and the lanes spread over the records).
+#ifndef ACN_WALK_EVERY_LANE
+            const unsigned int low = __reduce_min_sync( mask, more ? ( unsigned int )cur : 0xFFFFFFFFu );
+            if( low == 0xFFFFFFFFu ) break;
+            if( more && ( unsigned int )cur == low )
+#else
             if( !__any_sync( mask, more ) ) break;
             if( more )
+#endif
             {
                 const CRec<R> rec = sv.crec[ cur ];
                 const I4 lk = rec.link;

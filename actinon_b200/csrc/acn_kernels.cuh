@@ -803,9 +803,7 @@ k_primary( Wave<R> w, const double* __restrict__ xy )
 // explicit rays, read in place from the tops of the two ends of the ray stack: items [0, pad_a) are the take_a newest
 // rays of end A (reflection / chromatic), padded to a whole number of 32-ray groups so that no warp mixes the kinds,
 // items [pad_a, pad_a + take_b) the take_b newest of end B (refraction).  What k_shade spawns afterwards overwrites them.
-#if defined(ACN_SPEC_SCENE)
-template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
-k_rays( Wave<R> w, RayBuf<R> in )
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_rays_groups( const Wave<R>& w, const RayBuf<R>& in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     __shared__ unsigned long long ring_all[ ACN_BLOCK / 32 ][ ACN_PEND ];
@@ -876,7 +874,6 @@ k_rays( Wave<R> w, RayBuf<R> in )
     warp_count( &w.sc->stats[ ST_REFRACT ], n_refr, lane );
 }
 
-#else
 // ---------------------------------------------------------------------------------------------
 // The kernels that WALK the scene (no specialised code for its structure): refill loops.
 // A ray's walk through the threaded traversal records takes anything between one record (it misses the first bound)
@@ -914,8 +911,7 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ R walk_ligh
     return s.min_a;
 }
 
-template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
-k_rays( Wave<R> w, RayBuf<R> in )
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_rays_refill( const Wave<R>& w, const RayBuf<R>& in )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     __shared__ R   s_ln[ 3 ][ ACN_BLOCK ];          // transition of the closest light hit of the lane's ray
@@ -1029,7 +1025,18 @@ k_rays( Wave<R> w, RayBuf<R> in )
     warp_count( &w.sc->stats[ ST_CHROMATIC ], n_chro, lane );
     warp_count( &w.sc->stats[ ST_REFRACT ], n_refr, lane );
 }
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_RAYS : ACN_MINB_RAYS_G )
+k_rays( Wave<R> w, RayBuf<R> in )
+{
+#if defined(ACN_SPEC_SCENE)
+    k_rays_groups<R, MARCH, SH>( w, in );
+#else
+    // scenes of planes, spheres and quadrics walk with refill; where composite objects are met the rays of a group stay together
+    // (they reach the same object in the same iteration and run ONE event sweep program side by side)
+    if constexpr( MARCH == 2 ) k_rays_refill<R, MARCH, SH>( w, in );
+    else k_rays_groups<R, MARCH, SH>( w, in );
 #endif
+}
 
 // scene_s_lum (scene.c:420-667) over the hits of the iteration: emits child rays and diffuse tasks
 template <typename R, bool SH> __global__ void __launch_bounds__( ACN_BLOCK )
@@ -1099,9 +1106,7 @@ __device__ __forceinline__ ListWindow list_window( const u64* __restrict__ cum, 
 
 // direct lighting (scene.c:542-581): one lane per (task, light, sample); the shadow rays exist only
 // as (entry, child index) and are regenerated from the task with an O(1) LCG skip-ahead
-#if defined(ACN_SPEC_SCENE)
-template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
-k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_direct_groups( const Wave<R>& w, const TaskBuf<R>& in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
           const unsigned int* __restrict__ dl_dir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
@@ -1184,19 +1189,19 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     warp_count( &w.sc->stats[ ST_SHADOW ], n_shadow, lane );
 }
 
-#else
 // refill loop (see k_rays): blocks of 32 children are GENERATED by the whole warp (owner search, cone sampling, light test,
 // contribution) and the live ones — direction above the horizon, light met — queue in a ring; idle lanes take them
 // from there and walk the matter root for an occluder.  An unoccluded ray adds its contribution at once.
 #define ACN_RING 64
 template <typename R> struct ShadowRing { R ox[ ACN_RING ], oy[ ACN_RING ], oz[ ACN_RING ], dx[ ACN_RING ], dy[ ACN_RING ], dz[ ACN_RING ], tf[ ACN_RING ], cr[ ACN_RING ], cg[ ACN_RING ], cb[ ACN_RING ]; int smp[ ACN_RING ]; };
 
-template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
-k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_direct_refill( const Wave<R>& w, const TaskBuf<R>& in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
           const unsigned int* __restrict__ dl_dir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     __shared__ ShadowRing<R> rings[ ACN_BLOCK / 32 ];
+    __shared__ R   s_con[ 3 ][ ACN_BLOCK ];         // what the lane's ray adds to its sample when it reaches the light: kept out of the
+    __shared__ int s_smp[ ACN_BLOCK ];              // registers of the walk (written when the ray is taken, read when it is through)
     const unsigned long long n_entries = w.sc->dl_packed >> ACN_TASK_SHIFT, total = w.sc->dl_packed & ACN_TASK_MASK;
     if( total == 0 || w.sc->overflow ) return;
     const int chunk = launch_chunk( total >> 5 );
@@ -1210,29 +1215,33 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
     ShadowRing<R>& rg = rings[ threadIdx.x >> 5 ];
     int head = 0, ring_n = 0;
     bool input_done = false;
-    unsigned long long b_cur = 0, b_end = 0;
-    unsigned long long n_shadow = 0;
+    unsigned int b_cur = 0, b_end = 0;          // blocks of the list: < 2^32 (the list holds < 2^38 children)
+    unsigned int n_shadow = 0;
     HitCtx ctx; ctx.key = 0;
     // the lane's walk
-    int cur = WALK_END, smp = 0;
+    int cur = WALK_END;
     bool pend = false;
     Ray<R> ray; ray.p = ray.d = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
     R eps = sv0.eps, tfar = R( 0 );
-    V3<R> con = v3<R>( R( 0 ), R( 0 ), R( 0 ) );
     for( ;; )
     {
         const unsigned int idle = __ballot_sync( ACN_FULL, cur < 0 );
         if( idle == ACN_FULL || ( __popc( idle ) >= ACN_REFILL_MIN && !( input_done && ring_n == 0 ) ) )
         {
             const int n_idle = __popc( idle );
-            if( pend ) { pend = false; add_sample( w, smp, con ); }          // the unoccluded rays since the last refill, together (see k_rays)
+            if( pend )
+            {   // the unoccluded rays since the last refill, together (see k_rays)
+                pend = false;
+                add_sample( w, s_smp[ threadIdx.x ], v3<R>( s_con[ 0 ][ threadIdx.x ], s_con[ 1 ][ threadIdx.x ], s_con[ 2 ][ threadIdx.x ] ) );
+            }
             while( !input_done && ring_n < n_idle )
             {   // ---- generate the next block of 32 children
                 if( b_cur >= b_end )
                 {
-                    b_cur = warp_fetch( &w.sc->cur_direct, chunk, lane );
-                    b_end = b_cur + chunk < n_blocks ? b_cur + chunk : n_blocks;
-                    if( b_cur >= n_blocks ) { input_done = true; break; }
+                    const unsigned long long b0 = warp_fetch( &w.sc->cur_direct, chunk, lane );
+                    if( b0 >= n_blocks ) { input_done = true; break; }
+                    b_cur = ( unsigned int )b0;
+                    b_end = b0 + chunk < n_blocks ? ( unsigned int )( b0 + chunk ) : ( unsigned int )n_blocks;
                 }
                 const unsigned long long blk = b_cur++;
                 const ListWindow lw = list_window( dl_cum, dl_dir, blk, n_entries, lane );
@@ -1300,11 +1309,12 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
                 {
                     const int q = ( head + r ) & ( ACN_RING - 1 );
                     ray.p = v3<R>( rg.ox[ q ], rg.oy[ q ], rg.oz[ q ] ); ray.d = v3<R>( rg.dx[ q ], rg.dy[ q ], rg.dz[ q ] );
-                    tfar = rg.tf[ q ]; con = v3<R>( rg.cr[ q ], rg.cg[ q ], rg.cb[ q ] ); smp = rg.smp[ q ];
+                    tfar = rg.tf[ q ];
+                    s_con[ 0 ][ threadIdx.x ] = rg.cr[ q ]; s_con[ 1 ][ threadIdx.x ] = rg.cg[ q ]; s_con[ 2 ][ threadIdx.x ] = rg.cb[ q ]; s_smp[ threadIdx.x ] = rg.smp[ q ];
                     eps = ray_eps( prm, sv0.eps, ray.p );
                     SceneView<R, SH> sv = sv0; sv.eps = eps;
                     cur = walk_root( sv, ray, false, tfar );
-                    if( cur == WALK_END ) add_sample( w, smp, con );
+                    pend = cur == WALK_END;                  // no matter at all: settled at the next refill
                 }
                 head = ( head + n_take ) & ( ACN_RING - 1 ); ring_n -= n_take;
                 __syncwarp();
@@ -1319,15 +1329,25 @@ k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsign
             cur = nx;
         }
     }
-    warp_count( &w.sc->stats[ ST_SHADOW ], n_shadow, lane );
+    warp_count( &w.sc->stats[ ST_SHADOW ], ( unsigned long long )n_shadow, lane );
 }
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
+k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
+          const unsigned int* __restrict__ dl_dir )
+{
+#if defined(ACN_SPEC_SCENE)
+    k_direct_groups<R, MARCH, SH>( w, in, dl_cum, dl_slot, dl_dir );
+#else
+    // scenes of planes, spheres and quadrics walk with refill; where composite objects are met the rays of a group stay together
+    // (they reach the same object in the same iteration and run ONE event sweep program side by side)
+    if constexpr( MARCH == 2 ) k_direct_refill<R, MARCH, SH>( w, in, dl_cum, dl_slot, dl_dir );
+    else k_direct_groups<R, MARCH, SH>( w, in, dl_cum, dl_slot, dl_dir );
 #endif
+}
 
 // indirect rays (scene.c:584-621): one lane per (task, path sample); the child ray is generated,
 // traced and shaded in place, never stored.
-#if defined(ACN_SPEC_SCENE)
-template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_PATH : ACN_MINB_PATH_G )
-k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_path_groups( const Wave<R>& w, const TaskBuf<R>& in, const unsigned int* __restrict__ pdir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     __shared__ unsigned long long ring_all[ ACN_BLOCK / 32 ][ ACN_PEND ];
@@ -1428,13 +1448,11 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
 }
 
-#else
 // refill loop (see k_rays, k_direct): generated children above the horizon queue in a ring as ( ray, intensity, task, child );
 // what a finished walk needs beyond that (throughput, sample, depth, key of the task) is read again from the task.
 template <typename R> struct PathRing { R ox[ ACN_RING ], oy[ ACN_RING ], oz[ ACN_RING ], dx[ ACN_RING ], dy[ ACN_RING ], dz[ ACN_RING ], ci[ ACN_RING ]; unsigned int t[ ACN_RING ], i[ ACN_RING ]; };
 
-template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_PATH : ACN_MINB_PATH_G )
-k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
+template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_path_refill( const Wave<R>& w, const TaskBuf<R>& in, const unsigned int* __restrict__ pdir )
 {
     extern __shared__ __align__( 32 ) unsigned char smem[];
     __shared__ PathRing<R> rings[ ACN_BLOCK / 32 ];
@@ -1566,7 +1584,18 @@ k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
     }
     warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
 }
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_PATH : ACN_MINB_PATH_G )
+k_path( Wave<R> w, TaskBuf<R> in, const unsigned int* __restrict__ pdir )
+{
+#if defined(ACN_SPEC_SCENE)
+    k_path_groups<R, MARCH, SH>( w, in, pdir );
+#else
+    // scenes of planes, spheres and quadrics walk with refill; where composite objects are met the rays of a group stay together
+    // (they reach the same object in the same iteration and run ONE event sweep program side by side)
+    if constexpr( MARCH == 2 ) k_path_refill<R, MARCH, SH>( w, in, pdir );
+    else k_path_groups<R, MARCH, SH>( w, in, pdir );
 #endif
+}
 
 // New tasks of the iteration -> (a) the direct list: one entry per task with >= 1 shadow child,
 // (b) the task stack: tasks that still have path children.  A warp allocates its entries and their

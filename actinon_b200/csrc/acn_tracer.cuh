@@ -681,22 +681,30 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         // the last element of a list, whatever follows the list's compound — and a ray that passes a compound's bound goes
         // to the first record of its list.  The walk is a single index per ray: no stack, no "back to the parent list"
         // steps, and a traversal can be parked and resumed with four bytes of state (acn_kernels.cuh: refill loops).
-        // Lists are laid out depth-first; a compound referenced from two lists gets two copies of its list.
+        // A compound referenced from two lists gets two copies of its list.
         n_rec = threaded_record_count( fs );
         if( n_rec > ( ( size_t )1 << 26 ) ) { set_error( "flat scene: more than 2^26 traversal records (shared compounds expand into a tree)" ); return ACN_ERR_UNSUPPORTED; }
         std::vector<CRec<R>> crec( n_rec > 0 ? n_rec : 1 );
         const CullBounds cbnd( fs, !getenv( "ACN_NO_TIGHT_BOUNDS" ) );
+        // PRE-ORDER: an element's record is followed by the records of everything it contains, so first-child and skip
+        // links both point FORWARD.  The lockstep walk of a warp (acn_isect.cuh: scene_query) relies on that: it always
+        // advances the lanes at the lowest record, which keeps lanes that skipped a subtree waiting for the others at the
+        // next common record instead of running ahead through different objects.
         size_t next_free = 0;
-        std::function<int( int, int, bool )> emit = [ & ]( int compound, int escape, bool top ) -> int
-        {
+        const int SAME_AS_SKIP = -4;
+        std::function<int( int, bool, std::vector<int>& )> emit = [ & ]( int compound, bool top, std::vector<int>& open ) -> int
+        {   // returns the first record of the list (-1: empty); `open` collects the records whose skip is the escape of this list
             const acn_flat_node& cn = fs->nodes[ compound ];
-            if( cn.child1 <= 0 ) return escape;
-            const int base = ( int )next_free;
-            next_free += ( size_t )cn.child1;
+            int first = -1;
+            std::vector<int> wait;              // records whose skip is the next record of this list
             for( int i = 0; i < cn.child1; i++ )
             {
                 const int c = fs->children[ cn.child0 + i ];
-                CRec<R>& r = crec[ base + i ];
+                const int idx = ( int )next_free++;
+                for( int r : wait ) crec[ r ].link.z = idx;
+                wait.clear();
+                if( first < 0 ) first = idx;
+                CRec<R>& r = crec[ idx ];
                 r.env = env[ c ];
                 int flags = node_flags( link[ c ] );
                 const CullBounds::Rec& b = cbnd.rec[ c ];
@@ -708,19 +716,28 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
                 }
                 if( top ) flags |= F_TOP;
                 r.link.x = node_kind( link[ c ] ) | ( flags << 8 );
-                r.link.z = i + 1 < cn.child1 ? base + i + 1 : escape;
-                r.link.y = -1;
-                r.link.w = c;
+                r.link.y = -1; r.link.z = -1; r.link.w = c;
+                wait.push_back( idx );
+                if( fs->nodes[ c ].kind == ACN_KIND_COMPOUND )
+                {
+                    std::vector<int> sub;
+                    const int f = emit( c, false, sub );
+                    crec[ idx ].link.y = f >= 0 ? f : SAME_AS_SKIP;
+                    wait.insert( wait.end(), sub.begin(), sub.end() );
+                }
             }
-            for( int i = 0; i < cn.child1; i++ )
-            {
-                const int c = fs->children[ cn.child0 + i ];
-                if( fs->nodes[ c ].kind == ACN_KIND_COMPOUND ) crec[ base + i ].link.y = emit( c, crec[ base + i ].link.z, false );
-            }
-            return base;
+            open.insert( open.end(), wait.begin(), wait.end() );
+            return first;
         };
-        rec_light = emit( fs->light_root, -1, true );
-        rec_matter = emit( fs->matter_root, -1, true );
+        {
+            std::vector<int> open;
+            rec_light = emit( fs->light_root, true, open );
+            for( int r : open ) crec[ r ].link.z = -1;
+            open.clear();
+            rec_matter = emit( fs->matter_root, true, open );
+            for( int r : open ) crec[ r ].link.z = -1;
+            for( size_t i = 0; i < next_free; i++ ) if( crec[ i ].link.y == SAME_AS_SKIP ) crec[ i ].link.y = crec[ i ].link.z;
+        }
         if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: %zu traversal records: %d compounds with a tight cull bound, %d spheres held in their record, %d of both test the reference's envelope as well\n", n_rec, cbnd.n_tight, cbnd.n_self, cbnd.n_both );
         if( ( rc = dev_alloc( &d_crec, crec.size() ) ) ) return rc;
         ACN_CUDA( cudaMemcpy( d_crec, crec.data(), crec.size() * sizeof( CRec<R> ), cudaMemcpyHostToDevice ) );
