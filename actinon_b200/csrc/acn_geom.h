@@ -40,6 +40,7 @@ enum { GEO_STRIDE = 5 };
 enum { SEED_POSITION_HASH = 0, SEED_INDEX_KEYED = 1 };
 enum { CSG_MAX_STEPS = 512, COMPOUND_STACK = 16 };
 enum { CSG_LEAF = 0, CSG_NEG = 1, CSG_AND = 2, CSG_OR = 3, CSG_CLIP = 4, CSG_ENV = 5, CSG_RUN = 6, CSG_MEMBER = 7, CSG_MEMBER_NEG = 8, CSG_MORE = 9, CSG_XFORM = 10, CSG_XEND = 11 };   // word = op | arg << 4, see acn_isect.cuh
+enum { E_TAB = 0, E_VAR = 1, E_CLIP = 2, E_NEG = 3, E_AND = 4, E_OR = 5 };      // words of an evaluation program (acn_tracer.cuh: build_eval_program)
 enum { CSG_E = 16, CSG_VIRTUAL = 255, CSG_MAX_VARS = 64, CSG_TABLE_VARS = 12 };   // crossings kept per ray, id of envelope crossings, variable limits
 
 // A scene table: element i by value.  SH = false: a pointer (device global memory, or host memory in scene

@@ -179,10 +179,39 @@ template <bool DIST, typename R, bool SH> __device__ __forceinline__ V3<R> leaf_
 }
 
 // state of the solid for a variable assignment: truth table, or the postfix program on a bit stack
-template <typename R, bool SH> __device__ __forceinline__ int csg_state( const SceneView<R, SH>& sv, const I4& pr, unsigned long long vars )
+// dead: the CLIP variables of the sub-envelopes the ray misses altogether (pass 1 of csg_eval).  Such a subtree is 0 whatever
+// happens along the ray (objects.c:264), so the interpreter pushes a 0 and jumps over its words: a lamp of sixty butted
+// pieces, of which a ray meets the envelopes of two, costs the words of two pieces per evaluation instead of all of them
+// (hanging_lamps_in_row: the interpreter was 55 % of k_direct's instructions).
+template <typename R, bool SH> __device__ __forceinline__ int csg_state( const SceneView<R, SH>& sv, const I4& pr, unsigned long long vars, unsigned long long dead = 0ull )
 {
     if( pr.z >= 0 ) return ( sv.prog[ pr.z + ( int )( vars >> 5 ) ] >> ( ( unsigned int )vars & 31u ) ) & 1;
     unsigned int stk = 0;
+    if( pr.z <= -2 )
+    {   // evaluation program: truth tables over stretches of consecutive variables, joined by the operators of the chains they
+        // were cut from (acn_tracer.cuh: build_eval_program)
+        const int at = -2 - pr.z;
+        const int end = at + 1 + sv.prog[ at ];
+        #pragma unroll 1
+        for( int pc = at + 1; pc < end; pc++ )
+        {
+            const int ins = sv.prog[ pc ];
+            const int op = ins & 15;
+            if( op == E_TAB )
+            {
+                const int nv = ( ins >> 4 ) & 15, v0 = ( ins >> 8 ) & 63;
+                const unsigned int idx = ( unsigned int )( vars >> v0 ) & ( ( 1u << nv ) - 1u );
+                const int off = sv.prog[ ++pc ];
+                stk = ( stk << 1 ) | ( ( ( unsigned int )sv.prog[ off + ( int )( idx >> 5 ) ] >> ( idx & 31u ) ) & 1u );
+            }
+            else if( op == E_VAR )  stk = ( stk << 1 ) | ( unsigned int )( ( vars >> ( ins >> 4 ) ) & 1ull );
+            else if( op == E_CLIP ) stk &= ~1u | ( unsigned int )( ( vars >> ( ins >> 4 ) ) & 1ull );
+            else if( op == E_NEG )  stk ^= 1u;
+            else if( op == E_AND )  { const unsigned int t = stk & 1u; stk >>= 1; stk &= t | ~1u; }
+            else                    { const unsigned int t = stk & 1u; stk >>= 1; stk |= t; }
+        }
+        return ( int )( stk & 1u );
+    }
     int v = 0;
     #pragma unroll 1
     for( int pc = pr.x; pc < pr.x + pr.y; pc++ )
@@ -195,7 +224,12 @@ template <typename R, bool SH> __device__ __forceinline__ int csg_state( const S
         else if( op == CSG_NEG )  stk ^= 1u;
         else if( op == CSG_AND )  { const unsigned int t = stk & 1u; stk >>= 1; stk &= t | ~1u; }
         else if( op == CSG_OR )   { const unsigned int t = stk & 1u; stk >>= 1; stk |= t; }
-        else if( op == CSG_ENV ) pc++;                   // a skipped subtree is 0 through its CLIP variable; CSG_MORE: no effect
+        else if( op == CSG_ENV )
+        {   // next word: words up to and including the subtree's CLIP | its variables << 16 (the CLIP variable is the last of them)
+            const int w2 = sv.prog[ ++pc ];
+            const int nvs = w2 >> 16;
+            if( ( dead >> ( v + nvs - 1 ) ) & 1ull ) { stk <<= 1; v += nvs; pc += w2 & 0xFFFF; }
+        }                                                // CSG_MORE: no effect
     }
     return ( int )( stk & 1u );
 }
@@ -283,7 +317,7 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
     int s = -1;                                 // state of the solid before the next crossing (-1: not yet evaluated)
     for( int round = 0; round < 16; round++ )
     {
-        unsigned long long vars = 0;
+        unsigned long long vars = 0, dead = 0;
         int nv = 0, ne = 0;
         bool dropped = false;
         R tmin0 = inf; int kmin0 = -1;              // smallest crossing appended so far (-1: unknown, scan)
@@ -359,7 +393,7 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
                     const R4<R> e = sv.env[ n ];
                     c = sphere_events( xyz( e ), e.w, DIST ? rc : ray, &s0, &t0, &t1 );
                     if( DIST ) { t0 *= fac; t1 *= fac; }
-                    if( c == 0 ) { s0 = 0; skip_to = sub_end; }         // objects.c:264: the ray misses the envelope
+                    if( c == 0 ) { s0 = 0; skip_to = sub_end; dead |= 1ull << var; }     // objects.c:264: the ray misses the envelope
                 }
                 if( !__any_sync( __activemask(), pc + 1 >= skip_to ) ) { nv += w2 >> 16; pc = sub_end - 1; }
             }
@@ -417,13 +451,13 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
                 cm.t[ kmin * cm.stride ] = inf;
                 const unsigned long long bit = 1ull << ( iv >> 8 );
                 const bool first = !( tmin < t_group + sv.eps );
-                if( first ) { vars_pre = vars; t_group = tmin; s_pre = s_last >= 0 ? s_last : csg_state( sv, pr, vars_pre ); }
+                if( first ) { vars_pre = vars; t_group = tmin; s_pre = s_last >= 0 ? s_last : csg_state( sv, pr, vars_pre, dead ); }
                 vars ^= bit;
                 tcur = tmin; id = ( int )( iv & 255u );
                 s_last = -1;
                 if( id != CSG_VIRTUAL )
                 {
-                    const int s1 = csg_state( sv, pr, vars_pre ^ bit );
+                    const int s1 = csg_state( sv, pr, vars_pre ^ bit, dead );
                     if( s1 != s_pre ) { hit = true; break; }
                     if( first ) s_last = s1;            // vars == vars_pre ^ bit
                 }
@@ -433,7 +467,7 @@ template <bool DIST, typename R, bool SH> __device__ ACN_CSG_INLINE R csg_eval( 
         {
             for( ;; )
             {
-                const int s2 = csg_state( sv, pr, vars );
+                const int s2 = csg_state( sv, pr, vars, dead );
                 if( s >= 0 && s2 != s && id != CSG_VIRTUAL ) { hit = true; break; }
                 s = s2;
                 int kmin = kmin0; R tmin = tmin0;

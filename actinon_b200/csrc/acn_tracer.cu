@@ -134,6 +134,7 @@ int acn_tracer_create( const acn_flat_scene* scene, const acn_options* opt, acn_
     if( opt ) o = *opt; else acn_options_default( &o );
     int rc = validate_flat_scene( scene );
     if( rc ) return rc;
+    if( getenv( "ACN_DUMP_PROGRAMS" ) ) dump_programs( scene );
     int nd = acn_device_count();
     if( nd < 0 ) return nd;
     int dev = o.device;

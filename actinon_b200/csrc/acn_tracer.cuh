@@ -378,6 +378,126 @@ struct CsgBuilder
         else if( nd.kind == ACN_KIND_NEG || nd.kind == ACN_KIND_SCALE ) { parent[ nd.child0 ] = n; set_parents( nd.child0, guard + 1 ); }
     }
 
+    // ---- evaluation programs for functions of more than CSG_TABLE_VARS variables.
+    // The interpreter of the full program costs ~12 instructions per word and is called for every crossing of a ray: the five
+    // big objects of a hanging lamp (17 - 35 variables, 42 - 108 words) made it 55 % of k_direct's instructions.  Their
+    // functions are chains — unions of butted pieces, a body minus twenty drill holes — and a chain of one operator can be
+    // cut anywhere: every stretch of operands with <= CSG_TABLE_VARS variables in all becomes ONE truth table over its
+    // (consecutive) variables, and what is left of the program is a handful of table lookups joined by the chain's operator.
+    // Words: E_TAB | n << 4 | v0 << 8, table offset;  E_VAR | v << 4;  E_CLIP | v << 4;  E_NEG;  E_AND;  E_OR.
+    struct TNode { int kind = 0, var = 0, v0 = 0, nv = 0; std::vector<int> ch; };     // kind: 0 variable, 1 not, 2 and, 3 or
+    std::vector<TNode> tn;
+    int tn_var( int v ) { TNode t; t.kind = 0; t.var = v; t.v0 = v; t.nv = 1; tn.push_back( t ); return ( int )tn.size() - 1; }
+    int tn_op( int kind, int a, int b )
+    {
+        if( tn[ a ].kind == kind ) { tn[ a ].ch.push_back( b ); tn[ a ].nv += tn[ b ].nv; return a; }      // a op b op c: one chain
+        TNode t; t.kind = kind; t.ch = { a, b }; t.v0 = tn[ a ].v0; t.nv = tn[ a ].nv + tn[ b ].nv; tn.push_back( t ); return ( int )tn.size() - 1;
+    }
+    int tn_eval( int n, unsigned long long vars ) const
+    {
+        const TNode& t = tn[ n ];
+        if( t.kind == 0 ) return ( int )( ( vars >> t.var ) & 1ull );
+        if( t.kind == 1 ) return !tn_eval( t.ch[ 0 ], vars );
+        for( int c : t.ch ) { const int v = tn_eval( c, vars ); if( t.kind == 2 ? !v : v ) return t.kind == 2 ? 0 : 1; }
+        return t.kind == 2 ? 1 : 0;
+    }
+    // the expression tree of a program (same stack discipline as eval)
+    int parse_tree( size_t start, size_t len )
+    {
+        tn.clear();
+        std::vector<int> stk;
+        int v = 0;
+        for( size_t pc = start; pc < start + len; pc++ )
+        {
+            const int ins = prog[ pc ], op = ins & 15;
+            if( op == CSG_LEAF ) stk.push_back( tn_var( v++ ) );
+            else if( op == CSG_RUN ) { stk.push_back( tn_var( v++ ) ); pc += ( size_t )( ins >> 4 ); }
+            else if( op == CSG_CLIP ) { const int a = stk.back(); stk.pop_back(); TNode t; t.kind = 2; t.ch = { a, tn_var( v++ ) }; t.v0 = tn[ a ].v0; t.nv = tn[ a ].nv + 1; tn.push_back( t ); stk.push_back( ( int )tn.size() - 1 ); }
+            else if( op == CSG_NEG ) { const int a = stk.back(); stk.pop_back(); TNode t; t.kind = 1; t.ch = { a }; t.v0 = tn[ a ].v0; t.nv = tn[ a ].nv; tn.push_back( t ); stk.push_back( ( int )tn.size() - 1 ); }
+            else if( op == CSG_AND || op == CSG_OR ) { const int b = stk.back(); stk.pop_back(); const int a = stk.back(); stk.pop_back(); stk.push_back( tn_op( op == CSG_AND ? 2 : 3, a, b ) ); }
+            else if( op == CSG_ENV ) pc++;
+        }
+        return stk.size() == 1 ? stk[ 0 ] : -1;
+    }
+    void pack_table( int kind, const std::vector<int>& members, std::vector<int>& code, std::vector<std::pair<size_t, std::vector<int>>>& tables )
+    {   // one truth table over the consecutive variables of `members`, joined by `kind`
+        const int v0 = tn[ members.front() ].v0;
+        int nv = 0; for( int m : members ) nv += tn[ m ].nv;
+        if( members.size() == 1 && tn[ members[ 0 ] ].kind == 0 ) { code.push_back( E_VAR | ( v0 << 4 ) ); return; }
+        const size_t rows = ( size_t )1 << nv;
+        std::vector<int> tab( ( rows + 31 ) / 32, 0 );
+        for( size_t a = 0; a < rows; a++ )
+        {
+            const unsigned long long vars = ( unsigned long long )a << v0;
+            int r = kind == 2 ? 1 : 0;
+            for( int m : members ) { const int x = tn_eval( m, vars ); if( kind == 2 ) r &= x; else r |= x; }
+            if( r ) tab[ a >> 5 ] |= ( int )( 1u << ( a & 31 ) );
+        }
+        code.push_back( E_TAB | ( nv << 4 ) | ( v0 << 8 ) );
+        tables.push_back( { code.size(), tab } );
+        code.push_back( 0 );                                    // table offset, patched when the tables are appended
+    }
+    void pack( int n, std::vector<int>& code, std::vector<std::pair<size_t, std::vector<int>>>& tables )
+    {
+        const TNode& t = tn[ n ];
+        if( t.nv <= CSG_TABLE_VARS ) { pack_table( 3, { n }, code, tables ); return; }
+        if( t.kind == 1 ) { pack( t.ch[ 0 ], code, tables ); code.push_back( E_NEG ); return; }
+        std::vector<int> bin; int bin_nv = 0, items = 0;
+        auto flush = [ & ]() { if( bin.empty() ) return; pack_table( t.kind, bin, code, tables ); if( items++ > 0 ) code.push_back( t.kind == 2 ? E_AND : E_OR ); bin.clear(); bin_nv = 0; };
+        for( int c : t.ch )
+        {
+            if( tn[ c ].nv > CSG_TABLE_VARS ) { flush(); pack( c, code, tables ); if( items++ > 0 ) code.push_back( t.kind == 2 ? E_AND : E_OR ); continue; }
+            if( bin_nv + tn[ c ].nv > CSG_TABLE_VARS ) flush();
+            bin.push_back( c ); bin_nv += tn[ c ].nv;
+        }
+        flush();
+    }
+    // appends the evaluation program of [ start, start + len ) to prog; returns its offset (first word: number of words) or -1
+    int build_eval_program( size_t start, size_t len )
+    {
+        const int root = parse_tree( start, len );
+        if( root < 0 ) return -1;
+        std::vector<int> code;
+        std::vector<std::pair<size_t, std::vector<int>>> tables;
+        pack( root, code, tables );
+        const int at = ( int )prog.size();
+        prog.push_back( ( int )code.size() );
+        prog.insert( prog.end(), code.begin(), code.end() );
+        for( auto& tb : tables ) { prog[ ( size_t )at + 1 + tb.first ] = ( int )prog.size(); prog.insert( prog.end(), tb.second.begin(), tb.second.end() ); }
+        // the packed function must be the function of the program: checked on random assignments (and on all of a small one)
+        const int nv = tn[ root ].nv;
+        unsigned long long x = 0x9E3779B97F4A7C15ull;
+        for( int k = 0; k < 4096; k++ )
+        {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            const unsigned long long vars = nv >= 64 ? x : ( x & ( ( 1ull << nv ) - 1ull ) );
+            if( eval_packed( at, vars ) != eval( start, len, vars ) ) { prog.resize( at ); return -1; }
+        }
+        return at;
+    }
+    int eval_packed( int at, unsigned long long vars ) const           // host mirror of the device interpreter (acn_isect.cuh: csg_state)
+    {
+        unsigned int stk = 0;
+        const int n = prog[ at ];
+        for( int pc = at + 1; pc < at + 1 + n; pc++ )
+        {
+            const int ins = prog[ pc ], op = ins & 15;
+            if( op == E_TAB )
+            {
+                const int nv = ( ins >> 4 ) & 15, v0 = ( ins >> 8 ) & 63;
+                const unsigned int idx = ( unsigned int )( ( vars >> v0 ) & ( ( 1ull << nv ) - 1ull ) );
+                const int off = prog[ ++pc ];
+                stk = ( stk << 1 ) | ( ( ( unsigned int )prog[ off + ( int )( idx >> 5 ) ] >> ( idx & 31u ) ) & 1u );
+            }
+            else if( op == E_VAR )  stk = ( stk << 1 ) | ( unsigned int )( ( vars >> ( ins >> 4 ) ) & 1ull );
+            else if( op == E_CLIP ) stk &= ~1u | ( unsigned int )( ( vars >> ( ins >> 4 ) ) & 1ull );
+            else if( op == E_NEG )  stk ^= 1u;
+            else if( op == E_AND )  { const unsigned int t = stk & 1u; stk >>= 1; stk &= t | ~1u; }
+            else if( op == E_OR )   { const unsigned int t = stk & 1u; stk >>= 1; stk |= t; }
+        }
+        return ( int )( stk & 1u );
+    }
+
     void visit_compound( int c, int guard, bool enable )
     {
         if( guard > 64 ) return;
@@ -408,6 +528,11 @@ struct CsgBuilder
                         for( size_t a = 0; a < rows; a++ ) if( eval( mark, len, a ) ) tab[ a >> 5 ] |= ( int )( 1u << ( a & 31 ) );
                         prog.insert( prog.end(), tab.begin(), tab.end() );
                     }
+                    else if( !getenv( "ACN_NO_PACKED_EVAL" ) )
+                    {
+                        const int at = build_eval_program( mark, len );
+                        if( at >= 0 ) r.z = -2 - at;             // z <= -2: evaluation program at prog[ -z - 2 ]
+                    }
                     prog_ref[ n ] = r;
                     if( coincident_leaves( n ) ) has_coincident = true;
                 }
@@ -432,6 +557,29 @@ struct CsgBuilder
         if( prog.empty() ) prog.push_back( 0 );
     }
 };
+
+// diagnostics (no device needed): variables / words of every event-sweep program of a scene
+static void dump_programs( const acn_flat_scene* fs )
+{
+    CsgBuilder d; d.build( fs, true );
+    for( int i = 0; i < fs->n_nodes; i++ )
+        if( d.prog_ref[ i ].y > 0 )
+        {
+            fprintf( stderr, "acn: program of node %d: %d variables, %d words, %s", i, d.prog_ref[ i ].w, d.prog_ref[ i ].y, d.prog_ref[ i ].z >= 0 ? "table\n" : d.prog_ref[ i ].z == -1 ? "interpreted\n" : "packed: " );
+            if( d.prog_ref[ i ].z <= -2 ) fprintf( stderr, "%d evaluation words\n", d.prog[ -2 - d.prog_ref[ i ].z ] );
+            if( d.prog_ref[ i ].z == -1 && atoi( getenv( "ACN_DUMP_PROGRAMS" ) ) > 1 )
+            {
+                static const char* nm[] = { "LEAF", "NEG", "AND", "OR", "CLIP", "ENV", "RUN", "MEMBER", "MEMBER_NEG", "MORE", "XFORM", "XEND" };
+                for( int pc = d.prog_ref[ i ].x; pc < d.prog_ref[ i ].x + d.prog_ref[ i ].y; pc++ )
+                {
+                    const int ins = d.prog[ pc ], op = ins & 15;
+                    fprintf( stderr, " %s:%d", op < 12 ? nm[ op ] : "?", ins >> 4 );
+                    if( op == CSG_ENV ) { pc++; fprintf( stderr, "(skip %d vars %d)", d.prog[ pc ] & 0xFFFF, d.prog[ pc ] >> 16 ); }
+                }
+                fprintf( stderr, "\n" );
+            }
+        }
+}
 
 int validate_flat_scene( const acn_flat_scene* fs );   // acn_tracer.cu
 
@@ -620,7 +768,6 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     const acn_flat_params& p = fs->params;
     width = p.image_width; height = p.image_height;
     const int n = fs->n_nodes;
-
     // ---- pack the node table
     std::vector<R4<R>> env( n ), geo( ( size_t )n * GEO_STRIDE );
     std::vector<I4> link( n );
