@@ -801,6 +801,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     {
         eps = 1E-6;
         if( sizeof( R ) == 4 ) eps_rel = 16.0 * 1.1920929E-7;
+        if( sizeof( R ) == 4 && getenv( "ACN_EPS_ULPS" ) ) eps_rel = atof( getenv( "ACN_EPS_ULPS" ) ) * 1.1920929E-7;     // experiments (tools/c1_probe.py)
     }
     ( void )scale;
 
