@@ -611,7 +611,7 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ R scene_que
                 // rec.env: the element's cull bound — a tight ball round the contents (CullBounds; F_SELF: the sphere itself;
                 // F_ENV2: the reference's envelope must be met as well) or the reference's envelope
                 bool ok = !( fl & ( F_ENV | F_SELF ) ) || envelope_hits_before( rec.env, ray, hor );
-                if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits_before( sv.env[ c ], ray, hor );   // the ball sticks out of the envelope
+                if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits( sv.env[ c ], ray );      // the ball sticks out of the envelope: the envelope is a gate only
                 if( ok )
                 {
                     if( node_kind( lk ) == K_COMPOUND )
@@ -716,7 +716,7 @@ template <typename R, int MARCH, bool SH, bool STRICT> __device__ __forceinline_
     const R hor = t_far + R( 2 ) * sv.eps;
     const RayBall<R> rb( rec.env, ray, sv.eps );
     bool ok = !( fl & ( F_ENV | F_SELF ) ) || rb.before( hor );
-    if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits_before( sv.env[ c ], ray, hor );
+    if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits( sv.env[ c ], ray );
     const bool comp = node_kind( lk ) == K_COMPOUND, self = ( fl & F_SELF ) != 0;
     int next = ( ok && comp ) ? lk.y : lk.z;
     if( ok && self && rb.template hit_within<STRICT>( t_far ) ) next = WALK_FOUND;
@@ -764,7 +764,7 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ int walk_st
     const R hor = ( want_trans ? r_min( r_min( s.min_a + sv.eps, s.el_a ), far0 ) : far0 ) + R( 2 ) * sv.eps;
     const RayBall<R> rb( rec.env, ray, sv.eps );
     bool ok = !( fl & ( F_ENV | F_SELF ) ) || rb.before( hor );
-    if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits_before( sv.env[ c ], ray, hor );
+    if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits( sv.env[ c ], ray );
     const bool comp = node_kind( lk ) == K_COMPOUND;
     // a sphere held in its record whose hit needs no normal now: a probe, or inside a nested element
     const bool leaf = ( fl & ( F_SELF | F_ROUGH ) ) == F_SELF && ( !want_trans || s.nested );

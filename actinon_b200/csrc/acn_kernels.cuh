@@ -703,6 +703,9 @@ __device__ __forceinline__ int launch_chunk( unsigned long long groups )
 #ifndef ACN_MINB_DIRECT_G
 #define ACN_MINB_DIRECT_G 8
 #endif
+#ifndef ACN_MINB_DIRECT_R
+#define ACN_MINB_DIRECT_R 6     // refill body: 8 x 64 registers kept the walk's ray in local memory (19 LDL/STL per step); 6 x 80: 3, and no slower
+#endif
 
 enum { SCHED_PRIMARY = 0, SCHED_WAVE = 1 };
 
@@ -1331,7 +1334,7 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_dire
     }
     warp_count( &w.sc->stats[ ST_SHADOW ], ( unsigned long long )n_shadow, lane );
 }
-template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : ACN_MINB_DIRECT_G )
+template <typename R, int MARCH, bool SH> __global__ void __launch_bounds__( ACN_BLOCK, sizeof( R ) == 8 ? 4 : SH ? ACN_MINB_DIRECT : MARCH == 2 ? ACN_MINB_DIRECT_R : ACN_MINB_DIRECT_G )
 k_direct( Wave<R> w, TaskBuf<R> in, const u64* __restrict__ dl_cum, const unsigned int* __restrict__ dl_slot,
           const unsigned int* __restrict__ dl_dir )
 {

@@ -57,6 +57,10 @@ struct SpecGen
 
     int  kind( int n ) const { return fs->nodes[ n ].kind; }
     bool has_env( int n ) const { return fs->nodes[ n ].has_envelope != 0; }
+    // nodes whose contents are known to stick out of their envelope (CullBounds, acn_tracer.cuh): a hit in front of the envelope
+    // is possible, so the envelope is only a gate (objects.c:264) and must not be culled against the horizon
+    const std::vector<char>* env_gate_only = nullptr;
+    const char* env_test( int n ) const { return env_gate_only && ( *env_gate_only )[ n ] ? "envelope_hits( sv.env[ %d ], ray )" : "envelope_hits_before( sv.env[ %d ], ray, hor )"; }
     bool rough( int n ) const { return fs->nodes[ n ].surface_roughness > 0 && kind( n ) != ACN_KIND_COMPOUND; }
     static bool simple_leaf( int k ) { return k == ACN_KIND_PLANE || k == ACN_KIND_SPHERE || k == ACN_KIND_SQUAROID; }
     static int  max_crossings( int k ) { return k == ACN_KIND_PLANE ? 1 : 2; }
@@ -246,7 +250,7 @@ struct SpecGen
         const int k = kind( e );
         p( "%s{   // node %d\n", ind, e );
         p( "%s    const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, %s ), far0 ) : r_min( min_a, far0 ) ) + slack;\n", ind, nested ? "el_a" : "inf" );
-        if( has_env( e ) ) p( "%s    if( !found && envelope_hits_before( sv.env[ %d ], ray, hor ) )\n", ind, e );
+        if( has_env( e ) ) { p( "%s    if( !found && ", ind ); p( env_test( e ), e ); p( " )\n" ); }
         else               p( "%s    if( !found )\n", ind );
         p( "%s    {\n%s        V3<R> n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); R a;\n", ind, ind );
         bool roughen_here = rough( e );
@@ -272,7 +276,7 @@ struct SpecGen
             {
                 p( "%s{   // compound %d\n", ind, e );
                 p( "%s    const R hor = ( want_trans ? r_min( r_min( min_a + sv.eps, el_a ), far0 ) : r_min( min_a, far0 ) ) + slack;\n", ind );
-                if( has_env( e ) ) p( "%s    if( !found && envelope_hits_before( sv.env[ %d ], ray, hor ) )\n", ind, e );
+                if( has_env( e ) ) { p( "%s    if( !found && ", ind ); p( env_test( e ), e ); p( " )\n" ); }
                 else               p( "%s    if( !found )\n", ind );
                 p( "%s    {\n", ind );
                 std::string in2 = std::string( ind ) + "        ";
@@ -299,7 +303,7 @@ struct SpecGen
             {
                 p( "            {   // nested compound %d: one element of the root, its hit = the closest hit of its contents\n", e );
                 p( "                const R hor = ( want_trans ? r_min( min_a + sv.eps, far0 ) : r_min( min_a, far0 ) ) + slack;\n" );
-                if( has_env( e ) ) p( "                if( !found && envelope_hits_before( sv.env[ %d ], ray, hor ) )\n", e );
+                if( has_env( e ) ) { p( "                if( !found && " ); p( env_test( e ), e ); p( " )\n" ); }
                 else               p( "                if( !found )\n" );
                 p( "                {\n                    R el_a = inf; V3<R> el_n = v3<R>( R( 0 ), R( 0 ), R( 0 ) ); int el_obj = -1;\n" );
                 emit_nested( e, "                    " );

@@ -186,6 +186,103 @@ static int csg_depth( const acn_flat_scene* fs, int n, int guard )
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cull bounds of the traversal records.  The reference tests an element's envelope before the element
+// (objects.c:261-266, compound.c:215-244): a hit needs "ray meets the envelope AND ray meets the contents".
+// The envelopes of the shipped scenes are Monte-Carlo estimates (objects.c:312-363): loose where they matter (a
+// cluster of eight spheres of many_spheres.acn: radius 0.092 where 0.068 encloses it) and off-centre, so that they
+// do not even contain their contents everywhere.  With B a ball that contains the contents, "ray meets B AND ray
+// meets the envelope" is necessary for a hit; when B lies inside the envelope the first implies the second.  The
+// traversal records therefore carry B, the tightest ball the host can construct (plus a safety margin for FP32):
+//   sphere       B = the sphere itself: the record holds the shape (F_SELF), one test instead of two, no
+//                second load of the geometry table
+//   compound     B = enclosing ball of the children's balls (Badoiu-Clarkson iteration), also for compounds the
+//                script gave no envelope at all
+//   anything else (planes, quadrics, CSG, distance fields) keeps the reference's envelope.
+// Where B does not fit inside the element's envelope the record asks for the envelope test as well (F_ENV2, read
+// from env[]): the rays that pass B — about half of those that pass the envelope — pay a second test.  That second
+// test is a plain gate (objects.c:264), NOT culled against the horizon: contents that stick out of their envelope can be
+// hit in front of it.  (Culling an envelope against the best hit so far assumes that the contents lie inside it.  The
+// walk relies on that for the elements whose extent the host cannot compute — composite objects, quadrics — as the
+// scripts of the reference do when they set bounding envelopes by hand; for spheres and compounds of spheres it is
+// checked here.)  Same rays accepted and rejected as by the reference's order of tests; the node tables (env[], link[])
+// are untouched: they serve the CSG programs, the light tests and the FP64 march of the validation mode.
+// ---------------------------------------------------------------------------------------------
+struct CullBounds
+{
+    enum { KEEP = 0, TIGHT = 1, SELF = 2 };
+    struct Rec { int mode = KEEP; bool env_too = false; double c[ 3 ] = { 0, 0, 0 }, r = 0; };
+    struct Ball { bool ok = false; double c[ 3 ] = { 0, 0, 0 }, r = 0; };
+    std::vector<Rec> rec;
+    std::vector<Ball> ball;
+    int n_tight = 0, n_self = 0, n_both = 0;
+
+    static double dist( const double* a, const double* b ) { return sqrt( ( a[ 0 ] - b[ 0 ] ) * ( a[ 0 ] - b[ 0 ] ) + ( a[ 1 ] - b[ 1 ] ) * ( a[ 1 ] - b[ 1 ] ) + ( a[ 2 ] - b[ 2 ] ) * ( a[ 2 ] - b[ 2 ] ) ); }
+    static double margin( const double* c, double r ) { return 2E-5 * fmax( 1.0, fmax( fmax( fabs( c[ 0 ] ), fabs( c[ 1 ] ) ), fabs( c[ 2 ] ) ) + r ); }
+
+    // enclosing ball of balls
+    static Ball enclose( const std::vector<Ball>& in )
+    {
+        Ball b; b.ok = true;
+        for( const Ball& k : in ) for( int j = 0; j < 3; j++ ) b.c[ j ] += k.c[ j ] / ( double )in.size();
+        auto radius = [ & ]( const double* c, int* far ) { double r = 0; for( size_t i = 0; i < in.size(); i++ ) { const double d = dist( c, in[ i ].c ) + in[ i ].r; if( d > r ) { r = d; if( far ) *far = ( int )i; } } return r; };
+        double c[ 3 ] = { b.c[ 0 ], b.c[ 1 ], b.c[ 2 ] };
+        int far = 0;
+        b.r = radius( c, &far );
+        for( int it = 1; it <= 256 && in.size() > 1; it++ )
+        {   // step towards the farthest point of the farthest ball
+            const Ball& f = in[ far ];
+            const double d = dist( c, f.c );
+            double fp[ 3 ];
+            for( int j = 0; j < 3; j++ ) fp[ j ] = f.c[ j ] + ( d > 0 ? ( f.c[ j ] - c[ j ] ) / d * f.r : 0.0 );
+            for( int j = 0; j < 3; j++ ) c[ j ] += ( fp[ j ] - c[ j ] ) / ( double )( it + 1 );
+            const double r = radius( c, &far );
+            if( r < b.r ) { b.r = r; for( int j = 0; j < 3; j++ ) b.c[ j ] = c[ j ]; }
+        }
+        return b;
+    }
+
+    CullBounds( const acn_flat_scene* fs, bool enable )
+    {
+        const int n = fs->n_nodes;
+        rec.resize( n ); ball.resize( n );
+        if( !enable ) return;
+        // children have larger or smaller indices than their compound depending on the flattener: resolve recursively
+        std::vector<char> done( n, 0 );
+        std::function<void( int )> solve = [ & ]( int i )
+        {
+            if( done[ i ] ) return;
+            done[ i ] = 1;
+            const acn_flat_node& nd = fs->nodes[ i ];
+            Ball b;
+            if( nd.kind == ACN_KIND_SPHERE && nd.tail[ 0 ] > 0 ) { b.ok = true; for( int j = 0; j < 3; j++ ) b.c[ j ] = nd.pos[ j ]; b.r = nd.tail[ 0 ]; }
+            else if( nd.kind == ACN_KIND_COMPOUND && nd.child1 > 0 )
+            {
+                std::vector<Ball> ch;
+                bool all = true;
+                for( int k = 0; k < nd.child1; k++ )
+                {
+                    const int c = fs->children[ nd.child0 + k ];
+                    solve( c );
+                    if( !ball[ c ].ok ) { all = false; break; }
+                    ch.push_back( ball[ c ] );
+                }
+                if( all ) b = enclose( ch );
+            }
+            ball[ i ] = b;
+            if( !b.ok ) return;
+            const double m = margin( b.c, b.r );
+            Rec& r = rec[ i ];
+            r.env_too = nd.has_envelope && !( dist( b.c, nd.env_pos ) + b.r + 2 * m <= nd.env_radius );
+            if( r.env_too ) n_both++;
+            for( int j = 0; j < 3; j++ ) r.c[ j ] = b.c[ j ];
+            if( nd.kind == ACN_KIND_SPHERE ) { r.mode = SELF; r.r = b.r; n_self++; }
+            else                             { r.mode = TIGHT; r.r = b.r + m; n_tight++; }
+        };
+        for( int i = 0; i < n; i++ ) solve( i );
+    }
+};
+
 static int compound_depth( const acn_flat_scene* fs, int n, int guard )
 {
     if( guard > 64 ) return 64;
@@ -655,100 +752,6 @@ template <typename R> static bool stages_table( const acn_flat_scene* fs, size_t
     return sizeof( R ) == 4 && staged_table_bytes<R>( fs, n_prog ) <= 96 * 1024 && !getenv( "ACN_NO_STAGING" );
 }
 
-// ---------------------------------------------------------------------------------------------
-// Cull bounds of the traversal records.  The reference tests an element's envelope before the element
-// (objects.c:261-266, compound.c:215-244): a hit needs "ray meets the envelope AND ray meets the contents".
-// The envelopes of the shipped scenes are Monte-Carlo estimates (objects.c:312-363): loose where they matter (a
-// cluster of eight spheres of many_spheres.acn: radius 0.092 where 0.068 encloses it) and off-centre, so that they
-// do not even contain their contents everywhere.  With B a ball that contains the contents, "ray meets B AND ray
-// meets the envelope" is necessary for a hit; when B lies inside the envelope the first implies the second.  The
-// traversal records therefore carry B, the tightest ball the host can construct (plus a safety margin for FP32):
-//   sphere       B = the sphere itself: the record holds the shape (F_SELF), one test instead of two, no
-//                second load of the geometry table
-//   compound     B = enclosing ball of the children's balls (Badoiu-Clarkson iteration), also for compounds the
-//                script gave no envelope at all
-//   anything else (planes, quadrics, CSG, distance fields) keeps the reference's envelope.
-// Where B does not fit inside the element's envelope the record asks for the envelope test as well (F_ENV2, read
-// from env[]): the rays that pass B — about half of those that pass the envelope — pay a second test.  Same rays
-// accepted and rejected as by the reference's order of tests; the node tables (env[], link[]) are untouched: they
-// serve the CSG programs, the light tests and the FP64 march of the validation mode.
-// ---------------------------------------------------------------------------------------------
-struct CullBounds
-{
-    enum { KEEP = 0, TIGHT = 1, SELF = 2 };
-    struct Rec { int mode = KEEP; bool env_too = false; double c[ 3 ] = { 0, 0, 0 }, r = 0; };
-    struct Ball { bool ok = false; double c[ 3 ] = { 0, 0, 0 }, r = 0; };
-    std::vector<Rec> rec;
-    std::vector<Ball> ball;
-    int n_tight = 0, n_self = 0, n_both = 0;
-
-    static double dist( const double* a, const double* b ) { return sqrt( ( a[ 0 ] - b[ 0 ] ) * ( a[ 0 ] - b[ 0 ] ) + ( a[ 1 ] - b[ 1 ] ) * ( a[ 1 ] - b[ 1 ] ) + ( a[ 2 ] - b[ 2 ] ) * ( a[ 2 ] - b[ 2 ] ) ); }
-    static double margin( const double* c, double r ) { return 2E-5 * fmax( 1.0, fmax( fmax( fabs( c[ 0 ] ), fabs( c[ 1 ] ) ), fabs( c[ 2 ] ) ) + r ); }
-
-    // enclosing ball of balls
-    static Ball enclose( const std::vector<Ball>& in )
-    {
-        Ball b; b.ok = true;
-        for( const Ball& k : in ) for( int j = 0; j < 3; j++ ) b.c[ j ] += k.c[ j ] / ( double )in.size();
-        auto radius = [ & ]( const double* c, int* far ) { double r = 0; for( size_t i = 0; i < in.size(); i++ ) { const double d = dist( c, in[ i ].c ) + in[ i ].r; if( d > r ) { r = d; if( far ) *far = ( int )i; } } return r; };
-        double c[ 3 ] = { b.c[ 0 ], b.c[ 1 ], b.c[ 2 ] };
-        int far = 0;
-        b.r = radius( c, &far );
-        for( int it = 1; it <= 256 && in.size() > 1; it++ )
-        {   // step towards the farthest point of the farthest ball
-            const Ball& f = in[ far ];
-            const double d = dist( c, f.c );
-            double fp[ 3 ];
-            for( int j = 0; j < 3; j++ ) fp[ j ] = f.c[ j ] + ( d > 0 ? ( f.c[ j ] - c[ j ] ) / d * f.r : 0.0 );
-            for( int j = 0; j < 3; j++ ) c[ j ] += ( fp[ j ] - c[ j ] ) / ( double )( it + 1 );
-            const double r = radius( c, &far );
-            if( r < b.r ) { b.r = r; for( int j = 0; j < 3; j++ ) b.c[ j ] = c[ j ]; }
-        }
-        return b;
-    }
-
-    CullBounds( const acn_flat_scene* fs, bool enable )
-    {
-        const int n = fs->n_nodes;
-        rec.resize( n ); ball.resize( n );
-        if( !enable ) return;
-        // children have larger or smaller indices than their compound depending on the flattener: resolve recursively
-        std::vector<char> done( n, 0 );
-        std::function<void( int )> solve = [ & ]( int i )
-        {
-            if( done[ i ] ) return;
-            done[ i ] = 1;
-            const acn_flat_node& nd = fs->nodes[ i ];
-            Ball b;
-            if( nd.kind == ACN_KIND_SPHERE && nd.tail[ 0 ] > 0 ) { b.ok = true; for( int j = 0; j < 3; j++ ) b.c[ j ] = nd.pos[ j ]; b.r = nd.tail[ 0 ]; }
-            else if( nd.kind == ACN_KIND_COMPOUND && nd.child1 > 0 )
-            {
-                std::vector<Ball> ch;
-                bool all = true;
-                for( int k = 0; k < nd.child1; k++ )
-                {
-                    const int c = fs->children[ nd.child0 + k ];
-                    solve( c );
-                    if( !ball[ c ].ok ) { all = false; break; }
-                    ch.push_back( ball[ c ] );
-                }
-                if( all ) b = enclose( ch );
-            }
-            ball[ i ] = b;
-            if( !b.ok ) return;
-            const double m = margin( b.c, b.r );
-            if( nd.kind != ACN_KIND_SPHERE && nd.has_envelope && b.r + m >= nd.env_radius ) return;      // no tighter than the envelope
-            Rec& r = rec[ i ];
-            r.env_too = nd.has_envelope && !( dist( b.c, nd.env_pos ) + b.r + 2 * m <= nd.env_radius );
-            if( r.env_too ) n_both++;
-            for( int j = 0; j < 3; j++ ) r.c[ j ] = b.c[ j ];
-            if( nd.kind == ACN_KIND_SPHERE ) { r.mode = SELF; r.r = b.r; n_self++; }
-            else                             { r.mode = TIGHT; r.r = b.r + m; n_tight++; }
-        };
-        for( int i = 0; i < n; i++ ) solve( i );
-    }
-};
-
 // the source SpecGen writes for a scene ("" when the scene does not qualify) and the instantiation it belongs to
 struct SpecPlan { std::string src; bool march = false, sh = false; };
 template <typename R> static SpecPlan plan_spec( const acn_flat_scene* fs, const CsgBuilder& cb )
@@ -757,6 +760,10 @@ template <typename R> static SpecPlan plan_spec( const acn_flat_scene* fs, const
     pl.march = needs_march( fs, cb );
     pl.sh = stages_table<R>( fs, cb.prog.size() );
     SpecGen g; g.fs = fs; g.prog = &cb.prog; g.prog_ref = &cb.prog_ref;
+    const CullBounds cbnd( fs, true );
+    std::vector<char> gate( ( size_t )fs->n_nodes, 0 );
+    for( int i = 0; i < fs->n_nodes; i++ ) gate[ i ] = cbnd.rec[ i ].env_too ? 1 : 0;
+    g.env_gate_only = &gate;
     if( g.generate() ) pl.src = g.out;
     return pl;
 }
