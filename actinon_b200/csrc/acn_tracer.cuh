@@ -111,6 +111,8 @@ template <typename R> struct Tracer : TracerBase
     TaskBuf<R> task_stack, task_new;
     HitBuf<R>  hit_q;
     u64* d_dl_cum = nullptr; unsigned int* d_dl_slot = nullptr; unsigned int* d_dl_dir = nullptr; unsigned int* d_pdir = nullptr;
+    uint64_t   budget_opt = 0;      // acn_options.wave_budget (0: follow the size of the call)
+    uint64_t   budget_floor = 0;    // raised when a call overflowed the queues of an automatic budget
     uint64_t   budget = 0, ray_min = 0, ray_cap = 0, task_stack_cap = 0, task_new_cap = 0, dl_dir_cap = 0, pdir_cap = 0, prim_chunk = 0;
     Sched*     d_sc = nullptr;
     Sched*     h_sc = nullptr;        // pinned
@@ -151,6 +153,7 @@ template <typename R> struct Tracer : TracerBase
     }
 
     int init( const acn_flat_scene* fs, const acn_options* opt );
+    int ensure_queues( uint64_t n );
     int render( const double* d_xy, uint64_t n, uint64_t index_base, float* d_rgb, cudaStream_t st,
                 const volatile int* cancel, acn_stats* stats ) override;
 
@@ -1160,30 +1163,8 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     }
 
 
-    // ---- queues.  budget = path children (and explicit rays) traced per wavefront iteration
-    budget = opt->wave_budget > 0 ? ( uint64_t )opt->wave_budget : ( 1ull << 23 );
-    if( budget < 64 ) budget = 64;
-    ray_min = budget / 4 < 65536 ? budget / 4 : 65536;      // smaller ray waves wait for company while path work is pending
-    ray_cap = budget * 24;
-    task_stack_cap = budget * 6;
-    task_new_cap = budget * 2 + 64;
-    dl_dir_cap = task_new_cap * 16 > ( 1ull << 20 ) ? task_new_cap * 16 : ( 1ull << 20 );
-    pdir_cap = budget * 32 > ( 1ull << 20 ) ? budget * 32 : ( 1ull << 20 );
-    if( pdir_cap > ( 1ull << 27 ) ) pdir_cap = 1ull << 27;
-    prim_chunk = budget;
-    {   // first-generation tasks must fit the task-stack directory: chunk * path_samples children
-        const uint64_t ps = prm.path_samples > 0 ? ( uint64_t )prm.path_samples : 1;
-        const uint64_t lim = pdir_cap * 32 / ps / 2;
-        if( prim_chunk > lim ) prim_chunk = lim > 32 ? lim : 32;
-    }
-    if( ( rc = alloc_rays( ray_stack, ray_cap ) ) ) return rc;
-    if( ( rc = alloc_tasks( task_stack, task_stack_cap ) ) ) return rc;
-    if( ( rc = alloc_tasks( task_new, task_new_cap ) ) ) return rc;
-    if( ( rc = alloc_hits( hit_q, task_new_cap ) ) ) return rc;
-    if( ( rc = dev_alloc( &d_dl_cum, task_new_cap ) ) ) return rc;
-    if( ( rc = dev_alloc( &d_dl_slot, task_new_cap ) ) ) return rc;
-    if( ( rc = dev_alloc( &d_dl_dir, dl_dir_cap ) ) ) return rc;
-    if( ( rc = dev_alloc( &d_pdir, pdir_cap ) ) ) return rc;
+    // ---- queues: sized at the first render, from the wave budget of that call (ensure_queues)
+    budget_opt = opt->wave_budget > 0 ? ( uint64_t )opt->wave_budget : 0;
     if( ( rc = dev_alloc( &d_sc, 1 ) ) ) return rc;
     ACN_CUDA( cudaMallocHost( ( void** )&h_sc, sizeof( Sched ) ) );
 
@@ -1207,6 +1188,57 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
 
 static inline unsigned grid_for( uint64_t n, unsigned block ) { return ( unsigned )( ( n + block - 1 ) / block ); }
 
+// The wavefront queues.  budget = path children (and explicit rays) traced per wavefront iteration; everything an iteration
+// can spawn must fit: 24 ray slots, 6 + 2 task slots, 2 hits per unit of budget, ~2.9 KB in all — 24 GB at the default
+// ceiling of 2^23, which is what a 400x400 pass of wine_glass wants and absurd for a 64x48 test render.
+// Without an explicit acn_options.wave_budget the budget follows the call: 64 x the samples of the call rounded up to a power
+// of two, between 2^16 (190 MB) and 2^23.  Queues only grow; samples do not depend on the budget (fixed-point sums).
+template <typename R> int Tracer<R>::ensure_queues( uint64_t n )
+{
+    uint64_t want = budget_opt;
+    if( want == 0 )
+    {
+        want = 1ull << 16;
+        while( want < ( 1ull << 23 ) && want < n * 64 ) want <<= 1;
+        if( want < budget_floor ) want = budget_floor;
+    }
+    if( want < 64 ) want = 64;
+    if( want <= budget ) return ACN_OK;
+    int rc;
+    ACN_CUDA( cudaDeviceSynchronize() );
+    free_rays( ray_stack ); free_tasks( task_stack ); free_tasks( task_new ); free_hits( hit_q );
+    cudaFree( d_dl_cum ); cudaFree( d_dl_slot ); cudaFree( d_dl_dir ); cudaFree( d_pdir );
+    ray_stack = RayBuf<R>(); task_stack = TaskBuf<R>(); task_new = TaskBuf<R>(); hit_q = HitBuf<R>();
+    d_dl_cum = nullptr; d_dl_slot = nullptr; d_dl_dir = nullptr; d_pdir = nullptr;
+    budget = 0;
+    const uint64_t bd = want;
+    ray_min = bd / 4 < 65536 ? bd / 4 : 65536;      // smaller ray waves wait for company while path work is pending
+    ray_cap = bd * 24;
+    task_stack_cap = bd * 6;
+    task_new_cap = bd * 2 + 64;
+    dl_dir_cap = task_new_cap * 16 > ( 1ull << 20 ) ? task_new_cap * 16 : ( 1ull << 20 );
+    pdir_cap = bd * 32 > ( 1ull << 20 ) ? bd * 32 : ( 1ull << 20 );
+    if( pdir_cap > ( 1ull << 27 ) ) pdir_cap = 1ull << 27;
+    prim_chunk = bd;
+    {   // first-generation tasks must fit the task-stack directory: chunk * path_samples children
+        const uint64_t ps = prm.path_samples > 0 ? ( uint64_t )prm.path_samples : 1;
+        const uint64_t lim = pdir_cap * 32 / ps / 2;
+        if( prim_chunk > lim ) prim_chunk = lim > 32 ? lim : 32;
+    }
+    if( ( rc = alloc_rays( ray_stack, ray_cap ) ) ) return rc;
+    if( ( rc = alloc_tasks( task_stack, task_stack_cap ) ) ) return rc;
+    if( ( rc = alloc_tasks( task_new, task_new_cap ) ) ) return rc;
+    if( ( rc = alloc_hits( hit_q, task_new_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_dl_cum, task_new_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_dl_slot, task_new_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_dl_dir, dl_dir_cap ) ) ) return rc;
+    if( ( rc = dev_alloc( &d_pdir, pdir_cap ) ) ) return rc;
+    budget = bd;
+    if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: wavefront queues for a budget of %llu: %.2f GB\n", ( unsigned long long )bd,
+                                          ( double )( ray_cap * 4 * sizeof( R4<R> ) + ( task_stack_cap + task_new_cap ) * ( 4 * sizeof( R4<R> ) + 40 ) + task_new_cap * ( 4 * sizeof( R4<R> ) + 24 + 12 ) + ( dl_dir_cap + pdir_cap ) * 4 ) / 1e9 );
+    return ACN_OK;
+}
+
 template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uint64_t index_base, float* d_rgb, cudaStream_t st,
                                              const volatile int* cancel, acn_stats* stats )
 {
@@ -1214,6 +1246,7 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
     if( stats ) memset( stats, 0, sizeof( *stats ) );
     if( n == 0 ) return ACN_OK;
     if( n > 0x7FFFFFFFull ) { set_error( "at most 2^31-1 samples per call" ); return ACN_ERR_INVALID_ARG; }
+    { const int rq = ensure_queues( n ); if( rq ) return rq; }
     if( accum_cap < n )
     {
         cudaFree( d_accum ); d_accum = nullptr; accum_cap = 0;
@@ -1343,6 +1376,12 @@ template <typename R> int Tracer<R>::render( const double* d_xy, uint64_t n, uin
         stats->rays_path = ss[ ST_PATH ]; stats->rays_shadow = ss[ ST_SHADOW ];
         stats->rays_light = ss[ ST_LIGHT ]; stats->diffuse_hits = ss[ ST_DIFFUSE ];
         stats->kernel_launches = launches; stats->waves = h_sc->waves; stats->device_ms = ms;
+    }
+    if( result == ACN_ERR_OUT_OF_MEMORY && budget_opt == 0 && budget < ( 1ull << 23 ) && !kp.on )
+    {   // an automatic budget proved too small for this scene's fan-out: twice the queues, once more from the start
+        budget_floor = budget * 2;
+        if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: queue overflow at a budget of %llu, retrying with %llu\n", ( unsigned long long )budget, ( unsigned long long )budget_floor );
+        return render( d_xy, n, index_base, d_rgb, st, cancel, stats );
     }
     if( kp.on )
     {

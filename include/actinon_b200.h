@@ -170,7 +170,10 @@ typedef struct acn_options
     int32_t precision;        /* ACN_PRECISION_*                                                    */
     double  eps;              /* shell thickness (f3_eps, vectors.h:33). <=0: automatic — 1e-6 in
                                  f64, scene-scale aware in f32                      */
-    int64_t wave_budget;      /* max rays in flight per wavefront iteration; <=0: default           */
+    int64_t wave_budget;      /* path children / explicit rays traced per wavefront iteration; the queues take
+                                 ~2.9 KB of device memory per unit.  <=0: follows the call — 64 x its samples,
+                                 rounded up to a power of two, between 2^16 (190 MB) and 2^23 (24 GB); the queues
+                                 only grow.  Samples do not depend on it (fixed-point sums)                */
     int32_t device;           /* CUDA device ordinal; <0: current device                            */
     int32_t csg_mode;         /* ACN_CSG_*: how composite objects are intersected                   */
     int32_t specialize;       /* ACN_SPECIALIZE_*: scene-specialised kernels (same results, faster)  */

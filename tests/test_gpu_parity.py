@@ -68,9 +68,12 @@ def test_f64_validation_mode_matches_oracle_everywhere(orc, name):
 
 
 @pytest.mark.parametrize("name,max_frac_1e3,max_frac_1e2", [
-    ("primitives_c1", 0.010, 0.0015), ("glass_ball", 0.015, 0.0030), ("csg_zoo", 0.020, 0.0060),
-    ("primitives_path", 0.015, 0.0040), ("glass_ball_path", 0.030, 0.0150), ("csg_zoo_path", 0.035, 0.0200),
-    ("textures", 0.020, 0.0100),               # + pixels on the edges between chess squares (llrint of an f32 coordinate)
+    # limits = twice what is measured (round 2, B200; profiles/r02_parity.json, profiles/r02_c1_probe.txt): C1 0.031 % / 0.021 %,
+    # glass_ball 0.20 / 0.02, csg_zoo 0.26 / 0.13, primitives_path 0.07 / 0.06, glass_ball_path 0.42 / 0.33, csg_zoo_path
+    # 0.49 / 0.26, textures 0.06 / 0.01 (round 1 allowed 1 - 3.5 % beyond 1e-3)
+    ("primitives_c1", 0.0007, 0.0005), ("glass_ball", 0.0040, 0.0006), ("csg_zoo", 0.0052, 0.0030),
+    ("primitives_path", 0.0016, 0.0013), ("glass_ball_path", 0.0085, 0.0070), ("csg_zoo_path", 0.0100, 0.0060),
+    ("textures", 0.0015, 0.0005),              # + pixels on the edges between chess squares (llrint of an f32 coordinate)
 ])
 def test_f32_product_mode_vs_oracle(orc, name, max_frac_1e3, max_frac_1e2):
     flat, xy = full_pass(SCENES[name]())
