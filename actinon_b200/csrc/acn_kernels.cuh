@@ -1445,9 +1445,11 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_path
         if( has )
         {
             AccV<R> ms = miss != R( 0 ) ? acc_of( mul( prm.background, tpm ) * miss ) : acc_zero<R>();
-            ms = seg_sum_acc( ms, key, lane );
-            const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
-            if( key >= 0 && ( lane == 0 || kprev != key ) && acc_any( ms ) ) add_sample_acc( w, sample, ms );
+            {
+                ms = seg_sum_acc( ms, key, lane );
+                const int kprev = __shfl_up_sync( ACN_FULL, key, 1 );
+                if( key >= 0 && ( lane == 0 || kprev != key ) && acc_any( ms ) ) add_sample_acc( w, sample, ms );
+            }
         }
     }
     warp_count( &w.sc->stats[ ST_PATH ], n_path, lane );
