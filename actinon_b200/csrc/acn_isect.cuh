@@ -530,6 +530,25 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ R elem_hit(
 // ---------------------------------------------------------------------------------------------
 enum { Q_LIGHT = 1, Q_MATTER = 2, Q_TRANS = 4 };
 
+// one traversal record.  From global memory (FP32: 32 bytes, 32-byte aligned) it is ONE 256-bit load (sm_100: LDG.E.256)
+// instead of two 128-bit ones: the walk gathers a record per lane and step, and the L1 data pipe is what bounds it.
+template <typename R, bool SH> __device__ __forceinline__ CRec<R> load_rec( const SceneView<R, SH>& sv, int i )
+{
+#if !defined(ACN_NO_LD256)
+    if constexpr( !SH && sizeof( R ) == 4 )
+    {
+        CRec<R> r;
+        const CRec<R>* p = sv.crec.p + i;
+        asm( "ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+             : "=f"( r.env.x ), "=f"( r.env.y ), "=f"( r.env.z ), "=f"( r.env.w ), "=r"( r.link.x ), "=r"( r.link.y ), "=r"( r.link.z ), "=r"( r.link.w )
+             : "l"( p ) );
+        return r;
+    }
+    else
+#endif
+    return sv.crec[ i ];
+}
+
 template <typename R, bool SH> __device__ __forceinline__ void trans_commit( const SceneView<R, SH>& sv, const Ray<R>& ray, R a, V3<R> nor, int obj, R* min_a, Trans<R>* tl )
 {
     if( !( a < Num<R>::inf() ) ) return;
@@ -597,7 +616,7 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ R scene_que
             if( more )
 #endif
             {
-                const CRec<R> rec = sv.crec[ cur ];
+                const CRec<R> rec = load_rec( sv, cur );
                 const I4 lk = rec.link;
                 const int c = lk.w, fl = node_flags( lk );
                 cur = lk.z;
@@ -710,7 +729,7 @@ template <typename R> struct RayBall
 template <typename R, int MARCH, bool SH, bool STRICT> __device__ __forceinline__ int walk_any_step( const SceneView<R, SH>& sv, const Ray<R>& ray, const R t_far, const int cur,
                                                                                                HitCtx ctx, const CsgMem<R>& cm )
 {
-    const CRec<R> rec = sv.crec[ cur ];
+    const CRec<R> rec = load_rec( sv, cur );
     const I4 lk = rec.link;
     const int c = lk.w, fl = node_flags( lk );
     const R hor = t_far + R( 2 ) * sv.eps;
@@ -757,7 +776,7 @@ template <typename R, bool SH> __device__ __forceinline__ void walk_commit_neste
 template <typename R, int MARCH, bool SH> __device__ __forceinline__ int walk_step( const SceneView<R, SH>& sv, const Ray<R>& ray, const R far0, const bool want_trans, const int cur,
                                                                                WalkT<R>& s, HitCtx ctx, const CsgMem<R>& cm )
 {
-    const CRec<R> rec = sv.crec[ cur ];
+    const CRec<R> rec = load_rec( sv, cur );
     const I4 lk = rec.link;
     const int c = lk.w, fl = node_flags( lk );
     if( want_trans && s.nested && ( fl & F_TOP ) ) walk_commit_nested( sv, ray, s );         // back among the root's elements
