@@ -80,6 +80,7 @@ template <typename R, bool SH = false> struct SceneView
     int matter_root;
     int rec_light;      // first traversal record of each root list (-1: empty)
     int rec_matter;
+    int rec_matter_oct[ 8 ];    // the matter list front to back for each octant of ray directions (acn_tracer.cuh); = rec_matter when not built
     int seed_mode;
 };
 

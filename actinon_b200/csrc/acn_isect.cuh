@@ -818,12 +818,17 @@ template <typename R, bool SH> __device__ __forceinline__ void walk_trans_finish
 }
 
 // may the walk of a root compound start at all?  (the root's own envelope, culled against the horizon)
-template <typename R, bool SH> __device__ __forceinline__ int walk_root( const SceneView<R, SH>& sv, const Ray<R>& ray, const bool light, const R far0 )
+// front: walk the copy of the matter records laid out front to back for the ray's octant (closest-hit searches; the shadow
+// rays gain nothing from it — measured — and keep to the one canonical copy, which they then have the L1 for)
+template <typename R, bool SH> __device__ __forceinline__ int walk_root( const SceneView<R, SH>& sv, const Ray<R>& ray, const bool light, const R far0, const bool front = true )
 {
     const int root = light ? sv.light_root : sv.matter_root;
     const I4 rl = sv.link[ root ];
     if( ( node_flags( rl ) & F_ENV ) && !envelope_hits_before( sv.env[ root ], ray, far0 + R( 2 ) * sv.eps ) ) return WALK_END;
-    return light ? sv.rec_light : sv.rec_matter;
+    if( light ) return sv.rec_light;
+    if( !front ) return sv.rec_matter;
+    // the copy of the matter records that is laid out front to back for this ray's octant
+    return sv.rec_matter_oct[ ( ray.d.x < R( 0 ) ? 1 : 0 ) | ( ray.d.y < R( 0 ) ? 2 : 0 ) | ( ray.d.z < R( 0 ) ? 4 : 0 ) ];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -375,6 +375,7 @@ template <typename R, bool SH> __device__ __forceinline__ SceneView<R, SH> stage
         sv.children.a = 0;                       // march / host only
         sv.eps = prm.sv.eps; sv.light_root = prm.sv.light_root; sv.matter_root = prm.sv.matter_root; sv.seed_mode = prm.sv.seed_mode;
         sv.rec_light = prm.sv.rec_light; sv.rec_matter = prm.sv.rec_matter;
+        for( int k = 0; k < 8; k++ ) sv.rec_matter_oct[ k ] = prm.sv.rec_matter_oct[ k ];
         return sv;
     }
 }
@@ -1318,7 +1319,7 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ void k_dire
                     s_con[ 0 ][ threadIdx.x ] = rg.cr[ q ]; s_con[ 1 ][ threadIdx.x ] = rg.cg[ q ]; s_con[ 2 ][ threadIdx.x ] = rg.cb[ q ]; s_smp[ threadIdx.x ] = rg.smp[ q ];
                     eps = ray_eps( prm, sv0.eps, ray.p );
                     SceneView<R, SH> sv = sv0; sv.eps = eps;
-                    cur = walk_root( sv, ray, false, tfar );
+                    cur = walk_root( sv, ray, false, tfar, false );
                     pend = cur == WALK_END;                  // no matter at all: settled at the next refill
                 }
                 head = ( head + n_take ) & ( ACN_RING - 1 ); ring_n -= n_take;

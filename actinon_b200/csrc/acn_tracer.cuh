@@ -104,6 +104,7 @@ template <typename R> struct Tracer : TracerBase
     R4<R>* d_env = nullptr; I4* d_link = nullptr; R4<R>* d_geo = nullptr; int* d_children = nullptr; CRec<R>* d_crec = nullptr;
     int* d_prog = nullptr; I4* d_prog_ref = nullptr; int* d_parent = nullptr; int n_prog = 0;
     size_t n_rec = 0; int rec_light = -1, rec_matter = -1;     // traversal records: count, first record of each root list (-1: empty)
+    int rec_matter_oct[ 8 ] = { -1, -1, -1, -1, -1, -1, -1, -1 };   // the matter list laid out front to back per octant of ray directions (= rec_matter when not built)
     DMat<R>* d_mats = nullptr; DLight<R>* d_lights = nullptr;
     u64* d_skipA = nullptr; u64* d_skipC = nullptr;
     // queues
@@ -850,14 +851,32 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         // next common record instead of running ahead through different objects.
         size_t next_free = 0;
         const int SAME_AS_SKIP = -4;
+        // FRONT TO BACK.  For a scene of planes, spheres and quadrics whose tables stay in global memory (many_spheres) the
+        // matter records exist eight more times, once per octant of ray directions, the elements of every nested list sorted
+        // along the octant's diagonal: a ray walks the copy of its octant and meets near elements first — a closest-hit search
+        // tightens its horizon early, an any-hit search ends early.  Inside a nested compound the order of the tests does not
+        // matter (plain minimum; two hits at EXACTLY the same distance, which only coincident geometry produces, may then
+        // name the other object); the order of the root's own elements, whose coincident surfaces are merged in sequence
+        // (compound.c:246-299), is never changed.
+        int oct = -1;
+        auto front_key = [ & ]( int c ) -> double
+        {
+            const acn_flat_node& nd = fs->nodes[ c ];
+            const double* p = cbnd.ball[ c ].ok ? cbnd.ball[ c ].c : nd.has_envelope ? nd.env_pos : nd.pos;
+            if( nd.kind == ACN_KIND_PLANE ) return -1e300;
+            return ( ( oct & 1 ) ? -p[ 0 ] : p[ 0 ] ) + ( ( oct & 2 ) ? -p[ 1 ] : p[ 1 ] ) + ( ( oct & 4 ) ? -p[ 2 ] : p[ 2 ] );
+        };
         std::function<int( int, bool, std::vector<int>& )> emit = [ & ]( int compound, bool top, std::vector<int>& open ) -> int
         {   // returns the first record of the list (-1: empty); `open` collects the records whose skip is the escape of this list
             const acn_flat_node& cn = fs->nodes[ compound ];
             int first = -1;
             std::vector<int> wait;              // records whose skip is the next record of this list
+            std::vector<int> kids( fs->children + cn.child0, fs->children + cn.child0 + cn.child1 );
+            if( oct >= 0 && !top )
+                std::stable_sort( kids.begin(), kids.end(), [ & ]( int a, int b ) { return front_key( a ) < front_key( b ); } );
             for( int i = 0; i < cn.child1; i++ )
             {
-                const int c = fs->children[ cn.child0 + i ];
+                const int c = kids[ i ];
                 const int idx = ( int )next_free++;
                 for( int r : wait ) crec[ r ].link.z = idx;
                 wait.clear();
@@ -894,9 +913,25 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             open.clear();
             rec_matter = emit( fs->matter_root, true, open );
             for( int r : open ) crec[ r ].link.z = -1;
+            for( int k = 0; k < 8; k++ ) rec_matter_oct[ k ] = rec_matter;
+            bool prims = true;
+            for( int i = 0; i < n && prims; i++ ) prims = fs->nodes[ i ].kind <= ACN_KIND_SQUAROID;
+            const size_t n_matter = next_free - ( size_t )( rec_matter >= 0 ? rec_matter : ( int )next_free );
+            if( prims && n_matter > 64 && n_matter * 8 * sizeof( CRec<R> ) <= ( ( size_t )32 << 20 ) && staged_table_bytes<R>( fs, 0 ) > 96 * 1024 && !getenv( "ACN_NO_OCTANT_ORDER" ) )
+            {
+                crec.resize( next_free + 8 * n_matter );
+                for( oct = 0; oct < 8; oct++ )
+                {
+                    open.clear();
+                    rec_matter_oct[ oct ] = emit( fs->matter_root, true, open );
+                    for( int r : open ) crec[ r ].link.z = -1;
+                }
+                oct = -1;
+                n_rec = next_free;
+            }
             for( size_t i = 0; i < next_free; i++ ) if( crec[ i ].link.y == SAME_AS_SKIP ) crec[ i ].link.y = crec[ i ].link.z;
         }
-        if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: %zu traversal records: %d compounds with a tight cull bound, %d spheres held in their record, %d of both test the reference's envelope as well\n", n_rec, cbnd.n_tight, cbnd.n_self, cbnd.n_both );
+        if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: %zu traversal records%s: %d compounds with a tight cull bound, %d spheres held in their record, %d of both test the reference's envelope as well\n", n_rec, rec_matter_oct[ 0 ] != rec_matter ? " (matter list eight more times, front to back per octant)" : "", cbnd.n_tight, cbnd.n_self, cbnd.n_both );
         if( ( rc = dev_alloc( &d_crec, crec.size() ) ) ) return rc;
         ACN_CUDA( cudaMemcpy( d_crec, crec.data(), crec.size() * sizeof( CRec<R> ), cudaMemcpyHostToDevice ) );
     }
@@ -984,7 +1019,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         }
         SceneView<double> hv; hv.env = henv.data(); hv.geo = hgeo.data(); hv.link = link.data(); hv.children = fs->children;
         hv.prog = nullptr; hv.prog_ref = nullptr; hv.parent = nullptr;
-        hv.eps = eps; hv.light_root = fs->light_root; hv.matter_root = fs->matter_root; hv.seed_mode = 0; hv.rec_light = hv.rec_matter = -1;
+        hv.eps = eps; hv.light_root = fs->light_root; hv.matter_root = fs->matter_root; hv.seed_mode = 0; hv.rec_light = hv.rec_matter = -1; for( int k = 0; k < 8; k++ ) hv.rec_matter_oct[ k ] = -1;
         for( int i = 0; i < lroot.child1; i++ )
         {
             const int ln = fs->children[ lroot.child0 + i ];
@@ -1030,6 +1065,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
     prm.sv.prog = d_prog; prm.sv.prog_ref = d_prog_ref; prm.sv.parent = d_parent; prm.n_prog = n_prog;
     prm.sv.eps = ( R )eps; prm.sv.light_root = fs->light_root; prm.sv.matter_root = fs->matter_root;
     prm.sv.rec_light = rec_light; prm.sv.rec_matter = rec_matter;
+    for( int k = 0; k < 8; k++ ) prm.sv.rec_matter_oct[ k ] = rec_matter_oct[ k ];
     prm.sv.seed_mode = opt->seed_mode;
     prm.mats = d_mats; prm.lights = d_lights; prm.n_lights = lroot.child1; prm.n_materials = fs->n_materials;
     prm.n_nodes = n; prm.n_children = ( int )n_rec;
