@@ -227,3 +227,23 @@ def test_analytic_bounding_envelopes_contain_the_monte_carlo_ones_extent():
     assert e.value.code == -5
     with pytest.raises(acn.AcnError):
         (~sc.create_sphere(1.0)).set_bounding_envelope()
+
+
+def test_big_csg_functions_get_packed_evaluation_programs():
+    """Functions of more than 12 variables (the lamp's shade, body, chain holder ...) are cut into truth tables over stretches of
+    their operator chains on the host (CsgBuilder::build_eval_program, checked there against the full program on 4096
+    assignments each); no device is needed for that, and none of them may be left to the word-by-word interpreter."""
+    import os, subprocess, sys, re
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import actinon_b200 as acn\n"
+            "flat = acn.scenes.load('hanging_lamp')\n"
+            "try:\n    acn.Tracer(flat, acn.Options())\nexcept acn.AcnError:\n    pass\n") % ROOT
+    env = dict(os.environ, ACN_DUMP_PROGRAMS="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300).stderr
+    progs = re.findall(r"acn: program of node \d+: (\d+) variables, (\d+) words, (\w+)", out)
+    assert len(progs) > 50
+    big = [(int(v), int(w), kind) for v, w, kind in progs if int(v) > 12]
+    assert big and all(kind == "packed" for _, _, kind in big)
+    words = [int(x) for x in re.findall(r"packed: (\d+) evaluation words", out)]
+    assert len(words) == len(big) and max(words) <= 24 and max(w for _, w, _ in big) >= 100
