@@ -704,7 +704,7 @@ __device__ __forceinline__ int launch_chunk( unsigned long long groups )
 #define ACN_MINB_PATH_G 6
 #endif
 #ifndef ACN_MINB_DIRECT_G
-#define ACN_MINB_DIRECT_G 8
+#define ACN_MINB_DIRECT_G 6     // lamps, after the packed evaluation programs: 8 blocks x 64 registers 1.81 s, 7: 1.67, 6 x 80: 1.64, 5: 1.76
 #endif
 #ifndef ACN_MINB_DIRECT_R
 #define ACN_MINB_DIRECT_R 6     // refill body: 8 x 64 registers kept the walk's ray in local memory (19 LDL/STL per step); 6 x 80: 3, and no slower
