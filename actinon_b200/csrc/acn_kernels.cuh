@@ -318,9 +318,6 @@ template <typename R> __device__ __forceinline__ AccV<R> seg_sum_acc( AccV<R> v,
 
 template <typename R> __device__ __forceinline__ void add_sample_acc( const Wave<R>& w, int sample, const AccV<R>& c )
 {
-#ifdef ACN_TEST_NO_ACC
-    if( sample >= 0 ) return;       // timing experiment only
-#endif
     typename Acc<R>::T* a = w.accum + 4ull * ( unsigned long long )sample;
     atomic_add_acc( a + 0, c.x );
     atomic_add_acc( a + 1, c.y );
