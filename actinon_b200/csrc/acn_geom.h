@@ -31,7 +31,8 @@ template <typename R> struct CRec { R4<R> env; I4 link; };
 enum
 {
     K_COMPOUND = 0, K_PLANE = 1, K_SPHERE = 2, K_SQUAROID = 3, K_DIST_SPHERE = 4, K_DIST_TORUS = 5,
-    K_PAIR_INSIDE = 6, K_PAIR_OUTSIDE = 7, K_NEG = 8, K_SCALE = 9
+    K_PAIR_INSIDE = 6, K_PAIR_OUTSIDE = 7, K_NEG = 8, K_SCALE = 9,
+    K_GROUP = 10        // traversal records only: a pure bound over a run of consecutive elements of a list (acn_tracer.cuh)
 };
 // flags of a node; the last three occur in traversal records only (acn_tracer.cuh: CullBounds, threaded records) —
 // F_SELF: the record's ball IS the sphere; F_ENV2: test env[node] as well; F_TOP: element of a root compound

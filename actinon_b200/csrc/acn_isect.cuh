@@ -633,10 +633,10 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ R scene_que
                 if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits( sv.env[ c ], ray );      // the ball sticks out of the envelope: the envelope is a gate only
                 if( ok )
                 {
-                    if( node_kind( lk ) == K_COMPOUND )
+                    if( node_kind( lk ) == K_COMPOUND || node_kind( lk ) == K_GROUP )
                     {
-                        cur = lk.y;                          // first record of its list (its skip record when the list is empty)
-                        if( fl & F_TOP ) nested = true;
+                        cur = lk.y;                          // first record of its list (its skip record when the list is empty); first member of a group
+                        if( ( fl & F_TOP ) && node_kind( lk ) == K_COMPOUND ) nested = true;
                     }
                     else
                     {
@@ -736,7 +736,7 @@ template <typename R, int MARCH, bool SH, bool STRICT> __device__ __forceinline_
     const RayBall<R> rb( rec.env, ray, sv.eps );
     bool ok = !( fl & ( F_ENV | F_SELF ) ) || rb.before( hor );
     if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits( sv.env[ c ], ray );
-    const bool comp = node_kind( lk ) == K_COMPOUND, self = ( fl & F_SELF ) != 0;
+    const bool comp = node_kind( lk ) == K_COMPOUND || node_kind( lk ) == K_GROUP, self = ( fl & F_SELF ) != 0;
     int next = ( ok && comp ) ? lk.y : lk.z;
     if( ok && self && rb.template hit_within<STRICT>( t_far ) ) next = WALK_FOUND;
     if( ok && !comp && !self )
@@ -784,11 +784,11 @@ template <typename R, int MARCH, bool SH> __device__ __forceinline__ int walk_st
     const RayBall<R> rb( rec.env, ray, sv.eps );
     bool ok = !( fl & ( F_ENV | F_SELF ) ) || rb.before( hor );
     if( ok && ( fl & F_ENV2 ) ) ok = envelope_hits( sv.env[ c ], ray );
-    const bool comp = node_kind( lk ) == K_COMPOUND;
+    const bool comp = node_kind( lk ) == K_COMPOUND || node_kind( lk ) == K_GROUP;
     // a sphere held in its record whose hit needs no normal now: a probe, or inside a nested element
     const bool leaf = ( fl & ( F_SELF | F_ROUGH ) ) == F_SELF && ( !want_trans || s.nested );
     int next = ( ok && comp ) ? lk.y : lk.z;
-    if( ok && comp && ( fl & F_TOP ) ) s.nested = true;
+    if( ok && ( fl & F_TOP ) && node_kind( lk ) == K_COMPOUND ) s.nested = true;
     const R a_leaf = rb.hit();
     if( ok && leaf )
     {

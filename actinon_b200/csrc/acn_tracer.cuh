@@ -858,6 +858,24 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
         // matter (plain minimum; two hits at EXACTLY the same distance, which only coincident geometry produces, may then
         // name the other object); the order of the root's own elements, whose coincident surfaces are merged in sequence
         // (compound.c:246-299), is never changed.
+        const bool grouping = staged_table_bytes<R>( fs, 0 ) > 96 * 1024 && !getenv( "ACN_NO_GROUP_RECORDS" );
+        int n_groups = 0;
+        auto alloc_rec = [ & ]() -> int
+        {
+            if( next_free >= crec.size() ) crec.resize( crec.size() * 2 + 16 );
+            return ( int )next_free++;
+        };
+        // the bound a record tests first (with the horizon): the tight ball of CullBounds or the reference's envelope
+        auto first_bound = [ & ]( int c, CullBounds::Ball* out ) -> bool
+        {
+            const acn_flat_node& nd = fs->nodes[ c ];
+            const CullBounds::Rec& b = cbnd.rec[ c ];
+            out->ok = true;
+            if( b.mode != CullBounds::KEEP ) { for( int j = 0; j < 3; j++ ) out->c[ j ] = b.c[ j ]; out->r = b.r; return true; }
+            if( nd.has_envelope ) { for( int j = 0; j < 3; j++ ) out->c[ j ] = nd.env_pos[ j ]; out->r = nd.env_radius; return true; }
+            out->ok = false;
+            return false;
+        };
         int oct = -1;
         auto front_key = [ & ]( int c ) -> double
         {
@@ -874,10 +892,53 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
             std::vector<int> kids( fs->children + cn.child0, fs->children + cn.child0 + cn.child1 );
             if( oct >= 0 && !top )
                 std::stable_sort( kids.begin(), kids.end(), [ & ]( int a, int b ) { return front_key( a ) < front_key( b ); } );
+            // GROUP records over runs of consecutive elements of a long list (a lamp holds 61 objects): a pure bound, the ball round
+            // the members' own first bounds.  A ray that misses it (or enters it beyond its horizon) would fail every member's test
+            // one by one; it skips them in one step.  The members and the order of their tests are unchanged.
+            std::vector<int> group_len( ( size_t )cn.child1, 0 );        // at the first member of a group: its length
+            std::vector<CullBounds::Ball> group_ball( ( size_t )cn.child1 );
+            if( grouping && cn.child1 > 12 )
+            {
+                for( int i = 0; i < cn.child1; )
+                {
+                    CullBounds::Ball b0;
+                    if( !first_bound( kids[ i ], &b0 ) ) { i++; continue; }
+                    std::vector<CullBounds::Ball> mem = { b0 };
+                    CullBounds::Ball gb = b0;
+                    double maxr = b0.r;
+                    int j = i + 1;
+                    for( ; j < cn.child1 && ( int )mem.size() < 8; j++ )
+                    {
+                        CullBounds::Ball bj;
+                        if( !first_bound( kids[ j ], &bj ) ) break;
+                        mem.push_back( bj );
+                        const CullBounds::Ball nb = CullBounds::enclose( mem );
+                        if( nb.r > 3.0 * fmax( maxr, bj.r ) ) { mem.pop_back(); break; }
+                        gb = nb; maxr = fmax( maxr, bj.r );
+                    }
+                    if( mem.size() >= 3 ) { group_len[ i ] = ( int )mem.size(); group_ball[ i ] = gb; n_groups++; i += ( int )mem.size(); }
+                    else i++;
+                }
+            }
+            int group_rec = -1, group_left = 0;                           // the open group: its record, members still to come
             for( int i = 0; i < cn.child1; i++ )
             {
                 const int c = kids[ i ];
-                const int idx = ( int )next_free++;
+                if( group_len[ i ] > 0 )
+                {
+                    const int g = alloc_rec();
+                    for( int r : wait ) crec[ r ].link.z = g;
+                    wait.clear();
+                    if( first < 0 ) first = g;
+                    const CullBounds::Ball& gb = group_ball[ i ];
+                    const double m = CullBounds::margin( gb.c, gb.r );
+                    CRec<R>& gr = crec[ g ];
+                    gr.env.x = ( R )gb.c[ 0 ]; gr.env.y = ( R )gb.c[ 1 ]; gr.env.z = ( R )gb.c[ 2 ]; gr.env.w = ( R )( gb.r + m );
+                    gr.link.x = K_GROUP | ( ( F_ENV | ( top ? F_TOP : 0 ) ) << 8 );
+                    gr.link.y = g + 1; gr.link.z = -1; gr.link.w = -1;
+                    group_rec = g; group_left = group_len[ i ];
+                }
+                const int idx = alloc_rec();
                 for( int r : wait ) crec[ r ].link.z = idx;
                 wait.clear();
                 if( first < 0 ) first = idx;
@@ -902,6 +963,7 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
                     crec[ idx ].link.y = f >= 0 ? f : SAME_AS_SKIP;
                     wait.insert( wait.end(), sub.begin(), sub.end() );
                 }
+                if( group_rec >= 0 && --group_left == 0 ) { wait.push_back( group_rec ); group_rec = -1; }     // the group's skip: whatever follows its last member
             }
             open.insert( open.end(), wait.begin(), wait.end() );
             return first;
@@ -930,8 +992,10 @@ template <typename R> int Tracer<R>::init( const acn_flat_scene* fs, const acn_o
                 n_rec = next_free;
             }
             for( size_t i = 0; i < next_free; i++ ) if( crec[ i ].link.y == SAME_AS_SKIP ) crec[ i ].link.y = crec[ i ].link.z;
+            crec.resize( next_free > 0 ? next_free : 1 );
+            n_rec = next_free;
         }
-        if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: %zu traversal records%s: %d compounds with a tight cull bound, %d spheres held in their record, %d of both test the reference's envelope as well\n", n_rec, rec_matter_oct[ 0 ] != rec_matter ? " (matter list eight more times, front to back per octant)" : "", cbnd.n_tight, cbnd.n_self, cbnd.n_both );
+        if( getenv( "ACN_VERBOSE" ) ) fprintf( stderr, "acn: %zu traversal records%s, %d group records: %d compounds with a tight cull bound, %d spheres held in their record, %d of both test the reference's envelope as well\n", n_rec, rec_matter_oct[ 0 ] != rec_matter ? " (matter list eight more times, front to back per octant)" : "", n_groups, cbnd.n_tight, cbnd.n_self, cbnd.n_both );
         if( ( rc = dev_alloc( &d_crec, crec.size() ) ) ) return rc;
         ACN_CUDA( cudaMemcpy( d_crec, crec.data(), crec.size() * sizeof( CRec<R> ), cudaMemcpyHostToDevice ) );
     }
