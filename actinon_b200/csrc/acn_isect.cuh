@@ -192,24 +192,28 @@ template <typename R, bool SH> __device__ __forceinline__ int csg_state( const S
         // were cut from (acn_tracer.cuh: build_eval_program)
         const int at = -2 - pr.z;
         const int end = at + 1 + sv.prog[ at ];
+        const unsigned int vlo = ( unsigned int )vars, vhi = ( unsigned int )( vars >> 32 );
+        // bits v .. v+31 of vars with 32-bit shifts (one funnel shift instead of a 64-bit shift by a register)
+        #define ACN_VARS_FROM( v ) ( ( v ) < 32 ? __funnelshift_r( vlo, vhi, ( v ) ) : ( vhi >> ( ( v ) - 32 ) ) )
         #pragma unroll 1
         for( int pc = at + 1; pc < end; pc++ )
         {
             const int ins = sv.prog[ pc ];
             const int op = ins & 15;
             if( op == E_TAB )
-            {
+            {   // one word: the table sits ( ins >> 14 ) words behind the program's length word
                 const int nv = ( ins >> 4 ) & 15, v0 = ( ins >> 8 ) & 63;
-                const unsigned int idx = ( unsigned int )( vars >> v0 ) & ( ( 1u << nv ) - 1u );
-                const int off = sv.prog[ ++pc ];
+                const unsigned int idx = ACN_VARS_FROM( v0 ) & ( ( 1u << nv ) - 1u );
+                const int off = at + ( int )( ( unsigned int )ins >> 14 );
                 stk = ( stk << 1 ) | ( ( ( unsigned int )sv.prog[ off + ( int )( idx >> 5 ) ] >> ( idx & 31u ) ) & 1u );
             }
-            else if( op == E_VAR )  stk = ( stk << 1 ) | ( unsigned int )( ( vars >> ( ins >> 4 ) ) & 1ull );
-            else if( op == E_CLIP ) stk &= ~1u | ( unsigned int )( ( vars >> ( ins >> 4 ) ) & 1ull );
+            else if( op == E_VAR )  stk = ( stk << 1 ) | ( ACN_VARS_FROM( ins >> 4 ) & 1u );
+            else if( op == E_CLIP ) stk &= ~1u | ( ACN_VARS_FROM( ins >> 4 ) & 1u );
             else if( op == E_NEG )  stk ^= 1u;
             else if( op == E_AND )  { const unsigned int t = stk & 1u; stk >>= 1; stk &= t | ~1u; }
             else                    { const unsigned int t = stk & 1u; stk >>= 1; stk |= t; }
         }
+        #undef ACN_VARS_FROM
         return ( int )( stk & 1u );
     }
     int v = 0;

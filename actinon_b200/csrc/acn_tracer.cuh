@@ -485,7 +485,7 @@ struct CsgBuilder
     // functions are chains — unions of butted pieces, a body minus twenty drill holes — and a chain of one operator can be
     // cut anywhere: every stretch of operands with <= CSG_TABLE_VARS variables in all becomes ONE truth table over its
     // (consecutive) variables, and what is left of the program is a handful of table lookups joined by the chain's operator.
-    // Words: E_TAB | n << 4 | v0 << 8, table offset;  E_VAR | v << 4;  E_CLIP | v << 4;  E_NEG;  E_AND;  E_OR.
+    // Words: E_TAB | n << 4 | v0 << 8 | ( table offset behind the program's length word ) << 14;  E_VAR | v << 4;  E_CLIP | v << 4;  E_NEG;  E_AND;  E_OR.
     struct TNode { int kind = 0, var = 0, v0 = 0, nv = 0; std::vector<int> ch; };     // kind: 0 variable, 1 not, 2 and, 3 or
     std::vector<TNode> tn;
     int tn_var( int v ) { TNode t; t.kind = 0; t.var = v; t.v0 = v; t.nv = 1; tn.push_back( t ); return ( int )tn.size() - 1; }
@@ -534,9 +534,8 @@ struct CsgBuilder
             for( int m : members ) { const int x = tn_eval( m, vars ); if( kind == 2 ) r &= x; else r |= x; }
             if( r ) tab[ a >> 5 ] |= ( int )( 1u << ( a & 31 ) );
         }
-        code.push_back( E_TAB | ( nv << 4 ) | ( v0 << 8 ) );
         tables.push_back( { code.size(), tab } );
-        code.push_back( 0 );                                    // table offset, patched when the tables are appended
+        code.push_back( E_TAB | ( nv << 4 ) | ( v0 << 8 ) );     // | table offset relative to the program's first word << 14, patched when the tables are appended
     }
     void pack( int n, std::vector<int>& code, std::vector<std::pair<size_t, std::vector<int>>>& tables )
     {
@@ -564,7 +563,13 @@ struct CsgBuilder
         const int at = ( int )prog.size();
         prog.push_back( ( int )code.size() );
         prog.insert( prog.end(), code.begin(), code.end() );
-        for( auto& tb : tables ) { prog[ ( size_t )at + 1 + tb.first ] = ( int )prog.size(); prog.insert( prog.end(), tb.second.begin(), tb.second.end() ); }
+        for( auto& tb : tables )
+        {
+            const size_t rel = prog.size() - ( size_t )at;
+            if( rel >= ( ( size_t )1 << 17 ) ) { prog.resize( at ); return -1; }      // 18 bits of the word, sign bit kept clear
+            prog[ ( size_t )at + 1 + tb.first ] |= ( int )( rel << 14 );
+            prog.insert( prog.end(), tb.second.begin(), tb.second.end() );
+        }
         // the packed function must be the function of the program: checked on random assignments (and on all of a small one)
         const int nv = tn[ root ].nv;
         unsigned long long x = 0x9E3779B97F4A7C15ull;
@@ -587,7 +592,7 @@ struct CsgBuilder
             {
                 const int nv = ( ins >> 4 ) & 15, v0 = ( ins >> 8 ) & 63;
                 const unsigned int idx = ( unsigned int )( ( vars >> v0 ) & ( ( 1ull << nv ) - 1ull ) );
-                const int off = prog[ ++pc ];
+                const int off = at + ( int )( ( unsigned int )ins >> 14 );
                 stk = ( stk << 1 ) | ( ( ( unsigned int )prog[ off + ( int )( idx >> 5 ) ] >> ( idx & 31u ) ) & 1u );
             }
             else if( op == E_VAR )  stk = ( stk << 1 ) | ( unsigned int )( ( vars >> ( ins >> 4 ) ) & 1ull );
